@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 tripolar-grid path.
+
+    python bench.py --gpus N --steps K --warmup W            (own arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU restatement of the reference)
+
+Metric (BASELINE.json): grid cells/s for coords+metrics (FP64); zipper halo-fill GB/s.
+A "step" is one full construction of the 20 padded arrays of the 1/12 degree TripolarGrid
+(4320x2160x100, halo 4) -- the configuration the north-star target is quoted on, which fits one
+GPU.  At N > 1 the same global grid is partitioned (x, y) = (Rx, Ry) and every rank builds its
+own window (no data-path collective; strong scaling of the named configuration).
+
+One JSON line is printed by rank 0.  See DESIGN.md section "Measurement" for every key.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(Nx=4320, Ny=2160, Nz=100, halo=4, south=-80.0, north_poles_latitude=55.0,
+                first_pole_longitude=70.0, radius=6371.0e3)
+CPU_SAMPLE = dict(Nx=1440, Ny=720)          # 1/9 of the workload's cells per CPU step
+METRIC = "grid cells/s for coords+metrics (FP64)"
+UNIT = "cells/s"
+
+# FP64 work of the metrics tile kernel per cell, from the committed ncu capture
+# (profiles/): filled in by DESIGN.md section "Kernels"; None until measured.
+FP64_INST_PER_CELL_TILE = None
+
+
+def partition_for(n):
+    return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(n, (n, 1))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle = port of the reference)
+def cpu_construct_rate(threads, steps, warmup):
+    """cells/s of the CPU restatement (glibc libm, literal per-point evaluation like the
+    reference's kernels, row-parallel over `threads`) on the bounded sample."""
+    from oracle import oracle as orc
+    o = orc.Oracle(libm=True)
+    o.set_threads(threads)
+    p = orc.make_params((CPU_SAMPLE["Nx"], CPU_SAMPLE["Ny"], 1), (WORKLOAD["halo"],) * 3,
+                        WORKLOAD["south"], WORKLOAD["north_poles_latitude"], WORKLOAD["first_pole_longitude"],
+                        WORKLOAD["radius"])
+    for _ in range(warmup):
+        o.build(p)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.build(p)
+    dt = (time.perf_counter() - t0) / steps
+    return CPU_SAMPLE["Nx"] * CPU_SAMPLE["Ny"] / dt, dt
+
+
+def cpu_zipper_rate(threads):
+    """GB/s of the oracle's zipper fill (1 thread: it is a scalar port) on a 1/4-degree field."""
+    import numpy as np
+    from oracle import oracle as orc
+    o = orc.Oracle()
+    Nx, Ny, Nz, H = 1440, 720, 75, 4
+    c = np.zeros((Nz + 2 * H, Ny + 2 * H, Nx + 2 * H))
+    o.zipper(c, Nx, Ny, Nz, H, H, H, 0, 0, 1)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        o.zipper(c, Nx, Ny, Nz, H, H, H, 0, 0, 1)
+    dt = (time.perf_counter() - t0) / reps
+    nbytes = 2 * H * Nx * Nz * 8 + Nx * Nz * 8
+    return nbytes / dt / 1e9
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t_all = time.perf_counter()
+    rate, dt = cpu_construct_rate(threads, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{CPU_SAMPLE['Nx']}x{CPU_SAMPLE['Ny']} grid (1/9 of the workload's cells) per step, "
+                                   "CPU restatement of reference v0.2.1 with glibc libm; Julia is not installed"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    Rx, Ry = partition_for(n)
+    return {"workload": f"TripolarGrid {WORKLOAD['Nx']}x{WORKLOAD['Ny']}x{WORKLOAD['Nz']} (1/12 degree), halo 4, FP64, "
+                        "full construction: 8 coordinate + 12 metric padded arrays",
+            "partition": f"(x,y)=({Rx},{Ry})", "l2": "outputs 1.5 GB per step, larger than the 126 MB L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------ own arm
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    import ossg_b200 as ossg
+    from ossg_b200 import _lib
+    from ossg_b200.distributed import tile_of
+    from ossg_b200.grids import make_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    if L.ossg_device_ok() != 0:
+        raise SystemExit("no usable CUDA device: " + _lib.last_error())
+
+    W = WORKLOAD
+    Rx, Ry = partition_for(world)
+    rx, ry = rank // Ry, rank % Ry
+    i0, j0, nx, ny = tile_of(W["Nx"], W["Ny"], Rx, Ry, rx, ry)
+    H = W["halo"]
+    params = make_params((W["Nx"], W["Ny"], W["Nz"]), (H, H, H), W["south"], W["north_poles_latitude"],
+                         W["first_pole_longitude"], W["radius"], tile=(i0, j0, nx, ny))
+    shape = (ny + 2 * H, nx + 2 * H)
+    out = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(20)]
+    optr = _lib.ptr_array([t.data_ptr() for t in out])
+    nbytes = L.ossg_tripolar_workspace_bytes(C.byref(params), _lib.OSSG_F64)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _lib.check(L.ossg_tripolar_build(C.byref(params), _lib.OSSG_F64, optr, ws.data_ptr(), ws.numel(), stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    else:
+        ms_total = ms_local
+    ms_step = ms_total / args.steps
+    cells_global = W["Nx"] * W["Ny"]
+    value = cells_global / (ms_step * 1e-3)
+
+    # ---- per-kernel device times (events between the kernels), same workload
+    prof = (C.c_float * 4)()
+    acc = [0.0] * 4
+    nprof = max(3, min(args.steps, 10))
+    for _ in range(nprof):
+        _lib.check(L.ossg_tripolar_build_profiled(C.byref(params), _lib.OSSG_F64, optr, ws.data_ptr(), ws.numel(),
+                                                  stream.cuda_stream, prof))
+        for k in range(4):
+            acc[k] += prof[k] / nprof
+    kernel_ms = dict(zip(["tables", "coords", "metrics_tile", "metrics_frame"], acc))
+
+    # ---- end to end through the public API with host buffers: construct + D2H of the 20 arrays
+    host = [torch.empty(shape, dtype=torch.float64).pin_memory() for _ in range(20)]
+    pin_params = bytes(params)       # the only input: 64 bytes of scalars, passed as kernel arguments
+
+    def e2e_step():
+        step()
+        for h, d in zip(host, out):
+            h.copy_(d, non_blocking=True)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    d2h_bytes = 20 * shape[0] * shape[1] * 8
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- zipper halo fill (second half of the metric): 4 fields c,u,v,zeta on the local tile
+    zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny) if world == 1 else None
+
+    # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels)
+    ms = C.c_float(); fl = C.c_double()
+    _lib.check(L.ossg_fp64_peak_probe(20000, C.byref(ms), C.byref(fl), stream.cuda_stream))
+    fp64_peak_tflops = fl.value / (ms.value * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tile_cells = nx * (ny - 2)                      # cells the tile kernel covers (rows 2..Ny-1)
+    # algorithmic bytes of the dominant kernel per cell: reads 8 coordinate values, writes 12 metrics
+    tile_bytes = tile_cells * (8 + 12) * 8
+    tile_ms = kernel_ms["metrics_tile"]
+    achieved = tile_bytes / (tile_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "metrics_tile_kernel<double>", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": tile_bytes,
+                "note": "this kernel is FP64-pipe bound, not HBM bound; see roofline_fp64"}
+    roofline_fp64 = {"bound": "fp64_pipe", "peak": fp64_peak_tflops, "unit": "TFLOP/s (DFMA = 2 flop)",
+                     "peak_source": "ossg_fp64_peak_probe on this device, same run",
+                     "tile_ns_per_cell": tile_ms * 1e6 / tile_cells}
+    if FP64_INST_PER_CELL_TILE:
+        inst_rate = FP64_INST_PER_CELL_TILE * tile_cells / (tile_ms * 1e-3)
+        roofline_fp64.update({"achieved_fp64_inst_per_s": inst_rate,
+                              "frac": inst_rate / (fp64_peak_tflops * 1e12 / 2)})
+
+    cpu_threads = os.cpu_count() or 1
+    cpu_rate, cpu_dt = cpu_construct_rate(cpu_threads, 2, 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "kernel_ms": kernel_ms,
+        "roofline": roofline, "roofline_fp64": roofline_fp64,
+        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": f"{CPU_SAMPLE['Nx']}x{CPU_SAMPLE['Ny']} grid (1/9 of the workload's cells), 2 steps, "
+                                   "CPU restatement of reference v0.2.1 (glibc libm); Julia is not installed"},
+        "e2e": {"value": cells_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": len(pin_params),
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
+                "what": "ossg_tripolar_build + copy of the 20 arrays to pinned host buffers (TripolarGrid(CPU()) equivalent)"},
+        "gpu_launches": args.steps * 4,
+        "clocks": clocks,
+        "zipper": zipper,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
+    """zipper halo-fill GB/s: c (C,C,+1), u (F,C,-1), v (C,F,-1), zeta (F,F,+1) on the workload grid,
+    FP64, one batched launch per fill, L2 flushed between timed fills."""
+    H, Nz = W["halo"], W["Nz"]
+    shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
+    specs = [((0, 0), 1.0), ((1, 0), -1.0), ((0, 1), -1.0), ((1, 1), 1.0)]
+    try:
+        fields = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in specs]
+    except RuntimeError as e:                                   # not enough memory for 4 x 8 GB
+        return {"error": str(e)[:100]}
+    descs = (_lib.FieldDesc * len(specs))(*[
+        _lib.FieldDesc(t.data_ptr(), _lib.OSSG_F64, nx, ny, Nz, H, H, H, loc[0], loc[1], 0, 0, s)
+        for t, (loc, s) in zip(fields, specs)])
+    for k in range(len(specs)):
+        _lib.check(L.ossg_synth_field(C.byref(descs[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    algo = 0
+    for (loc, _) in specs:
+        algo += 2 * H * nx * Nz * 8 + (nx * Nz * 8 if loc[1] == 0 else 0)
+    res = {}
+    for name, n in (("batch4", 4), ("single", 1)):
+        times = []
+        for it in range(8):
+            flush.fill_(it)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _lib.check(L.ossg_zipper_fill_batch(descs, n, stream.cuda_stream))
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        b = algo if n == 4 else (2 * H * nx * Nz * 8 + nx * Nz * 8)
+        res[name] = {"ms": ms, "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9}
+    res["config"] = f"{nx}x{ny}x{Nz} FP64 fields c,u,v,zeta, Hy=4, L2 flushed (256 MB write) before each timed fill"
+    del fields
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/*
+ * include/ossg_b200.h -- C ABI of libossg_b200.so
+ *
+ * B200 (sm_100a) implementation of the data-parallel hot path of
+ * CliMA/OrthogonalSphericalShellGrids.jl v0.2.1: TripolarGrid coordinate + metric generation and
+ * the zipper (north-fold) halo fill.  The reference has no FFI for this path (it is pure Julia
+ * multiple dispatch); each entry point below names the reference method whose body it replaces
+ * when called through `ccall` (see INTEGRATION.md for the Julia shim).
+ *
+ * Conventions
+ *  - Every pointer to array data is a DEVICE pointer owned by the caller.  The library never
+ *    allocates, frees, copies to or from host memory on the caller's behalf, and never
+ *    synchronises the device; all work is enqueued on the `stream` argument (a cudaStream_t
+ *    passed as void*; NULL = legacy default stream).
+ *  - Arrays use the reference's memory layout: the parent array of the OffsetArray, column-major,
+ *    i fastest.  A "padded" 2-D array has (nx+2Hx) x (ny+2Hy) elements, Julia index (i, j) at
+ *    element (i+Hx-1) + (j+Hy-1)*(nx+2Hx).  A 3-D field parent has (nx+2Hx)(ny+2Hy)(nz+2Hz).
+ *  - Every function returns 0 on success, a negative OSSG_E* code for an argument error
+ *    (the Julia shim raises ArgumentError), or a positive cudaError_t.  ossg_last_error()
+ *    returns a thread-local message.  Nothing aborts, exits or throws across the ABI.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef OSSG_B200_H
+#define OSSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSSG_VERSION_MAJOR 0
+#define OSSG_VERSION_MINOR 1
+
+/* argument errors */
+#define OSSG_EINVAL      (-1)   /* null pointer / nonsensical size                               */
+#define OSSG_EODD_NX     (-2)   /* "The number of cells in the longitude dimension should be even!"
+                                   src/tripolar_grid.jl:81-83                                    */
+#define OSSG_EHALO       (-3)   /* halo larger than the fold can serve (needs Hy <= Ny-1, Hx <= Nx) */
+#define OSSG_EWINDOW     (-4)   /* tile window outside the global padded extent                  */
+#define OSSG_EALIGN      (-5)   /* device pointer not aligned to its element size                */
+#define OSSG_ELOCATION   (-6)   /* location code not 0 (Center) / 1 (Face)                       */
+#define OSSG_EWORKSPACE  (-7)   /* workspace too small                                           */
+
+/* staggering codes: Oceananigans Center / Face */
+#define OSSG_CENTER 0
+#define OSSG_FACE   1
+
+/* element types */
+#define OSSG_F64 0
+#define OSSG_F32 1
+
+/* index of each array in the `out[20]` argument = positional order of the
+ * OrthogonalSphericalShellGrid constructor call at src/tripolar_grid.jl:308-328 (z omitted) */
+enum {
+    OSSG_LAM_CC = 0, OSSG_LAM_FC, OSSG_LAM_CF, OSSG_LAM_FF,
+    OSSG_PHI_CC, OSSG_PHI_FC, OSSG_PHI_CF, OSSG_PHI_FF,
+    OSSG_DX_CC, OSSG_DX_FC, OSSG_DX_CF, OSSG_DX_FF,
+    OSSG_DY_CC, OSSG_DY_CF, OSSG_DY_FC, OSSG_DY_FF,      /* sic: cc, cf, fc, ff (:321-324) */
+    OSSG_AZ_CC, OSSG_AZ_FC, OSSG_AZ_CF, OSSG_AZ_FF,
+    OSSG_N_ARRAYS
+};
+
+/* Keyword arguments of TripolarGrid(arch, FT; size, southernmost_latitude, halo, radius, z,
+ * north_poles_latitude, first_pole_longitude)  (src/tripolar_grid.jl:59-66) plus the tile window
+ * of a Distributed grid (src/distributed_tripolar_grid.jl:41-49, 112-120). */
+typedef struct ossg_tripolar_params {
+    int32_t Nx, Ny;                 /* global size[1], size[2]                                   */
+    int32_t Hx, Hy;                 /* halo[1], halo[2]                                          */
+    double  southernmost_latitude;  /* default -80                                               */
+    double  north_poles_latitude;   /* default  55                                               */
+    double  first_pole_longitude;   /* default  70                                               */
+    double  radius;                 /* default R_Earth = 6371.0e3                                */
+    /* Tile: interior cells i0 .. i0+nx-1, j0 .. j0+ny-1 (1-based, global); the arrays written
+     * are the window [i0-Hx, i0+nx-1+Hx] x [j0-Hy, j0+ny-1+Hy] of the GLOBAL padded arrays, i.e.
+     * exactly partition_tripolar_metric's slice.  Serial grid: i0 = j0 = 1, nx = Nx, ny = Ny.
+     * Setting nx = 0 (or ny = 0) means "whole grid" for that direction.                          */
+    int32_t i0, j0, nx, ny;
+} ossg_tripolar_params;
+
+/* ---- housekeeping ------------------------------------------------------------------------- */
+int         ossg_version(void);                 /* major*100 + minor                             */
+const char* ossg_last_error(void);              /* thread-local, never NULL                      */
+int         ossg_device_ok(void);               /* 0 iff a CUDA device of compute capability 10.x
+                                                   is current; else a positive cudaError_t / -1  */
+
+/* ---- TripolarGrid constructor ------------------------------------------------------------- *
+ * Replaces the body of TripolarGrid(arch, FT; ...) between src/tripolar_grid.jl:95 and :300
+ * (rows C0-C3, M1-M3 of SURVEY.md section 8a) and of TripolarGrid(arch::Distributed, ...)
+ * src/distributed_tripolar_grid.jl:36-73.
+ *
+ * workspace: device scratch of at least ossg_tripolar_workspace_bytes() bytes, 16-byte aligned
+ * (1-D tables; plus the 8 FP64 coordinate arrays when out_type = OSSG_F32, because the metrics
+ * are always computed from FP64 coordinates and rounded once at the end,
+ * src/tripolar_grid.jl:308-328).                                                               */
+size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, int out_type);
+
+/* all 20 arrays; out[k] (k = OSSG_LAM_CC ...) has (nx+2Hx)(ny+2Hy) elements of out_type */
+int ossg_tripolar_build(const ossg_tripolar_params* p, int out_type, void* const out[20],
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* same launches with CUDA events between the kernels; synchronises the stream and returns the
+ * device time of tables / coordinates / metrics (tile) / metrics (halo frame) in ms[0..3].
+ * Measurement aid for bench.py's roofline; not meant for production callers.                    */
+int ossg_tripolar_build_profiled(const ossg_tripolar_params* p, int out_type, void* const out[20],
+                                 void* workspace, size_t workspace_bytes, void* stream, float ms[4]);
+
+/* stage-wise entry points (same kernels; used for staged parity tests and by with_halo-style
+ * callers that already hold coordinates).  coords[8]: lam cc,fc,cf,ff, phi cc,fc,cf,ff, always
+ * FP64.  metrics[12]: dx cc,fc,cf,ff, dy cc,cf,fc,ff, az cc,fc,cf,ff of metrics_type.
+ * ossg_tripolar_metrics reads the coordinate arrays it is given: with a whole-grid window they
+ * may come from any source (e.g. the CPU oracle); with a tile window the halo ring, whose
+ * stencil leaves the window, is evaluated from the closed form instead.                          */
+int ossg_tripolar_coords(const ossg_tripolar_params* p, void* const coords[8],
+                         void* workspace, size_t workspace_bytes, void* stream);
+int ossg_tripolar_metrics(const ossg_tripolar_params* p, const void* const coords[8],
+                          int metrics_type, void* const metrics[12],
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Zipper boundary condition ------------------------------------------------------------- *
+ * Replaces the per-thread bodies fold_north_{center_center,face_center,center_face,face_face}!
+ * (src/zipper_boundary_condition.jl:70-138) as dispatched by _fill_north_halo! (:146-155), for
+ * all i in 1..Nx and the parent k-levels [k0, k0+nk):
+ *     c[i, Ny+j, k] = s * c[i', Ny-j(+1), k],  j = 1..Hy ;  y-Center: c[i, Ny, k] = s*c[i', Ny, k] for i > Nx/2
+ * `sign` is bc.condition (ZipperBoundaryCondition(sign), :52).                                  */
+typedef struct ossg_field_desc {
+    void*   data;                   /* parent array, device                                      */
+    int32_t elem_type;              /* OSSG_F64 / OSSG_F32                                       */
+    int32_t Nx, Ny, Nz;             /* interior size                                             */
+    int32_t Hx, Hy, Hz;             /* halo                                                      */
+    int32_t locx, locy;             /* OSSG_CENTER / OSSG_FACE                                   */
+    int32_t k0, nk;                 /* parent k-levels to fill; nk = 0 means k0 = Hz, nk = Nz    */
+    double  sign;                   /* bc.condition                                              */
+} ossg_field_desc;
+
+int ossg_zipper_fill(const ossg_field_desc* f, void* stream);
+/* several fields in ONE launch (tupled_fill_halo_regions!, src/tripolar_grid_extensions.jl:17) */
+int ossg_zipper_fill_batch(const ossg_field_desc* f, int nfields, void* stream);
+/* zipper north fill followed by the periodic west/east fill over the whole (y,z) parent extent --
+ * fill_halo_regions! of a field on a TripolarGrid whose other boundaries are `nothing`
+ * (src/tripolar_grid.jl:147-186); one launch per batch.                                          */
+int ossg_fill_halo_regions_batch(const ossg_field_desc* f, int nfields, void* stream);
+
+/* ---- (x, y)-partitioned fold: pack / unpack around the mirror-rank exchange ----------------- *
+ * New relative to the reference (which only supports Y slabs, src/distributed_tripolar_grid.jl:
+ * 28-31).  A top-row rank owning global columns [i0, i0+nx-1] needs, for its north halo, the
+ * source rows of global columns [Nx-(i0+nx-1)+1(+1) .. ] held by its mirror rank.
+ * ossg_fold_pack gathers, from the LOCAL field, the rows another rank needs into a contiguous
+ * buffer; ossg_fold_unpack writes a received buffer into the local north halo with the i-reversal
+ * and sign.  The exchange itself (ncclSend/ncclRecv or peer copy) is the caller's.
+ * Buffer layout: [k][row r = 0..nrows-1][global column ascending], nrows = Hy (+1 for y-Center:
+ * the row-Ny overwrite), element type of the field.                                             */
+typedef struct ossg_fold_window {
+    int32_t gNx;                    /* global Nx                                                 */
+    int32_t i0, nx;                 /* this rank's global first interior column and width        */
+    int32_t src_i0, src_n;          /* global column range [src_i0, src_i0+src_n) to pack/unpack */
+} ossg_fold_window;
+
+size_t ossg_fold_buffer_elems(const ossg_field_desc* f, const ossg_fold_window* w);
+int ossg_fold_pack(const ossg_field_desc* f, const ossg_fold_window* w, void* buffer, void* stream);
+int ossg_fold_unpack(const ossg_field_desc* f, const ossg_fold_window* w, const void* buffer, void* stream);
+
+/* ---- measurement / test utilities (not part of the reference surface) ---------------------- */
+/* interior(c)[i,j,k] = hash(seed, global i, j, k) in [-1, 1); halos are filled with a NaN payload */
+int ossg_synth_field(const ossg_field_desc* f, uint64_t seed, int32_t gi0, int32_t gj0, void* stream);
+/* sustained FP64 FMA rate of the current device: runs `iters` dependent-chain DFMA steps per
+ * thread on a full grid; returns elapsed ms via *ms and executed flops via *flops              */
+int ossg_fp64_peak_probe(int iters, float* ms, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSSG_B200_H */

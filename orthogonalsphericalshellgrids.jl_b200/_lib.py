@@ -1,0 +1,119 @@
+"""Loader of the sm_100a shared library (libossg_b200.so) and the ctypes mirror of
+include/ossg_b200.h.  There is no fallback: if the library is missing or no B200-class device
+is current, every compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libossg_b200.so")
+HEADER_PATH = os.path.join(_ROOT, "include", "ossg_b200.h")
+
+# error codes (include/ossg_b200.h)
+OSSG_EINVAL, OSSG_EODD_NX, OSSG_EHALO, OSSG_EWINDOW, OSSG_EALIGN, OSSG_ELOCATION, OSSG_EWORKSPACE = -1, -2, -3, -4, -5, -6, -7
+OSSG_CENTER, OSSG_FACE = 0, 1
+OSSG_F64, OSSG_F32 = 0, 1
+
+ARRAY_NAMES = ["lam_cc", "lam_fc", "lam_cf", "lam_ff", "phi_cc", "phi_fc", "phi_cf", "phi_ff",
+               "dx_cc", "dx_fc", "dx_cf", "dx_ff", "dy_cc", "dy_cf", "dy_fc", "dy_ff",
+               "az_cc", "az_fc", "az_cf", "az_ff"]
+
+
+class TripolarParams(C.Structure):
+    _fields_ = [("Nx", C.c_int32), ("Ny", C.c_int32), ("Hx", C.c_int32), ("Hy", C.c_int32),
+                ("southernmost_latitude", C.c_double), ("north_poles_latitude", C.c_double),
+                ("first_pole_longitude", C.c_double), ("radius", C.c_double),
+                ("i0", C.c_int32), ("j0", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32)]
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("elem_type", C.c_int32),
+                ("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32),
+                ("Hx", C.c_int32), ("Hy", C.c_int32), ("Hz", C.c_int32),
+                ("locx", C.c_int32), ("locy", C.c_int32),
+                ("k0", C.c_int32), ("nk", C.c_int32), ("sign", C.c_double)]
+
+
+class FoldWindow(C.Structure):
+    _fields_ = [("gNx", C.c_int32), ("i0", C.c_int32), ("nx", C.c_int32),
+                ("src_i0", C.c_int32), ("src_n", C.c_int32)]
+
+
+class OSSGError(RuntimeError):
+    """Non-argument failure reported by libossg_b200.so (a CUDA error)."""
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libossg_b200.so for sm_100a in-tree with nvcc (csrc/Makefile)."""
+    res = subprocess.run(["make", "-C", os.path.join(_PKG, "csrc")], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc build of libossg_b200.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises if it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vpp = C.POINTER(C.c_void_p)
+    L.ossg_version.restype = C.c_int
+    L.ossg_last_error.restype = C.c_char_p
+    L.ossg_device_ok.restype = C.c_int
+    L.ossg_tripolar_workspace_bytes.argtypes = [C.POINTER(TripolarParams), C.c_int]
+    L.ossg_tripolar_workspace_bytes.restype = C.c_size_t
+    L.ossg_tripolar_build.argtypes = [C.POINTER(TripolarParams), C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.ossg_tripolar_build_profiled.argtypes = [C.POINTER(TripolarParams), C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
+    L.ossg_tripolar_coords.argtypes = [C.POINTER(TripolarParams), vpp, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.ossg_tripolar_metrics.argtypes = [C.POINTER(TripolarParams), vpp, C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.ossg_zipper_fill.argtypes = [C.POINTER(FieldDesc), C.c_void_p]
+    L.ossg_zipper_fill_batch.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_void_p]
+    L.ossg_fill_halo_regions_batch.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_void_p]
+    L.ossg_fold_buffer_elems.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow)]
+    L.ossg_fold_buffer_elems.restype = C.c_size_t
+    L.ossg_fold_pack.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow), C.c_void_p, C.c_void_p]
+    L.ossg_fold_unpack.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow), C.c_void_p, C.c_void_p]
+    L.ossg_synth_field.argtypes = [C.POINTER(FieldDesc), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
+    L.ossg_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().ossg_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Map a return code to the exception the Julia shim would raise: negative -> ArgumentError
+    (ValueError here), positive -> CUDA failure."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc < 0:
+        raise ValueError(msg)
+    raise OSSGError(f"CUDA error {rc}: {msg}")
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return C.cast(arr, C.POINTER(C.c_void_p))
+
+
+def declared_symbols() -> list:
+    """Function names declared in include/ossg_b200.h (for the export test)."""
+    import re
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ossg_[a-z0-9_]+)\s*\(", text)))

@@ -1,0 +1,488 @@
+// csrc/ossg_tripolar.cu -- TripolarGrid coordinate + metric generation on sm_100a.
+//
+// Kernels (all FP64 arithmetic, outputs FP64 or rounded once to FP32):
+//   K0 tables_kernel        1-D tables: a*sind/cosd(lam1D), cosh/sinh(psi(phi1D)), lat-lon rows
+//   K1 coords_kernel        8 padded coordinate arrays; circshift + zipper/periodic halos are
+//                           index maps (every element evaluated at its source)
+//   K2 metrics_tile_kernel  12 metric arrays over the interior: coordinate tile + 1-cell apron
+//                           staged in shared memory, per-point cos(phi) and unit vectors computed
+//                           once per tile point, coalesced stores
+//   K2f metrics_frame_kernel  the halo frame (north fold image, x halos, fold row Ny, south
+//                           continuation rows): each element evaluated at its source
+// Compile with -fmad=false: see ossg_math.cuh for the determinism contract.
+#include "ossg_common.cuh"
+#include "ossg_tripolar_core.cuh"
+
+namespace ossg {
+
+struct Window {
+    int I0, J0;      // global padded index of window element (0, 0)
+    int wnx, wny;    // window extents (halos included); pitch == wnx
+};
+
+struct BuildArgs {
+    GridDims g;
+    Window w;
+    double south, north_poles_latitude, first_pole_longitude, radius;
+    double* tables;               // workspace: tables_doubles() doubles
+    double* coords64[8];          // FP64 coordinates (outputs when FT = double, scratch otherwise)
+    void* coords_out[8];          // FT coordinates (== coords64 when FT = double)
+    void* metrics_out[12];        // FT metrics
+};
+
+__host__ __device__ inline Tables make_tables(const double* base, int Nx, int Ny)
+{
+    Tables t;
+    t.asF = base;            t.acF = base + Nx;       t.asC = base + 2 * (size_t)Nx; t.acC = base + 3 * (size_t)Nx;
+    const double* y = base + 4 * (size_t)Nx;
+    t.chF = y;               t.shF = y + Ny;          t.chC = y + 2 * (size_t)Ny;    t.shC = y + 3 * (size_t)Ny;
+    t.ll = y + 4 * (size_t)Ny;
+    return t;
+}
+
+// ------------------------------------------------------------------ K0
+__global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, double north_poles_latitude,
+                                                     double radius, double* __restrict__ base)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Nx = g.Nx, Ny = g.Ny;
+    double* xs = base;
+    double* ys = base + 4 * (size_t)Nx;
+    double* ll = ys + 4 * (size_t)Ny;
+    if (t < 2 * Nx) {
+        // x tables, stored in post-circshift order; one thread per (face|center, i)
+        const int face = t < Nx;
+        const int i = face ? t + 1 : t - Nx + 1;
+        const int ip = preshift(i, Nx);
+        const double a = focal_distance(north_poles_latitude);
+        const double lam = face ? lam_face(ip, Nx) : lam_center(ip, Nx);
+        const int o = face ? 0 : 2;
+        xs[(size_t)(o + 0) * Nx + (i - 1)] = a * m::sind(lam);      // generate_tripolar_coordinates.jl:67
+        xs[(size_t)(o + 1) * Nx + (i - 1)] = a * m::cosd(lam);      // :68
+    } else if (t < 2 * Nx + 2 * Ny) {
+        const int u = t - 2 * Nx;
+        const int face = u < Ny;
+        const int j = face ? u + 1 : u - Ny + 1;
+        const double a = focal_distance(north_poles_latitude);
+        const double phi = face ? phi_face(j, Ny, south) : phi_center(j, Ny, south);
+        const double psi = m::asinh_cr(m::tand((90.0 - phi) / 2) / a);   // :66
+        const int o = face ? 0 : 2;
+        ys[(size_t)(o + 0) * Ny + (j - 1)] = m::cosh_cr(psi);
+        ys[(size_t)(o + 1) * Ny + (j - 1)] = m::sinh_cr(psi);
+    } else if (t < 2 * Nx + 2 * Ny + g.Hy + 1) {
+        const int r = t - 2 * Nx - 2 * Ny;                  // row r <-> j = r + 1 - Hy
+        latlon_row(r + 1 - g.Hy, Nx, Ny, g.Hy, south, radius, ll + (size_t)r * LL_NCOL);
+    }
+}
+
+// ------------------------------------------------------------------ K1
+template <typename FT>
+__global__ void __launch_bounds__(256) coords_kernel(BuildArgs a)
+{
+    const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jw = blockIdx.y;
+    if (iw >= a.w.wnx) return;
+    const int I = a.w.I0 + iw, J = a.w.J0 + jw;
+    const GridDims g = a.g;
+    const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
+    const size_t o = (size_t)jw * a.w.wnx + iw;
+    double lam[4], phi[4];
+    if (I >= 1 && I <= g.Nx && J >= 1 && J < g.Ny) {
+        // bulk: all four staggerings sit at their own (I, J)
+        const int ip = preshift(I, g.Nx);
+        const bool one = ip == 1, half = ip <= g.Nx / 2;
+        const double asF = tb.asF[I - 1], acF = tb.acF[I - 1], asC = tb.asC[I - 1], acC = tb.acC[I - 1];
+        const double chF = tb.chF[J - 1], shF = tb.shF[J - 1], chC = tb.chC[J - 1], shC = tb.shC[J - 1];
+        tripolar_point(asC, acC, chC, shC, one, half, a.first_pole_longitude, lam[CC], phi[CC]);
+        tripolar_point(asF, acF, chC, shC, one, half, a.first_pole_longitude, lam[FC], phi[FC]);
+        tripolar_point(asC, acC, chF, shF, one, half, a.first_pole_longitude, lam[CF], phi[CF]);
+        tripolar_point(asF, acF, chF, shF, one, half, a.first_pole_longitude, lam[FF], phi[FF]);
+    } else {
+#pragma unroll
+        for (int loc = 0; loc < 4; ++loc)
+            coord_at(tb, g, a.first_pole_longitude, loc, I, J, lam[loc], phi[loc]);
+    }
+#pragma unroll
+    for (int loc = 0; loc < 4; ++loc) {
+        a.coords64[loc][o] = lam[loc];
+        a.coords64[4 + loc][o] = phi[loc];
+        if (sizeof(FT) == 4) {
+            static_cast<FT*>(a.coords_out[loc])[o] = (FT)lam[loc];
+            static_cast<FT*>(a.coords_out[4 + loc])[o] = (FT)phi[loc];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K2 (tile)
+constexpr int TX = 32, TY = 8;
+constexpr int PX = TX + 2, PY = TY + 2, PTS = PX * PY;
+// shared arrays: lam, phr, cosphi per staggering (12) + unit vectors of CC and FF (6)
+constexpr int N_SMEM_ARRAYS = 18;
+constexpr size_t TILE_SMEM_BYTES = (size_t)N_SMEM_ARRAYS * PTS * sizeof(double);
+
+struct FastRect { int I0, J0, nx, ny; };   // global indices of the first fast cell, extents
+
+template <typename FT>
+__global__ void __launch_bounds__(TX * TY, 2) metrics_tile_kernel(BuildArgs a, FastRect fr)
+{
+    extern __shared__ __align__(16) double smem[];
+    double* s_lam = smem;                    // [4][PTS]
+    double* s_phr = smem + 4 * PTS;          // [4][PTS]  deg2rad(phi)
+    double* s_cos = smem + 8 * PTS;          // [4][PTS]  cos(deg2rad(phi))
+    double* s_ux = smem + 12 * PTS;          // [2][PTS]  unit vectors: slot 0 = CC, slot 1 = FF
+    double* s_uy = smem + 14 * PTS;
+    double* s_uz = smem + 16 * PTS;
+
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
+    const Window w = a.w;
+
+    // ---- point stage: load the coordinate tile + apron once, hoist per-point trig
+    // task order: CC, FF (unit vectors needed), then FC, CF
+    for (int t = tid; t < 4 * PTS; t += TX * TY) {
+        const int q = t / PTS, p = t - q * PTS;
+        const int loc = (q == 0) ? CC : (q == 1) ? FF : (q == 2) ? FC : CF;
+        const int pj = p / PX, pi = p - pj * PX;
+        const int iw = It0 - 1 + pi - w.I0, jw = Jt0 - 1 + pj - w.J0;
+        double lam = 0.0, phi = 0.0;
+        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
+            const size_t o = (size_t)jw * w.wnx + iw;
+            lam = a.coords64[loc][o];
+            phi = a.coords64[4 + loc][o];
+        }
+        const double phr = phi * D2R;
+        s_lam[loc * PTS + p] = lam;
+        s_phr[loc * PTS + p] = phr;
+        s_cos[loc * PTS + p] = m::cos_rad(phr);
+        if (q < 2) {
+            const Vec3 u = lat_lon_to_cartesian(phi, lam);
+            s_ux[q * PTS + p] = u.x;
+            s_uy[q * PTS + p] = u.y;
+            s_uz[q * PTS + p] = u.z;
+        }
+    }
+    __syncthreads();
+
+    const int ci = blockIdx.x * TX + threadIdx.x, cj = blockIdx.y * TY + threadIdx.y;
+    if (ci >= fr.nx || cj >= fr.ny) return;
+    const double R = a.radius;
+    const int p00 = (threadIdx.y + 1) * PX + (threadIdx.x + 1);
+    const int p10 = p00 + 1, pm0 = p00 - 1, p01 = p00 + PX, p0m = p00 - PX, p11 = p01 + 1, pmm = p0m - 1;
+
+#define HAV(L, px, py) haversine_pre(s_lam[(L) * PTS + (px)], s_phr[(L) * PTS + (px)], s_cos[(L) * PTS + (px)], \
+                                     s_lam[(L) * PTS + (py)], s_phr[(L) * PTS + (py)], s_cos[(L) * PTS + (py)], R)
+#define UV(slot, px) Vec3{ s_ux[(slot) * PTS + (px)], s_uy[(slot) * PTS + (px)], s_uz[(slot) * PTS + (px)] }
+
+    const double dx_cc = HAV(FC, p10, p00);      // tripolar_grid_utils.jl:13
+    const double dx_fc = HAV(CC, p00, pm0);      // :14
+    const double dx_cf = HAV(FF, p10, p00);      // :15
+    const double dx_ff = HAV(CF, p00, pm0);      // :16
+    const double dy_cc = HAV(CF, p01, p00);      // :18
+    const double dy_fc = HAV(FF, p01, p00);      // :19
+    const double dy_cf = HAV(CC, p00, p0m);      // :20
+    const double dy_ff = HAV(FC, p00, p0m);      // :21
+    const double az_cc = spherical_area_quadrilateral(UV(1, p00), UV(1, p10), UV(1, p11), UV(1, p01)) * (R * R);   // :23-28
+    const double az_fc = dy_fc * dx_fc;          // :34
+    const double az_cf = dy_cf * dx_cf;          // :35
+    const double az_ff = spherical_area_quadrilateral(UV(0, pmm), UV(0, p0m), UV(0, p00), UV(0, pm0)) * (R * R);   // :38-43
+#undef HAV
+#undef UV
+
+    const size_t o = (size_t)(Jt0 + threadIdx.y - w.J0) * w.wnx + (It0 + threadIdx.x - w.I0);
+    static_cast<FT*>(a.metrics_out[DX_CC])[o] = (FT)dx_cc;
+    static_cast<FT*>(a.metrics_out[DX_FC])[o] = (FT)dx_fc;
+    static_cast<FT*>(a.metrics_out[DX_CF])[o] = (FT)dx_cf;
+    static_cast<FT*>(a.metrics_out[DX_FF])[o] = (FT)dx_ff;
+    static_cast<FT*>(a.metrics_out[DY_CC])[o] = (FT)dy_cc;
+    static_cast<FT*>(a.metrics_out[DY_CF])[o] = (FT)dy_cf;
+    static_cast<FT*>(a.metrics_out[DY_FC])[o] = (FT)dy_fc;
+    static_cast<FT*>(a.metrics_out[DY_FF])[o] = (FT)dy_ff;
+    static_cast<FT*>(a.metrics_out[AZ_CC])[o] = (FT)az_cc;
+    static_cast<FT*>(a.metrics_out[AZ_FC])[o] = (FT)az_fc;
+    static_cast<FT*>(a.metrics_out[AZ_CF])[o] = (FT)az_cf;
+    static_cast<FT*>(a.metrics_out[AZ_FF])[o] = (FT)az_ff;
+}
+
+// ------------------------------------------------------------------ K2f (frame)
+struct GlobalAcc {          // read the window's coordinate arrays
+    const double* const* c; int I0, J0, pitch;
+    __device__ void operator()(int loc, int I, int J, double& lam, double& phi) const
+    {
+        const size_t o = (size_t)(J - J0) * pitch + (I - I0);
+        lam = c[loc][o];
+        phi = c[4 + loc][o];
+    }
+};
+struct ClosedFormAcc {      // evaluate the coordinate at its source from the tables
+    Tables tb; GridDims g; double fpl;
+    __device__ void operator()(int loc, int I, int J, double& lam, double& phi) const
+    {
+        coord_at(tb, g, fpl, loc, I, J, lam, phi);
+    }
+};
+
+// frame = window minus fast rectangle, enumerated as four rectangles
+struct Frame {
+    int jlo, jhi, ilo, ihi;     // fast rectangle in WINDOW coordinates: [ilo, ihi) x [jlo, jhi)
+    long long n_south, n_north, n_west, n_east;
+};
+
+__host__ __device__ inline Frame make_frame(const Window& w, const FastRect& fr)
+{
+    Frame f;
+    if (fr.nx <= 0 || fr.ny <= 0) { f.ilo = f.ihi = 0; f.jlo = f.jhi = w.wny; }
+    else { f.ilo = fr.I0 - w.I0; f.ihi = f.ilo + fr.nx; f.jlo = fr.J0 - w.J0; f.jhi = f.jlo + fr.ny; }
+    f.n_south = (long long)f.jlo * w.wnx;
+    f.n_north = (long long)(w.wny - f.jhi) * w.wnx;
+    f.n_west = (long long)(f.jhi - f.jlo) * f.ilo;
+    f.n_east = (long long)(f.jhi - f.jlo) * (w.wnx - f.ihi);
+    return f;
+}
+
+template <typename FT, bool CLOSED_FORM>
+__global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const Window w = a.w;
+    int iw, jw;
+    if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
+    else if ((t -= f.n_south) < f.n_north) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); jw += f.jhi; }
+    else if ((t -= f.n_north) < f.n_west) { jw = (int)(t / f.ilo); iw = (int)(t - (long long)jw * f.ilo); jw += f.jlo; }
+    else if ((t -= f.n_west) < f.n_east) {
+        const int ne = w.wnx - f.ihi;
+        jw = (int)(t / ne); iw = (int)(t - (long long)jw * ne) + f.ihi; jw += f.jlo;
+    } else return;
+
+    const GridDims g = a.g;
+    const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
+    double out[N_METRIC];
+    if (CLOSED_FORM) {
+        ClosedFormAcc acc{ tb, g, a.first_pole_longitude };
+        metrics_at_padded(acc, tb, g, a.radius, w.I0 + iw, w.J0 + jw, out);
+    } else {
+        GlobalAcc acc{ a.coords64, w.I0, w.J0, w.wnx };
+        metrics_at_padded(acc, tb, g, a.radius, w.I0 + iw, w.J0 + jw, out);
+    }
+    const size_t o = (size_t)jw * w.wnx + iw;
+#pragma unroll
+    for (int k = 0; k < N_METRIC; ++k) static_cast<FT*>(a.metrics_out[k])[o] = (FT)out[k];
+}
+
+// ------------------------------------------------------------------ host side
+static int check_params(const ossg_tripolar_params* p, ossg_tripolar_params& q)
+{
+    if (!p) return set_error(OSSG_EINVAL, "params is NULL");
+    q = *p;
+    if (q.Nx < 2 || q.Ny < 2) return set_error(OSSG_EINVAL, "size must be at least (2, 2), got (%d, %d)", q.Nx, q.Ny);
+    if (q.Nx % 2 != 0)
+        return set_error(OSSG_EODD_NX, "The number of cells in the longitude dimension should be even!");
+    if (q.Hx < 1 || q.Hy < 1) return set_error(OSSG_EHALO, "halo must be at least (1, 1), got (%d, %d)", q.Hx, q.Hy);
+    if (q.Hy > q.Ny - 1 || q.Hx > q.Nx)
+        return set_error(OSSG_EHALO, "halo (%d, %d) too large for size (%d, %d): need Hx <= Nx, Hy <= Ny-1", q.Hx, q.Hy, q.Nx, q.Ny);
+    if (q.nx == 0) { q.i0 = 1; q.nx = q.Nx; }
+    if (q.ny == 0) { q.j0 = 1; q.ny = q.Ny; }
+    if (q.i0 < 1 || q.nx < 1 || q.i0 + q.nx - 1 > q.Nx || q.j0 < 1 || q.ny < 1 || q.j0 + q.ny - 1 > q.Ny)
+        return set_error(OSSG_EWINDOW, "tile i0=%d nx=%d j0=%d ny=%d outside the %dx%d grid", q.i0, q.nx, q.j0, q.ny, q.Nx, q.Ny);
+    if (!(q.radius > 0.0)) return set_error(OSSG_EINVAL, "radius must be positive");
+    return 0;
+}
+
+static size_t table_bytes(const ossg_tripolar_params& q)
+{
+    size_t n = tables_doubles(q.Nx, q.Ny, q.Hy);
+    n = (n + 1) & ~(size_t)1;            // keep what follows 16-byte aligned
+    return n * sizeof(double);
+}
+static size_t window_elems(const ossg_tripolar_params& q)
+{
+    return (size_t)(q.nx + 2 * q.Hx) * (size_t)(q.ny + 2 * q.Hy);
+}
+
+static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* workspace)
+{
+    a.g = GridDims{ q.Nx, q.Ny, q.Hx, q.Hy };
+    a.w = Window{ q.i0 - q.Hx, q.j0 - q.Hy, q.nx + 2 * q.Hx, q.ny + 2 * q.Hy };
+    a.south = q.southernmost_latitude;
+    a.north_poles_latitude = q.north_poles_latitude;
+    a.first_pole_longitude = q.first_pole_longitude;
+    a.radius = q.radius;
+    a.tables = static_cast<double*>(workspace);
+}
+
+static int launch_tables(const BuildArgs& a, cudaStream_t s)
+{
+    const int n = 2 * a.g.Nx + 2 * a.g.Ny + a.g.Hy + 1;
+    tables_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a.g, a.south, a.north_poles_latitude, a.radius, a.tables);
+    OSSG_LAUNCH_CHECK("tables_kernel");
+    return 0;
+}
+
+template <typename FT>
+static int launch_coords(const BuildArgs& a, cudaStream_t s)
+{
+    dim3 block(256), grid(ceil_div(a.w.wnx, 256), a.w.wny);
+    coords_kernel<FT><<<grid, block, 0, s>>>(a);
+    OSSG_LAUNCH_CHECK("coords_kernel");
+    return 0;
+}
+
+template <typename FT>
+static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, cudaEvent_t between = nullptr)
+{
+    const Window& w = a.w;
+    // fast rectangle: global interior rows 2..Ny-1, columns 1..Nx, one cell inside the window ring
+    FastRect fr;
+    const int Ilo = max(1, w.I0 + 1), Ihi = min(a.g.Nx, w.I0 + w.wnx - 2);
+    const int Jlo = max(2, w.J0 + 1), Jhi = min(a.g.Ny - 1, w.J0 + w.wny - 2);
+    fr.I0 = Ilo; fr.J0 = Jlo; fr.nx = Ihi - Ilo + 1; fr.ny = Jhi - Jlo + 1;
+    if (fr.nx > 0 && fr.ny > 0) {
+        static bool attr_set[2] = { false, false };
+        const int which = sizeof(FT) == 4;
+        if (!attr_set[which]) {
+            OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
+            attr_set[which] = true;
+        }
+        dim3 block(TX, TY), grid(ceil_div(fr.nx, TX), ceil_div(fr.ny, TY));
+        metrics_tile_kernel<FT><<<grid, block, TILE_SMEM_BYTES, s>>>(a, fr);
+        OSSG_LAUNCH_CHECK("metrics_tile_kernel");
+    }
+    if (between) OSSG_CUDA_TRY(cudaEventRecord(between, s));
+    const Frame f = make_frame(w, fr);
+    const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
+    if (n > 0) {
+        if (whole_grid) metrics_frame_kernel<FT, false><<<ceil_div(n, 128), 128, 0, s>>>(a, f);
+        else metrics_frame_kernel<FT, true><<<ceil_div(n, 128), 128, 0, s>>>(a, f);
+        OSSG_LAUNCH_CHECK("metrics_frame_kernel");
+    }
+    return 0;
+}
+
+static bool is_whole_grid(const ossg_tripolar_params& q)
+{
+    return q.i0 == 1 && q.j0 == 1 && q.nx == q.Nx && q.ny == q.Ny;
+}
+
+static int check_ptrs(void* const* v, int n, size_t align, const char* what)
+{
+    if (!v) return set_error(OSSG_EINVAL, "%s is NULL", what);
+    for (int k = 0; k < n; ++k) {
+        if (!v[k]) return set_error(OSSG_EINVAL, "%s[%d] is NULL", what, k);
+        if (reinterpret_cast<uintptr_t>(v[k]) % align) return set_error(OSSG_EALIGN, "%s[%d] is not %zu-byte aligned", what, k, align);
+    }
+    return 0;
+}
+
+}  // namespace ossg
+
+using namespace ossg;
+
+extern "C" size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, int out_type)
+{
+    ossg_tripolar_params q;
+    if (check_params(p, q)) return 0;
+    size_t b = table_bytes(q);
+    if (out_type == OSSG_F32) b += 8 * window_elems(q) * sizeof(double);
+    return b;
+}
+
+static int build_impl(const ossg_tripolar_params* p, int out_type, void* const out[20],
+                      void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t* ev /*[5] or NULL*/)
+{
+    ossg_tripolar_params q;
+    int rc = check_params(p, q);
+    if (rc) return rc;
+    if (out_type != OSSG_F64 && out_type != OSSG_F32) return set_error(OSSG_EINVAL, "out_type must be OSSG_F64 or OSSG_F32");
+    const size_t esz = out_type == OSSG_F64 ? 8 : 4;
+    if ((rc = check_ptrs(out, 20, esz, "out"))) return rc;
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 16) return set_error(OSSG_EALIGN, "workspace must be a 16-byte aligned device pointer");
+    if (workspace_bytes < ossg_tripolar_workspace_bytes(p, out_type))
+        return set_error(OSSG_EWORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, ossg_tripolar_workspace_bytes(p, out_type));
+    BuildArgs a;
+    fill_common(a, q, workspace);
+    for (int k = 0; k < 8; ++k) a.coords_out[k] = out[k];
+    for (int k = 0; k < 12; ++k) a.metrics_out[k] = out[8 + k];
+    if (out_type == OSSG_F64) {
+        for (int k = 0; k < 8; ++k) a.coords64[k] = static_cast<double*>(out[k]);
+    } else {
+        double* scratch = reinterpret_cast<double*>(static_cast<char*>(workspace) + table_bytes(q));
+        for (int k = 0; k < 8; ++k) a.coords64[k] = scratch + (size_t)k * window_elems(q);
+    }
+    cudaStream_t s = as_stream(stream);
+    const bool whole = is_whole_grid(q);
+    if (ev) OSSG_CUDA_TRY(cudaEventRecord(ev[0], s));
+    if ((rc = launch_tables(a, s))) return rc;
+    if (ev) OSSG_CUDA_TRY(cudaEventRecord(ev[1], s));
+    rc = out_type == OSSG_F64 ? launch_coords<double>(a, s) : launch_coords<float>(a, s);
+    if (rc) return rc;
+    if (ev) OSSG_CUDA_TRY(cudaEventRecord(ev[2], s));
+    rc = out_type == OSSG_F64 ? launch_metrics<double>(a, whole, s, ev ? ev[3] : nullptr)
+                              : launch_metrics<float>(a, whole, s, ev ? ev[3] : nullptr);
+    if (rc) return rc;
+    if (ev) OSSG_CUDA_TRY(cudaEventRecord(ev[4], s));
+    return 0;
+}
+
+extern "C" int ossg_tripolar_build(const ossg_tripolar_params* p, int out_type, void* const out[20],
+                                   void* workspace, size_t workspace_bytes, void* stream)
+{
+    return build_impl(p, out_type, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int ossg_tripolar_build_profiled(const ossg_tripolar_params* p, int out_type, void* const out[20],
+                                            void* workspace, size_t workspace_bytes, void* stream, float ms[4])
+{
+    if (!ms) return set_error(OSSG_EINVAL, "ms is NULL");
+    cudaEvent_t ev[5];
+    for (int k = 0; k < 5; ++k) OSSG_CUDA_TRY(cudaEventCreate(&ev[k]));
+    int rc = build_impl(p, out_type, out, workspace, workspace_bytes, stream, ev);
+    if (rc == 0) {
+        cudaError_t e = cudaEventSynchronize(ev[4]);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
+        for (int k = 0; k < 4 && rc == 0; ++k) {
+            e = cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventElapsedTime");
+        }
+    }
+    for (int k = 0; k < 5; ++k) cudaEventDestroy(ev[k]);
+    return rc;
+}
+
+extern "C" int ossg_tripolar_coords(const ossg_tripolar_params* p, void* const coords[8],
+                                    void* workspace, size_t workspace_bytes, void* stream)
+{
+    ossg_tripolar_params q;
+    int rc = check_params(p, q);
+    if (rc) return rc;
+    if ((rc = check_ptrs(coords, 8, 8, "coords"))) return rc;
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 16) return set_error(OSSG_EALIGN, "workspace must be a 16-byte aligned device pointer");
+    if (workspace_bytes < table_bytes(q)) return set_error(OSSG_EWORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, table_bytes(q));
+    BuildArgs a;
+    fill_common(a, q, workspace);
+    for (int k = 0; k < 8; ++k) { a.coords64[k] = static_cast<double*>(coords[k]); a.coords_out[k] = coords[k]; }
+    for (int k = 0; k < 12; ++k) a.metrics_out[k] = nullptr;
+    cudaStream_t s = as_stream(stream);
+    if ((rc = launch_tables(a, s))) return rc;
+    return launch_coords<double>(a, s);
+}
+
+extern "C" int ossg_tripolar_metrics(const ossg_tripolar_params* p, const void* const coords[8],
+                                     int metrics_type, void* const metrics[12],
+                                     void* workspace, size_t workspace_bytes, void* stream)
+{
+    ossg_tripolar_params q;
+    int rc = check_params(p, q);
+    if (rc) return rc;
+    if (metrics_type != OSSG_F64 && metrics_type != OSSG_F32) return set_error(OSSG_EINVAL, "metrics_type must be OSSG_F64 or OSSG_F32");
+    if ((rc = check_ptrs(const_cast<void* const*>(coords), 8, 8, "coords"))) return rc;
+    if ((rc = check_ptrs(metrics, 12, metrics_type == OSSG_F64 ? 8 : 4, "metrics"))) return rc;
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 16) return set_error(OSSG_EALIGN, "workspace must be a 16-byte aligned device pointer");
+    if (workspace_bytes < table_bytes(q)) return set_error(OSSG_EWORKSPACE, "workspace has %zu bytes, need %zu", workspace_bytes, table_bytes(q));
+    BuildArgs a;
+    fill_common(a, q, workspace);
+    for (int k = 0; k < 8; ++k) { a.coords64[k] = static_cast<double*>(const_cast<void*>(coords[k])); a.coords_out[k] = nullptr; }
+    for (int k = 0; k < 12; ++k) a.metrics_out[k] = metrics[k];
+    cudaStream_t s = as_stream(stream);
+    if ((rc = launch_tables(a, s))) return rc;     // lat-lon rows (and closed-form tables for tile windows)
+    if (metrics_type == OSSG_F64) return launch_metrics<double>(a, is_whole_grid(q), s);
+    return launch_metrics<float>(a, is_whole_grid(q), s);
+}

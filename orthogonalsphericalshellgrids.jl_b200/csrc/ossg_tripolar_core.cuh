@@ -1,0 +1,340 @@
+// csrc/ossg_tripolar_core.cuh -- per-point / per-cell formulas and index maps of the tripolar
+// constructor, shared by all kernels in ossg_tripolar.cu.
+//
+// Reference rows implemented here:
+//   C0  1-D coordinates                      src/tripolar_grid.jl:76,90,95-97
+//   C1  cofocal ellipse/hyperbola map        src/generate_tripolar_coordinates.jl:53-89
+//   C2  circshift by Nx/4                    src/tripolar_grid.jl:121-130
+//   C3  coordinate halos (zipper +1, periodic x, south halo stays 0)   src/tripolar_grid.jl:137-199
+//   M1  haversine spacings / quadrilateral areas                       src/tripolar_grid_utils.jl:4-45
+//   M2  metric halos (zipper +1 incl. row-Ny overwrite, periodic x)    src/tripolar_grid.jl:230-273
+//   M3  south continuation with lat-lon metrics                        src/tripolar_grid.jl:287-300,336-357
+//
+// The reference materialises C2/C3/M2 as array passes (circshift, 20 fill_halo_regions!, 12
+// deepcopy).  Here they are index maps: every element of every padded output array is a pure
+// function of a *source* interior index, so a halo element is evaluated at its source -- which
+// yields the same bits as copying -- and a rank can build any window of the global padded
+// arrays without communication.
+#pragma once
+
+#include "ossg_math.cuh"
+
+namespace ossg {
+
+// staggering ids, in the array order of the C ABI (cc, fc, cf, ff)
+enum Loc : int { CC = 0, FC = 1, CF = 2, FF = 3 };
+OSSG_HD int loc_x(int loc) { return loc & 1; }        // 1 = Face in x
+OSSG_HD int loc_y(int loc) { return (loc >> 1) & 1; } // 1 = Face in y
+
+struct GridDims {
+    int Nx, Ny, Hx, Hy;
+};
+
+// 1-D tables produced by the table kernel (device memory, doubles):
+//   xs[0..4)  : a*sind(lamF), a*cosd(lamF), a*sind(lamC), a*cosd(lamC), each Nx long, indexed by
+//               the POST-circshift i-1 (value taken at the pre-shift index mod1(i - Nx/4, Nx))
+//   ys[0..4)  : cosh(psiF), sinh(psiF), cosh(psiC), sinh(psiC), each Ny long, indexed by j-1
+//   ll        : (Hy+1) rows x 9 lat-lon metrics for j = 1-Hy .. 1 (row r = j + Hy - 1)
+struct Tables {
+    const double* asF; const double* acF; const double* asC; const double* acC;
+    const double* chF; const double* shF; const double* chC; const double* shC;
+    const double* ll;
+};
+enum LLCol : int { LL_DX_FC = 0, LL_DX_CF, LL_DX_FF, LL_DX_CC, LL_DY, LL_AZ_FC, LL_AZ_CF, LL_AZ_FF, LL_AZ_CC, LL_NCOL };
+
+OSSG_HD size_t tables_doubles(int Nx, int Ny, int Hy) { return 4 * (size_t)Nx + 4 * (size_t)Ny + (size_t)LL_NCOL * (Hy + 1); }
+
+// ---------------------------------------------------------------- C0: 1-D coordinates
+// longitude = (-180, 180), Periodic, regular: faces -180 + (i-1) 360/Nx, centres half a cell on
+OSSG_HD double lam_face(int i, int Nx)
+{
+    return m::rational_point(-180.0, (double)(Nx - (i - 1)), 180.0, (double)(i - 1), (double)Nx);
+}
+OSSG_HD double lam_center(int i, int Nx)
+{
+    return m::rational_point(-180.0, (double)(2 * Nx - (2 * i - 1)), 180.0, (double)(2 * i - 1), (double)(2 * Nx));
+}
+// range(south, 90, length = Ny)[j]
+OSSG_HD double phi_center(int j, int Ny, double south)
+{
+    return m::rational_point(south, (double)(Ny - j), 90.0, (double)(j - 1), (double)(Ny - 1));
+}
+OSSG_HD double phi_face(int j, int Ny, double south)
+{
+    const double dphi = phi_center(2, Ny, south) - phi_center(1, Ny, south);   // tripolar_grid.jl:96
+    return phi_center(j, Ny, south) - dphi / 2;                                 // :97
+}
+OSSG_HD double focal_distance(double north_poles_latitude)
+{
+    return m::tand((90.0 - north_poles_latitude) / 2);                          // :76
+}
+// pre-circshift index of post-shift i: new[i] = old[mod1(i - Nx/4, Nx)]        (:121-130)
+OSSG_HD int preshift(int i, int Nx)
+{
+    const int is = i - Nx / 4;
+    return is < 1 ? is + Nx : is;
+}
+
+// (external) LatitudeLongitudeGrid(size, latitude=(south,90), longitude=(-180,180), halo, radius)
+// precomputed metrics of row j in [1-Hy, 1]; Oceananigans' precompute kernel starts at row
+// 2-Hy, so row 1-Hy of the x-spacings and areas keeps its initial 0.
+OSSG_HD void latlon_row(int j, int Nx, int Ny, int Hy, double south, double R, double* row /*[LL_NCOL]*/)
+{
+    const double pi = m::PI_F64;
+    const double d2r = pi / 180.0;
+    const double dlam = 360.0 / (double)Nx;
+    const double dphi = (90.0 - south) / (double)Ny;
+    row[LL_DY] = R * (dphi * d2r);
+    if (j == 1 - Hy) {
+        row[LL_DX_FC] = row[LL_DX_CF] = row[LL_DX_FF] = row[LL_DX_CC] = 0.0;
+        row[LL_AZ_FC] = row[LL_AZ_CF] = row[LL_AZ_FF] = row[LL_AZ_CC] = 0.0;
+        return;
+    }
+    const double phiF_j  = m::rational_point(south, (double)(Ny - (j - 1)), 90.0, (double)(j - 1), (double)Ny);
+    const double phiF_j1 = m::rational_point(south, (double)(Ny - j), 90.0, (double)j, (double)Ny);
+    const double phiC_j  = m::rational_point(south, (double)(2 * Ny - (2 * j - 1)), 90.0, (double)(2 * j - 1), (double)(2 * Ny));
+    const double phiC_jm = m::rational_point(south, (double)(2 * Ny - (2 * j - 3)), 90.0, (double)(2 * j - 3), (double)(2 * Ny));
+    const double rdl = R * (dlam * d2r);
+    row[LL_DX_FC] = rdl * m::cos_rad(pi * phiC_j / 180);
+    row[LL_DX_CC] = row[LL_DX_FC];
+    row[LL_DX_CF] = rdl * m::cos_rad(pi * phiF_j / 180);
+    row[LL_DX_FF] = row[LL_DX_CF];
+    const double r2dl = R * R * (dlam * d2r);
+    row[LL_AZ_FC] = r2dl * (m::sin_rad(pi * phiF_j1 / 180) - m::sin_rad(pi * phiF_j / 180));
+    row[LL_AZ_CC] = row[LL_AZ_FC];
+    row[LL_AZ_CF] = r2dl * (m::sin_rad(pi * phiC_j / 180) - m::sin_rad(pi * phiC_jm / 180));
+    row[LL_AZ_FF] = row[LL_AZ_CF];
+}
+
+// ---------------------------------------------------------------- C1: one staggering point
+// as_i = a*sind(lam1D[ip]), ac_i = a*cosd(lam1D[ip]) (ip = pre-shift index), ch_j/sh_j = cosh/sinh psi_j
+OSSG_HD void tripolar_point(double as_i, double ac_i, double ch_j, double sh_j, bool ip_is_one,
+                            bool ip_le_half, double first_pole_longitude, double& lam, double& phi)
+{
+    const double x = as_i * ch_j;                                             // :67
+    const double y = ac_i * sh_j;                                             // :68
+    const bool on_the_north_pole = (x == 0.0) & (y == 0.0);                   // :74
+    const double north_pole_value = ip_is_one ? -90.0 : 90.0;                 // :75
+    constexpr double m180_pi = -180.0 / m::PI_F64;
+    constexpr double p360_pi = 360.0 / m::PI_F64;
+    double l = on_the_north_pole ? north_pole_value : m180_pi * m::atan_f(y / x);   // :77
+    phi = 90.0 - p360_pi * m::atan_f(sqrt(y * y + x * x));                    // :78
+    l += ip_le_half ? -90.0 : 90.0;                                           // :82
+    l += first_pole_longitude + 90.0;                                         // :86
+    // convert_to_0_360, src/OrthogonalSphericalShellGrids.jl:24 (fmod(l,360) == l when |l| < 360)
+    double r = (fabs(l) < 360.0) ? l : fmod(l, 360.0);
+    r += 360.0;
+    lam = (r < 360.0) ? r : fmod(r, 360.0);
+}
+
+// ---------------------------------------------------------------- C3 / M2 index maps
+// Source of the padded element (I, J) of a field at (locx, locy) after
+//   zipper north fill over i in 1..Nx (src/zipper_boundary_condition.jl:70-138, sign handled by
+//   the caller), then periodic x fill over every row (external Oceananigans ordering).
+// Returns false for the south halo (J < 1), which neither fill touches.
+// `wrapped` is set when the x-Face fold source wrapped around (i' > Nx): the reference takes
+// |sign| there (zipper_boundary_condition.jl:74-75, 91-92).
+OSSG_HD bool halo_source(int locx, int locy, int I, int J, int Nx, int Ny, int& i, int& j, bool& wrapped)
+{
+    wrapped = false;
+    if (J < 1) return false;
+    i = I < 1 ? I + Nx : (I > Nx ? I - Nx : I);
+    j = J;
+    const bool north = J > Ny;
+    const bool redundant = (J == Ny) && (locy == 0) && (i > Nx / 2);   // row-Ny overwrite, :102,135
+    if (north || redundant) {
+        int ip = locx ? Nx - i + 2 : Nx - i + 1;
+        if (ip > Nx) { ip -= Nx; wrapped = true; }
+        i = ip;
+        if (north) {
+            const int d = J - Ny;
+            j = locy ? Ny - d + 1 : Ny - d;
+        }
+    }
+    return true;
+}
+
+// coordinate value (lam, phi) of staggering `loc` at padded global index (I, J), straight from
+// the tables (C1 + C2 + C3).  South halo: 0.
+OSSG_HD void coord_at(const Tables& tb, const GridDims& g, double first_pole_longitude, int loc, int I, int J,
+                      double& lam, double& phi)
+{
+    int i, j; bool wrapped;
+    if (!halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, i, j, wrapped)) { lam = 0.0; phi = 0.0; return; }
+    const int ip = preshift(i, g.Nx);
+    const bool fx = loc_x(loc) != 0, fy = loc_y(loc) != 0;
+    const double as_i = fx ? tb.asF[i - 1] : tb.asC[i - 1];
+    const double ac_i = fx ? tb.acF[i - 1] : tb.acC[i - 1];
+    const double ch_j = fy ? tb.chF[j - 1] : tb.chC[j - 1];
+    const double sh_j = fy ? tb.shF[j - 1] : tb.shC[j - 1];
+    tripolar_point(as_i, ac_i, ch_j, sh_j, ip == 1, ip <= g.Nx / 2, first_pole_longitude, lam, phi);
+}
+
+// ---------------------------------------------------------------- M1 formulas
+// (external) Distances.jl 0.10 Haversine()(x, y): x = (lam, phi) of the first point.  phi1r, phi2r
+// are deg2rad(phi) = phi * (pi/180), c1, c2 their cosines (hoisted per point by the tile kernel).
+constexpr double D2R = m::PI_F64 / 180.0;
+
+OSSG_HD double haversine_pre(double lam_x, double phi1r, double c1, double lam_y, double phi2r, double c2, double radius)
+{
+    const double dlam = (lam_y - lam_x) * D2R;
+    const double dphi = phi2r - phi1r;
+    const double s1 = m::sin_rad(dphi / 2);
+    const double s2 = m::sin_rad(dlam / 2);
+    const double a = s1 * s1 + c1 * c2 * (s2 * s2);
+    double r = sqrt(a);
+    if (!(r < 1.0)) r = (r != r) ? r : 1.0;                 // min(sqrt(a), 1)
+    return 2 * (radius * m::asin_f(r));
+}
+
+struct Vec3 { double x, y, z; };
+
+// (external) Oceananigans.Grids.lat_lon_to_cartesian(lat, lon, 1)
+OSSG_HD Vec3 lat_lon_to_cartesian(double lat, double lon)
+{
+    const double cl = m::cosd(lat);
+    Vec3 v;
+    v.x = m::cosd(lon) * cl;
+    v.y = m::sind(lon) * cl;
+    v.z = m::sind(lat);
+    return v;
+}
+OSSG_HD double dot3(const Vec3& a, const Vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+OSSG_HD Vec3 cross3(const Vec3& a, const Vec3& b)
+{
+    Vec3 c;
+    c.x = a.y * b.z - a.z * b.y;
+    c.y = a.z * b.x - a.x * b.z;
+    c.z = a.x * b.y - a.y * b.x;
+    return c;
+}
+// (external) Oceananigans.Grids.spherical_area_quadrilateral: half the sum of the four triangles
+// (a,b,c), (a,b,d), (a,c,d), (b,c,d); triangle area = 2 atan(|a1.(a2 x a3)| / (1 + a1.a2 + a2.a3 + a1.a3)).
+// The six pair dot products and three cross products are shared between the triangles; each
+// value is produced by the same expression as in the unshared form.
+OSSG_HD double spherical_area_quadrilateral(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d)
+{
+    const double ab = dot3(a, b), ac = dot3(a, c), ad = dot3(a, d);
+    const double bc = dot3(b, c), bd = dot3(b, d), cd = dot3(c, d);
+    const Vec3 bxc = cross3(b, c), bxd = cross3(b, d), cxd = cross3(c, d);
+    const double t_abc = fabs(dot3(a, bxc)) / (1 + ab + bc + ac);
+    const double t_abd = fabs(dot3(a, bxd)) / (1 + ab + bd + ad);
+    const double t_acd = fabs(dot3(a, cxd)) / (1 + ac + cd + ad);
+    const double t_bcd = fabs(dot3(b, cxd)) / (1 + bc + cd + bd);
+    return 0.5 * (2 * m::atan_f(t_abc) + 2 * m::atan_f(t_abd) + 2 * m::atan_f(t_acd) + 2 * m::atan_f(t_bcd));
+}
+
+// metric ids in C-ABI order
+enum Metric : int { DX_CC = 0, DX_FC, DX_CF, DX_FF, DY_CC, DY_CF, DY_FC, DY_FF, AZ_CC, AZ_FC, AZ_CF, AZ_FF, N_METRIC };
+// staggering class of each metric (which halo map applies to it in M2)
+OSSG_HD int metric_loc(int mtr)
+{
+    switch (mtr) {
+    case DX_CC: case DY_CC: case AZ_CC: return CC;
+    case DX_FC: case DY_FC: case AZ_FC: return FC;
+    case DX_CF: case DY_CF: case AZ_CF: return CF;
+    default: return FF;
+    }
+}
+
+// M1 at interior cell (i, j) through a coordinate accessor
+//   acc(loc, I, J, lam, phi)  -> padded coordinate values.
+// `mask` selects which staggering classes are wanted (bit loc); unwanted outputs are left alone.
+template <class Acc>
+OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask, double* out /*[N_METRIC]*/)
+{
+    double l0, p0, l1, p1, l2, p2, l3, p3;
+    const bool want_cc = mask & (1u << CC), want_fc = mask & (1u << FC), want_cf = mask & (1u << CF), want_ff = mask & (1u << FF);
+    // FF points: (i,j) (i+1,j) (i+1,j+1) (i,j+1)     -> dx_cf, dy_fc, az_cc
+    if (want_cf || want_fc || want_cc) {
+        acc(FF, i, j, l0, p0); acc(FF, i + 1, j, l1, p1); acc(FF, i + 1, j + 1, l2, p2); acc(FF, i, j + 1, l3, p3);
+        const double r0 = p0 * D2R, r1 = p1 * D2R, r3 = p3 * D2R;
+        const double c0 = m::cos_rad(r0);
+        if (want_cf) out[DX_CF] = haversine_pre(l1, r1, m::cos_rad(r1), l0, r0, c0, R);      // utils.jl:15
+        if (want_fc) out[DY_FC] = haversine_pre(l3, r3, m::cos_rad(r3), l0, r0, c0, R);      // :19
+        if (want_cc) {
+            const Vec3 a = lat_lon_to_cartesian(p0, l0), b = lat_lon_to_cartesian(p1, l1);
+            const Vec3 c = lat_lon_to_cartesian(p2, l2), d = lat_lon_to_cartesian(p3, l3);
+            out[AZ_CC] = spherical_area_quadrilateral(a, b, c, d) * (R * R);               // :23-28
+        }
+    }
+    // CC points: (i,j) (i-1,j) (i,j-1) (i-1,j-1)     -> dx_fc, dy_cf, az_ff
+    if (want_fc || want_cf || want_ff) {
+        acc(CC, i, j, l0, p0); acc(CC, i - 1, j, l1, p1); acc(CC, i, j - 1, l2, p2); acc(CC, i - 1, j - 1, l3, p3);
+        const double r0 = p0 * D2R, r1 = p1 * D2R, r2 = p2 * D2R;
+        const double c0 = m::cos_rad(r0);
+        if (want_fc) out[DX_FC] = haversine_pre(l0, r0, c0, l1, r1, m::cos_rad(r1), R);      // :14
+        if (want_cf) out[DY_CF] = haversine_pre(l0, r0, c0, l2, r2, m::cos_rad(r2), R);      // :20
+        if (want_ff) {
+            const Vec3 a = lat_lon_to_cartesian(p3, l3), b = lat_lon_to_cartesian(p2, l2);
+            const Vec3 c = lat_lon_to_cartesian(p0, l0), d = lat_lon_to_cartesian(p1, l1);
+            out[AZ_FF] = spherical_area_quadrilateral(a, b, c, d) * (R * R);               // :38-43
+        }
+    }
+    // FC points: (i,j) (i+1,j) (i,j-1)               -> dx_cc, dy_ff
+    if (want_cc || want_ff) {
+        acc(FC, i, j, l0, p0);
+        const double r0 = p0 * D2R;
+        const double c0 = m::cos_rad(r0);
+        if (want_cc) {
+            acc(FC, i + 1, j, l1, p1);
+            const double r1 = p1 * D2R;
+            out[DX_CC] = haversine_pre(l1, r1, m::cos_rad(r1), l0, r0, c0, R);              // :13
+        }
+        if (want_ff) {
+            acc(FC, i, j - 1, l2, p2);
+            const double r2 = p2 * D2R;
+            out[DY_FF] = haversine_pre(l0, r0, c0, l2, r2, m::cos_rad(r2), R);              // :21
+        }
+    }
+    // CF points: (i,j) (i-1,j) (i,j+1)               -> dx_ff, dy_cc
+    if (want_ff || want_cc) {
+        acc(CF, i, j, l0, p0);
+        const double r0 = p0 * D2R;
+        const double c0 = m::cos_rad(r0);
+        if (want_ff) {
+            acc(CF, i - 1, j, l1, p1);
+            const double r1 = p1 * D2R;
+            out[DX_FF] = haversine_pre(l0, r0, c0, l1, r1, m::cos_rad(r1), R);              // :16
+        }
+        if (want_cc) {
+            acc(CF, i, j + 1, l3, p3);
+            const double r3 = p3 * D2R;
+            out[DY_CC] = haversine_pre(l3, r3, m::cos_rad(r3), l0, r0, c0, R);              // :18
+        }
+    }
+    if (want_fc) out[AZ_FC] = out[DY_FC] * out[DX_FC];                                     // :34
+    if (want_cf) out[AZ_CF] = out[DY_CF] * out[DX_CF];                                     // :35
+}
+
+// Full value of the 12 metrics at padded global element (I, J): M1 evaluated at each class's M2
+// source, or the lat-lon row for J <= 1 (M3).  Generic (slow) path used for halo elements and by
+// tests; the tile kernel handles the bulk.
+template <class Acc>
+OSSG_HD void metrics_at_padded(const Acc& acc, const Tables& tb, const GridDims& g, double R, int I, int J,
+                               double* out /*[N_METRIC]*/)
+{
+    if (J <= 1) {
+        const double* row = tb.ll + (size_t)(J + g.Hy - 1) * LL_NCOL;
+        out[DX_FF] = row[LL_DX_FF]; out[DX_FC] = row[LL_DX_FC]; out[DX_CF] = row[LL_DX_CF]; out[DX_CC] = row[LL_DX_CC];
+        out[DY_FF] = row[LL_DY];    out[DY_FC] = row[LL_DY];    out[DY_CF] = row[LL_DY];    out[DY_CC] = row[LL_DY];
+        out[AZ_FF] = row[LL_AZ_FF]; out[AZ_FC] = row[LL_AZ_FC]; out[AZ_CF] = row[LL_AZ_CF]; out[AZ_CC] = row[LL_AZ_CC];
+        return;
+    }
+    int si[4], sj[4];
+    for (int loc = 0; loc < 4; ++loc) {
+        bool wrapped;
+        halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, si[loc], sj[loc], wrapped);
+    }
+    unsigned done = 0;
+    for (int loc = 0; loc < 4; ++loc) {
+        if (done & (1u << loc)) continue;
+        unsigned mask = 0;
+        for (int l2 = loc; l2 < 4; ++l2)
+            if (!(done & (1u << l2)) && si[l2] == si[loc] && sj[l2] == sj[loc]) mask |= 1u << l2;
+        metrics_cell(acc, si[loc], sj[loc], R, mask, out);
+        done |= mask;
+    }
+}
+
+}  // namespace ossg

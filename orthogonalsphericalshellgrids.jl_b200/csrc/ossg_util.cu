@@ -1,0 +1,109 @@
+// csrc/ossg_util.cu -- measurement / test utilities exported next to the product entry points:
+// deterministic synthetic fields and an FP64 FMA rate probe that gives
+// the roofline denominator for the coordinate/metric kernels (MEASURED_PEAKS.json has no FP64
+// figure).  Nothing here is on the reference's path.
+#include "ossg_common.cuh"
+
+namespace ossg {
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// value in [-1, 1) with 24 random bits, exactly representable in FP32 and FP64
+__device__ __forceinline__ double hash_value(uint64_t seed, int gi, int gj, int k)
+{
+    const uint64_t key = ((uint64_t)(uint32_t)gi) | ((uint64_t)(uint32_t)gj << 21) | ((uint64_t)(uint32_t)k << 42);
+    const uint64_t h = splitmix64(seed ^ splitmix64(key));
+    return (double)(int64_t)(h >> 40) * (1.0 / 8388608.0) - 1.0;
+}
+
+template <typename T> __device__ __forceinline__ T poison();
+template <> __device__ __forceinline__ double poison<double>() { return __longlong_as_double(0x7ff8dead0000beefll); }
+template <> __device__ __forceinline__ float poison<float>() { return __int_as_float(0x7fc0dead); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) synth_kernel(ossg_field_desc f, uint64_t seed, int gi0, int gj0)
+{
+    const int sx = f.Nx + 2 * f.Hx, sy = f.Ny + 2 * f.Hy;
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;                       // row = kz * sy + jy
+    if (ix >= sx) return;
+    const int kz = row / sy, jy = row - kz * sy;
+    const int i = ix - f.Hx + 1, j = jy - f.Hy + 1, k = kz - f.Hz + 1;
+    const bool inside = i >= 1 && i <= f.Nx && j >= 1 && j <= f.Ny && k >= 1 && k <= f.Nz;
+    T* c = static_cast<T*>(f.data);
+    c[((size_t)kz * sy + jy) * sx + ix] = inside ? (T)hash_value(seed, gi0 + i - 1, gj0 + j - 1, k) : poison<T>();
+}
+
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double* sink)
+{
+    // 8 independent FMA chains per thread: enough ILP to cover the FP64 pipe latency
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 0.125, a2 = a0 + 0.25, a3 = a0 + 0.375;
+    double a4 = a0 + 0.5, a5 = a0 + 0.625, a6 = a0 + 0.75, a7 = a0 + 0.875;
+    const double m = 0.999999999, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) sink[0] = r;                  // never true; keeps the chains alive
+}
+
+}  // namespace ossg
+
+using namespace ossg;
+
+extern "C" int ossg_synth_field(const ossg_field_desc* f, uint64_t seed, int32_t gi0, int32_t gj0, void* stream)
+{
+    if (!f || !f->data) return set_error(OSSG_EINVAL, "field or its data is NULL");
+    if (f->elem_type != OSSG_F64 && f->elem_type != OSSG_F32) return set_error(OSSG_EINVAL, "elem_type must be OSSG_F64 or OSSG_F32");
+    const long long sx = f->Nx + 2 * f->Hx, rows = (long long)(f->Ny + 2 * f->Hy) * (f->Nz + 2 * f->Hz);
+    if (sx <= 0 || rows <= 0) return set_error(OSSG_EINVAL, "empty field");
+    // rows can exceed 65535: loop over chunks of rows by offsetting the data pointer per level
+    const int sy = f->Ny + 2 * f->Hy, sz = f->Nz + 2 * f->Hz;
+    const int levels_per_launch = 65535 / sy > 0 ? 65535 / sy : 0;
+    if (levels_per_launch == 0) return set_error(OSSG_EINVAL, "Ny + 2Hy = %d too large for the synthetic-field kernel", sy);
+    for (int kz0 = 0; kz0 < sz; kz0 += levels_per_launch) {
+        const int nl = sz - kz0 < levels_per_launch ? sz - kz0 : levels_per_launch;
+        ossg_field_desc g = *f;
+        // shift the level origin: treat levels [kz0, kz0+nl) as a sub-field whose first level has k = kz0 - Hz + 1
+        const size_t esz = f->elem_type == OSSG_F64 ? 8 : 4;
+        g.data = static_cast<char*>(f->data) + (size_t)kz0 * sy * sx * esz;
+        g.Hz = f->Hz - kz0;            // k = kz - g.Hz + 1 = (kz + kz0) - Hz + 1
+        dim3 grid(ceil_div(sx, 256), nl * sy);
+        if (f->elem_type == OSSG_F64) synth_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(g, seed, gi0, gj0);
+        else synth_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(g, seed, gi0, gj0);
+        OSSG_LAUNCH_CHECK("synth_kernel");
+    }
+    return 0;
+}
+
+extern "C" int ossg_fp64_peak_probe(int iters, float* ms, double* flops, void* stream)
+{
+    if (iters < 1 || !ms || !flops) return set_error(OSSG_EINVAL, "bad arguments");
+    int dev = 0, sms = 0;
+    OSSG_CUDA_TRY(cudaGetDevice(&dev));
+    OSSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256;
+    double* sink = nullptr;
+    OSSG_CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    OSSG_CUDA_TRY(cudaEventCreate(&e0));
+    OSSG_CUDA_TRY(cudaEventCreate(&e1));
+    cudaStream_t s = as_stream(stream);
+    fp64_probe_kernel<<<blocks, threads, 0, s>>>(iters / 8 + 1, sink);      // warm-up
+    OSSG_CUDA_TRY(cudaEventRecord(e0, s));
+    fp64_probe_kernel<<<blocks, threads, 0, s>>>(iters, sink);
+    OSSG_CUDA_TRY(cudaEventRecord(e1, s));
+    OSSG_CUDA_TRY(cudaEventSynchronize(e1));
+    OSSG_CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+    *flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    OSSG_LAUNCH_CHECK("fp64_probe_kernel");
+    return 0;
+}

@@ -1,0 +1,270 @@
+// csrc/ossg_zipper.cu -- zipper (north-fold) halo fill on sm_100a.
+//
+// Reference: src/zipper_boundary_condition.jl:70-155.  There, Oceananigans launches one thread
+// per (i, k) which loops j = 1..Hy.  Here one thread moves one element: the destination row
+// segment is contiguous in i and the source segment is the same span read in reverse, so a warp
+// reads one contiguous 32-element span and writes one (a warp-cooperative gather across the
+// fold); rows x levels x fields are spread over blockIdx.y/z so a batch of fields is ONE launch.
+// The operation is a copy with a sign: bit-exact by construction.
+#include "ossg_common.cuh"
+
+namespace ossg {
+
+constexpr int MAX_BATCH = 24;          // ossg_field_desc is 64 B; 24 of them fit kernel parameter space comfortably
+constexpr int ZB = 256;                // threads per block along i
+
+struct FieldBatch {
+    ossg_field_desc f[MAX_BATCH];
+    int n;
+};
+
+template <typename T>
+__device__ __forceinline__ T apply_sign(T v, double s)
+{
+    if (s == 1.0) return v;
+    if (s == -1.0) return -v;
+    return (T)(s * (double)v);
+}
+
+// rows handled per level: Hy halo rows (+1 for y-Center: the redundant half of row Ny)
+__device__ __host__ inline int fold_rows(const ossg_field_desc& f) { return f.Hy + (f.locy == OSSG_CENTER ? 1 : 0); }
+
+template <typename T>
+__device__ __forceinline__ void zipper_element(const ossg_field_desc& f, int i /*1..Nx*/, int r, int kk)
+{
+    const int Nx = f.Nx, Ny = f.Ny;
+    const size_t sx = (size_t)(Nx + 2 * f.Hx), sxy = sx * (size_t)(Ny + 2 * f.Hy);
+    T* c = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
+    double s = f.sign;
+    int ip = f.locx ? Nx - i + 2 : Nx - i + 1;                 // zipper_boundary_condition.jl:73,90,110,125
+    if (ip > Nx) { s = fabs(s); ip -= Nx; }                     // :74-75, :91-92
+    int jd, js;
+    if (r < f.Hy) {                                            // halo row j = r + 1
+        jd = Ny + r + 1;
+        js = f.locy ? Ny - r : Ny - r - 1;                      // :80, :97, :115, :130
+    } else {                                                   // redundant part of row Ny, :102, :135
+        if (i <= Nx / 2) return;
+        jd = Ny; js = Ny;
+    }
+    const T v = c[(size_t)(js + f.Hy - 1) * sx + (ip + f.Hx - 1)];
+    c[(size_t)(jd + f.Hy - 1) * sx + (i + f.Hx - 1)] = apply_sign(v, s);
+}
+
+__global__ void __launch_bounds__(ZB) zipper_kernel(const __grid_constant__ FieldBatch b)
+{
+    const ossg_field_desc& f = b.f[blockIdx.z];
+    const int i = blockIdx.x * ZB + threadIdx.x + 1;
+    if (i > f.Nx) return;
+    const int rows = fold_rows(f);
+    const int row = blockIdx.y;                 // row = kk * rows + r
+    if (row >= rows * f.nk) return;
+    const int kk = row / rows, r = row - kk * rows;
+    if (f.elem_type == OSSG_F64) zipper_element<double>(f, i, r, kk);
+    else zipper_element<float>(f, i, r, kk);
+}
+
+// periodic west/east fill over the whole (y, z) parent extent (external Oceananigans periodic
+// halo kernel); run after the zipper so the NW/NE corners carry the folded values.
+template <typename T>
+__device__ __forceinline__ void periodic_element(const ossg_field_desc& f, int h /*0..2Hx-1*/, size_t row)
+{
+    const size_t sx = (size_t)(f.Nx + 2 * f.Hx);
+    T* c = static_cast<T*>(f.data) + row * sx;
+    if (h < f.Hx) c[h] = c[f.Nx + h];                            // west halo <- east interior
+    else c[f.Nx + h] = c[h];                                     // east halo <- west interior  (h in Hx..2Hx-1)
+}
+
+__global__ void __launch_bounds__(ZB) periodic_x_kernel(const __grid_constant__ FieldBatch b)
+{
+    const ossg_field_desc& f = b.f[blockIdx.z];
+    const int w = 2 * f.Hx;
+    const size_t rows = (size_t)(f.Ny + 2 * f.Hy) * (size_t)(f.Nz + 2 * f.Hz);
+    const size_t t = (size_t)blockIdx.x * ZB + threadIdx.x;
+    if (t >= rows * w) return;
+    const size_t row = t / w;
+    const int h = (int)(t - row * w);
+    if (f.elem_type == OSSG_F64) periodic_element<double>(f, h, row);
+    else periodic_element<float>(f, h, row);
+}
+
+// ------------------------------------------------------------------ (x,y)-partition fold: pack / unpack
+struct FoldArgs {
+    ossg_field_desc f;
+    ossg_fold_window w;
+    void* buffer;
+};
+
+template <typename T>
+__device__ __forceinline__ void pack_element(const FoldArgs& a, int c, int r, int kk)
+{
+    const ossg_field_desc& f = a.f;
+    const size_t sx = (size_t)(f.Nx + 2 * f.Hx), sxy = sx * (size_t)(f.Ny + 2 * f.Hy);
+    const int rows = fold_rows(f);
+    const int li = a.w.src_i0 + c - a.w.i0 + 1;                 // local 1-based column of global src_i0 + c
+    const int js = (r < f.Hy) ? (f.locy ? f.Ny - r : f.Ny - r - 1) : f.Ny;
+    const T* src = static_cast<const T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
+    static_cast<T*>(a.buffer)[((size_t)kk * rows + r) * a.w.src_n + c] = src[(size_t)(js + f.Hy - 1) * sx + (li + f.Hx - 1)];
+}
+
+__global__ void __launch_bounds__(ZB) fold_pack_kernel(const __grid_constant__ FoldArgs a)
+{
+    const int c = blockIdx.x * ZB + threadIdx.x;
+    if (c >= a.w.src_n) return;
+    const int rows = fold_rows(a.f);
+    const int row = blockIdx.y;
+    const int kk = row / rows, r = row - kk * rows;
+    if (a.f.elem_type == OSSG_F64) pack_element<double>(a, c, r, kk);
+    else pack_element<float>(a, c, r, kk);
+}
+
+template <typename T>
+__device__ __forceinline__ void unpack_element(const FoldArgs& a, int li /*1..nx local*/, int r, int kk)
+{
+    const ossg_field_desc& f = a.f;
+    const int gNx = a.w.gNx;
+    const int i = a.w.i0 + li - 1;                               // global destination column
+    double s = f.sign;
+    int ip = f.locx ? gNx - i + 2 : gNx - i + 1;
+    if (ip > gNx) { s = fabs(s); ip -= gNx; }
+    const int c = ip - a.w.src_i0;
+    if (c < 0 || c >= a.w.src_n) return;                         // that column comes from another message
+    const size_t sx = (size_t)(f.Nx + 2 * f.Hx), sxy = sx * (size_t)(f.Ny + 2 * f.Hy);
+    const int rows = fold_rows(f);
+    int jd;
+    if (r < f.Hy) jd = f.Ny + r + 1;
+    else { if (i <= gNx / 2) return; jd = f.Ny; }
+    T* dst = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
+    const T v = static_cast<const T*>(a.buffer)[((size_t)kk * rows + r) * a.w.src_n + c];
+    dst[(size_t)(jd + f.Hy - 1) * sx + (li + f.Hx - 1)] = apply_sign(v, s);
+}
+
+__global__ void __launch_bounds__(ZB) fold_unpack_kernel(const __grid_constant__ FoldArgs a)
+{
+    const int li = blockIdx.x * ZB + threadIdx.x + 1;
+    if (li > a.f.Nx) return;
+    const int rows = fold_rows(a.f);
+    const int row = blockIdx.y;
+    const int kk = row / rows, r = row - kk * rows;
+    if (a.f.elem_type == OSSG_F64) unpack_element<double>(a, li, r, kk);
+    else unpack_element<float>(a, li, r, kk);
+}
+
+// ------------------------------------------------------------------ host side
+static int check_field(const ossg_field_desc& in, ossg_field_desc& f, int idx)
+{
+    f = in;
+    if (!f.data) return set_error(OSSG_EINVAL, "field %d: data is NULL", idx);
+    if (f.elem_type != OSSG_F64 && f.elem_type != OSSG_F32) return set_error(OSSG_EINVAL, "field %d: elem_type must be OSSG_F64 or OSSG_F32", idx);
+    const size_t esz = f.elem_type == OSSG_F64 ? 8 : 4;
+    if (reinterpret_cast<uintptr_t>(f.data) % esz) return set_error(OSSG_EALIGN, "field %d: data is not %zu-byte aligned", idx, esz);
+    if (f.Nx < 2 || f.Ny < 2 || f.Nz < 1) return set_error(OSSG_EINVAL, "field %d: size (%d, %d, %d) too small", idx, f.Nx, f.Ny, f.Nz);
+    if (f.Hx < 0 || f.Hy < 0 || f.Hz < 0) return set_error(OSSG_EINVAL, "field %d: negative halo", idx);
+    if (f.Hy > f.Ny - 1 || f.Hx > f.Nx) return set_error(OSSG_EHALO, "field %d: halo (%d, %d) too large for size (%d, %d)", idx, f.Hx, f.Hy, f.Nx, f.Ny);
+    if ((f.locx != OSSG_CENTER && f.locx != OSSG_FACE) || (f.locy != OSSG_CENTER && f.locy != OSSG_FACE))
+        return set_error(OSSG_ELOCATION, "field %d: location codes must be OSSG_CENTER or OSSG_FACE", idx);
+    if (f.nk == 0) { f.k0 = f.Hz; f.nk = f.Nz; }
+    if (f.k0 < 0 || f.nk < 0 || f.k0 + f.nk > f.Nz + 2 * f.Hz) return set_error(OSSG_EINVAL, "field %d: k-range [%d, %d) outside the parent array", idx, f.k0, f.k0 + f.nk);
+    return 0;
+}
+
+static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_periodic, cudaStream_t s)
+{
+    if (!fields || n < 0) return set_error(OSSG_EINVAL, "fields is NULL or nfields < 0");
+    for (int base = 0; base < n; base += MAX_BATCH) {
+        FieldBatch b;
+        b.n = n - base < MAX_BATCH ? n - base : MAX_BATCH;
+        int gx = 0, gy = 0;
+        size_t pmax = 0;
+        for (int k = 0; k < b.n; ++k) {
+            const ossg_field_desc& in = fields[base + k];
+            if (in.Nx % 2 != 0) return set_error(OSSG_EODD_NX, "field %d: Nx must be even for the fold", base + k);
+            int rc = check_field(in, b.f[k], base + k);
+            if (rc) return rc;
+            if (b.f[k].Hy == 0) continue;
+            gx = max(gx, ceil_div(b.f[k].Nx, ZB));
+            gy = max(gy, fold_rows(b.f[k]) * b.f[k].nk);
+            const size_t prow = (size_t)(b.f[k].Ny + 2 * b.f[k].Hy) * (size_t)(b.f[k].Nz + 2 * b.f[k].Hz) * (size_t)(2 * b.f[k].Hx);
+            pmax = pmax > prow ? pmax : prow;
+        }
+        if (gx > 0 && gy > 0) {
+            if (gy > 65535) return set_error(OSSG_EINVAL, "too many (row, level) pairs for one launch: %d", gy);
+            zipper_kernel<<<dim3(gx, gy, b.n), ZB, 0, s>>>(b);
+            OSSG_LAUNCH_CHECK("zipper_kernel");
+        }
+        if (with_periodic && pmax > 0) {
+            periodic_x_kernel<<<dim3(ceil_div((long long)pmax, ZB), 1, b.n), ZB, 0, s>>>(b);
+            OSSG_LAUNCH_CHECK("periodic_x_kernel");
+        }
+    }
+    return 0;
+}
+
+}  // namespace ossg
+
+using namespace ossg;
+
+extern "C" int ossg_zipper_fill(const ossg_field_desc* f, void* stream)
+{
+    return launch_zipper_batch(f, 1, false, as_stream(stream));
+}
+
+extern "C" int ossg_zipper_fill_batch(const ossg_field_desc* f, int nfields, void* stream)
+{
+    return launch_zipper_batch(f, nfields, false, as_stream(stream));
+}
+
+extern "C" int ossg_fill_halo_regions_batch(const ossg_field_desc* f, int nfields, void* stream)
+{
+    return launch_zipper_batch(f, nfields, true, as_stream(stream));
+}
+
+static int check_fold(const ossg_field_desc* fin, const ossg_fold_window* w, ossg_field_desc& f)
+{
+    if (!fin || !w) return set_error(OSSG_EINVAL, "field or window is NULL");
+    int rc = check_field(*fin, f, 0);
+    if (rc) return rc;
+    if (w->gNx < 2 || w->gNx % 2) return set_error(OSSG_EODD_NX, "global Nx must be even, got %d", w->gNx);
+    if (w->nx != f.Nx) return set_error(OSSG_EWINDOW, "window nx (%d) differs from the field's local Nx (%d)", w->nx, f.Nx);
+    if (w->i0 < 1 || w->i0 + w->nx - 1 > w->gNx) return set_error(OSSG_EWINDOW, "local columns [%d, %d] outside 1..%d", w->i0, w->i0 + w->nx - 1, w->gNx);
+    if (w->src_n < 0 || w->src_i0 < 1 || w->src_i0 + w->src_n - 1 > w->gNx) return set_error(OSSG_EWINDOW, "source columns [%d, %d) outside 1..%d", w->src_i0, w->src_i0 + w->src_n, w->gNx);
+    return 0;
+}
+
+extern "C" size_t ossg_fold_buffer_elems(const ossg_field_desc* fin, const ossg_fold_window* w)
+{
+    ossg_field_desc f;
+    if (check_fold(fin, w, f)) return 0;
+    return (size_t)f.nk * fold_rows(f) * (size_t)w->src_n;
+}
+
+extern "C" int ossg_fold_pack(const ossg_field_desc* fin, const ossg_fold_window* w, void* buffer, void* stream)
+{
+    FoldArgs a;
+    int rc = check_fold(fin, w, a.f);
+    if (rc) return rc;
+    if (!buffer) return set_error(OSSG_EINVAL, "buffer is NULL");
+    // the packed columns must exist in the local array (interior or x-halo)
+    const int lo = w->src_i0 - w->i0 + 1, hi = lo + w->src_n - 1;
+    if (w->src_n > 0 && (lo < 1 - a.f.Hx || hi > a.f.Nx + a.f.Hx))
+        return set_error(OSSG_EWINDOW, "source columns [%d, %d] are not held by this rank (local %d..%d)", w->src_i0, w->src_i0 + w->src_n - 1, lo, hi);
+    a.w = *w; a.buffer = buffer;
+    const int gy = fold_rows(a.f) * a.f.nk;
+    if (w->src_n == 0 || gy == 0) return 0;
+    fold_pack_kernel<<<dim3(ceil_div(w->src_n, ZB), gy), ZB, 0, as_stream(stream)>>>(a);
+    OSSG_LAUNCH_CHECK("fold_pack_kernel");
+    return 0;
+}
+
+extern "C" int ossg_fold_unpack(const ossg_field_desc* fin, const ossg_fold_window* w, const void* buffer, void* stream)
+{
+    FoldArgs a;
+    int rc = check_fold(fin, w, a.f);
+    if (rc) return rc;
+    if (!buffer) return set_error(OSSG_EINVAL, "buffer is NULL");
+    a.w = *w; a.buffer = const_cast<void*>(buffer);
+    const int gy = fold_rows(a.f) * a.f.nk;
+    if (w->src_n == 0 || gy == 0) return 0;
+    fold_unpack_kernel<<<dim3(ceil_div(a.f.Nx, ZB), gy), ZB, 0, as_stream(stream)>>>(a);
+    OSSG_LAUNCH_CHECK("fold_unpack_kernel");
+    return 0;
+}

@@ -1,0 +1,320 @@
+"""Distributed tripolar grid and halo exchange: one process per GPU, torch.distributed (NCCL over
+NVLink on the GPU box, gloo in CPU tests) for the plumbing.
+
+Mirrors:
+  TripolarGrid(arch::Distributed, FT; halo, kwargs...)      src/distributed_tripolar_grid.jl:24-110
+  partition_tripolar_metric                                 src/distributed_tripolar_grid.jl:112-120
+  reconstruct_global_grid                                   src/distributed_tripolar_grid.jl:201-226
+The reference supports Y slabs only (:28-31) and builds the whole global grid on every rank (:36)
+before slicing.  Here every rank evaluates only its own window of the global padded arrays
+(ossg_tripolar_build with a tile window; zero communication), and the partition may also split x:
+the fold then crosses ranks and is served by a pack -> NCCL send/recv -> unpack exchange between
+mirror ranks of the top row (new relative to the reference; its correctness spec is "every
+rank's tile equals the same slice of the serial result").
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ARRAY_NAMES, FoldWindow
+from .grids import (GPU, Float64, OffsetArray, OrthogonalSphericalShellGrid, R_Earth, Tripolar,
+                    _generate_z, _require_cuda, build_arrays, make_params)
+
+
+@dataclass(frozen=True)
+class Partition:
+    """Oceananigans.DistributedComputations.Partition(x, y): number of ranks per direction."""
+    x: int = 1
+    y: int = 1
+
+
+def local_sizes(N: int, R: int) -> list:
+    """Equal partition, the last rank takes the remainder (external: Oceananigans local_size;
+    src/distributed_tripolar_grid.jl:41-49)."""
+    base = N // R
+    sizes = [base] * R
+    sizes[-1] += N - base * R
+    return sizes
+
+
+class Distributed:
+    """Oceananigans.Distributed(child_architecture; partition).  Rank r sits at
+    (rx, ry) = (r // Ry, r % Ry) (Oceananigans rank2index: x slowest)."""
+
+    def __init__(self, child_architecture=None, partition: Optional[Partition] = None,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, group=None,
+                 y_slabs_only: bool = False):
+        import torch.distributed as dist
+        self.child_architecture = child_architecture if child_architecture is not None else GPU()
+        self.group = group
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        if world_size is None:
+            world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.local_rank = int(rank)
+        self.world_size = int(world_size)
+        self.partition = partition if partition is not None else Partition(1, self.world_size)
+        if self.partition.x * self.partition.y != self.world_size:
+            raise ValueError(f"partition {self.partition} does not match {self.world_size} ranks")
+        if y_slabs_only and self.partition.x != 1:     # src/distributed_tripolar_grid.jl:30-31
+            raise ValueError("The tripolar grid is supported only on a Y-partitioning configuration")
+        self.Rx, self.Ry = self.partition.x, self.partition.y
+        self.rx, self.ry = self.local_rank // self.Ry, self.local_rank % self.Ry
+
+    def rank_of(self, rx: int, ry: int) -> int:
+        return rx * self.Ry + ry
+
+    def is_top_row(self) -> bool:
+        return self.ry == self.Ry - 1
+
+    def torch_device(self):
+        return self.child_architecture.torch_device()
+
+    def __repr__(self):
+        return f"Distributed({self.child_architecture}, {self.partition}, rank {self.local_rank}/{self.world_size})"
+
+
+def tile_of(Nx: int, Ny: int, Rx: int, Ry: int, rx: int, ry: int):
+    """(i0, j0, nx, ny) of rank (rx, ry): jstart = 1 + sum(nlocal[1:rank]) (:47)."""
+    sx, sy = local_sizes(Nx, Rx), local_sizes(Ny, Ry)
+    return 1 + sum(sx[:rx]), 1 + sum(sy[:ry]), sx[rx], sy[ry]
+
+
+def DistributedTripolarGrid(arch: Distributed, FT=Float64, *, size, southernmost_latitude=-80, halo=(4, 4, 4),
+                            radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70):
+    Nx, Ny, Nz = (int(s) for s in size)
+    Hx, Hy, Hz = (int(h) for h in halo)
+    if Nx % 2 == 1:
+        raise ValueError("The number of cells in the longitude dimension should be even!")
+    i0, j0, nx, ny = tile_of(Nx, Ny, arch.Rx, arch.Ry, arch.rx, arch.ry)
+    if ny - 1 < Hy and arch.is_top_row():
+        raise ValueError(f"top-row tile has {ny} rows: the fold needs at least Hy+1 = {Hy + 1}")
+    params = make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius,
+                         tile=(i0, j0, nx, ny))
+    _require_cuda()
+    device = arch.torch_device()
+    parents = build_arrays(params, FT, device)
+    zc = _generate_z(z, Nz)
+    LX = "Periodic" if arch.Rx == 1 else "FullyConnected"
+    LY = "RightConnected" if arch.ry == 0 else "FullyConnected"     # :75
+    return OrthogonalSphericalShellGrid(
+        architecture=arch, Nx=nx, Ny=ny, Nz=Nz, Hx=Hx, Hy=Hy, Hz=Hz, Lz=zc.Lz, z=zc, radius=float(radius),
+        conformal_mapping=Tripolar(north_poles_latitude, first_pole_longitude, southernmost_latitude),
+        dtype=parents[0].dtype, topology=(LX, LY, "Bounded"),
+        arrays={n: OffsetArray(t, Hx, Hy) for n, t in zip(ARRAY_NAMES, parents)},
+        i0=i0, j0=j0, global_size=(Nx, Ny, Nz))
+
+
+def reconstruct_global_grid(grid: OrthogonalSphericalShellGrid):
+    """src/distributed_tripolar_grid.jl:201-226: the global grid on the child architecture (note:
+    like the reference, `radius` is not forwarded)."""
+    from .grids import TripolarGrid
+    arch = grid.architecture
+    cm = grid.conformal_mapping
+    return TripolarGrid(arch.child_architecture, grid.dtype, halo=grid.halo, size=grid.global_size,
+                        north_poles_latitude=cm.north_poles_latitude,
+                        first_pole_longitude=cm.first_pole_longitude,
+                        southernmost_latitude=cm.southernmost_latitude, z=grid.z.zf)
+
+
+# ---------------------------------------------------------------- fold communication plan
+@dataclass(frozen=True)
+class FoldMessage:
+    """Rank `src` packs global columns [src_i0, src_i0 + n) of its fold source rows and sends
+    them to rank `dst` (top row), which unpacks them into its north halo."""
+    src: int
+    dst: int
+    src_i0: int
+    n: int
+
+
+def fold_plan(Nx: int, Rx: int, Ry: int, locx: int) -> list:
+    """All messages of one fold exchange for fields at x-location `locx`, identical on every rank.
+    Destination column i needs source column i' = Nx - i + 1 (+1 for x-Face, wrapping Nx+1 -> 1)
+    (src/zipper_boundary_condition.jl:73-75,90-92,110,125)."""
+    sx = local_sizes(Nx, Rx)
+    starts = [1 + sum(sx[:r]) for r in range(Rx)]
+    top = Ry - 1
+    msgs = []
+    for drx in range(Rx):
+        lo, hi = starts[drx], starts[drx] + sx[drx] - 1          # destination columns
+        a, b = Nx - hi + 1 + locx, Nx - lo + 1 + locx            # source columns, ascending
+        ranges = [(a, min(b, Nx))] if a <= Nx else []
+        if b > Nx:
+            ranges.append((1, b - Nx))                           # periodic wrap of the x-Face fold
+        for (ra, rb) in ranges:
+            for srx in range(Rx):
+                slo, shi = starts[srx], starts[srx] + sx[srx] - 1
+                c0, c1 = max(ra, slo), min(rb, shi)
+                if c0 <= c1:
+                    msgs.append(FoldMessage(src=srx * Ry + top, dst=drx * Ry + top, src_i0=c0, n=c1 - c0 + 1))
+    return msgs
+
+
+class CudaPacker:
+    """pack / unpack through libossg_b200.so (ossg_fold_pack / ossg_fold_unpack)."""
+
+    def empty(self, f, n_elems: int) -> torch.Tensor:
+        return torch.empty(n_elems, dtype=f.data.dtype, device=f.data.device)
+
+    def buffer_elems(self, f, window: FoldWindow) -> int:
+        import ctypes as C
+        d = f.descriptor()
+        return int(_lib.lib().ossg_fold_buffer_elems(C.byref(d), C.byref(window)))
+
+    def pack(self, f, window: FoldWindow, buf: torch.Tensor, stream) -> None:
+        import ctypes as C
+        d = f.descriptor()
+        _lib.check(_lib.lib().ossg_fold_pack(C.byref(d), C.byref(window), buf.data_ptr(), stream))
+
+    def unpack(self, f, window: FoldWindow, buf: torch.Tensor, stream) -> None:
+        import ctypes as C
+        d = f.descriptor()
+        _lib.check(_lib.lib().ossg_fold_unpack(C.byref(d), C.byref(window), buf.data_ptr(), stream))
+
+    def stream(self, f):
+        return torch.cuda.current_stream(f.data.device).cuda_stream
+
+    def copy_rows(self, dst, src):
+        dst.copy_(src)
+
+
+def _window(f, gNx: int, src_i0: int, n: int) -> FoldWindow:
+    return FoldWindow(gNx, f.grid.i0, f.grid.Nx, src_i0, n)
+
+
+def fold_exchange(fields: Sequence, packer=None, group=None) -> None:
+    """Fold-partner exchange for a batch of fields on an (x, y)-partitioned tripolar grid: every
+    top-row rank packs the source rows each destination needs, all messages of the batch to one
+    partner travel as ONE send (fields and k-levels aggregated), then each rank unpacks with the
+    i-reversal and sign.  Ranks below the top row return immediately."""
+    import torch.distributed as dist
+    from .fields import is_zipper
+    fields = [f for f in fields if f.boundary_conditions is not None and is_zipper(f.boundary_conditions.north)]
+    if not fields:
+        return
+    arch = fields[0].grid.architecture
+    if not arch.is_top_row():
+        return
+    packer = packer or CudaPacker()
+    gNx = fields[0].grid.global_size[0]
+    me = arch.local_rank
+    # per-partner segment lists: (field, window, n_elems)
+    send_segs, recv_segs, local_segs = {}, {}, []
+    for f in fields:
+        locx = _lib.OSSG_FACE if f.descriptor().locx == _lib.OSSG_FACE else _lib.OSSG_CENTER
+        for msg in fold_plan(gNx, arch.Rx, arch.Ry, locx):
+            if msg.src != me and msg.dst != me:
+                continue
+            w = _window(f, gNx, msg.src_i0, msg.n)
+            ne = packer.buffer_elems(f, w)
+            if msg.src == me and msg.dst == me:
+                local_segs.append((f, w, ne))
+            elif msg.src == me:
+                send_segs.setdefault(msg.dst, []).append((f, w, ne))
+            else:
+                recv_segs.setdefault(msg.src, []).append((f, w, ne))
+    stream = packer.stream(fields[0])
+    # pack: one buffer per partner (all fields share a dtype per buffer; split by dtype if mixed)
+    ops, send_bufs, recv_bufs = [], {}, {}
+    for peer, segs in sorted(send_segs.items()):
+        for dt in sorted({s[0].data.dtype for s in segs}, key=str):
+            sel = [s for s in segs if s[0].data.dtype == dt]
+            buf = packer.empty(sel[0][0], sum(s[2] for s in sel))
+            off = 0
+            for (f, w, ne) in sel:
+                packer.pack(f, w, buf[off:off + ne], stream)
+                off += ne
+            send_bufs[(peer, dt)] = buf
+            ops.append(dist.P2POp(dist.isend, buf, peer, group))
+    for peer, segs in sorted(recv_segs.items()):
+        for dt in sorted({s[0].data.dtype for s in segs}, key=str):
+            sel = [s for s in segs if s[0].data.dtype == dt]
+            buf = packer.empty(sel[0][0], sum(s[2] for s in sel))
+            recv_bufs[(peer, dt)] = (buf, sel)
+            ops.append(dist.P2POp(dist.irecv, buf, peer, group))
+    # self part (Rx == 1, or the middle rank of an odd top row, or the wrapped x-Face column)
+    for (f, w, ne) in local_segs:
+        buf = packer.empty(f, ne)
+        packer.pack(f, w, buf, stream)
+        packer.unpack(f, w, buf, stream)
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for (peer, dt), (buf, sel) in recv_bufs.items():
+        off = 0
+        for (f, w, ne) in sel:
+            packer.unpack(f, w, buf[off:off + ne], stream)
+            off += ne
+
+
+def distributed_fill_halo_regions(fields: Sequence, stream=None, packer=None, group=None) -> None:
+    """fill_halo_regions! for fields on a distributed tripolar grid: fold exchange on the top row
+    (interior columns), then -- when x is not partitioned -- the local periodic west/east fill.
+    Ordinary south/north and west/east neighbour exchanges are ordinary_halo_exchange()."""
+    fold_exchange(fields, packer=packer, group=group)
+    ordinary_halo_exchange(fields, packer=packer, group=group)
+
+
+def ordinary_halo_exchange(fields: Sequence, packer=None, group=None) -> None:
+    """South/north slabs between j-adjacent ranks, then west/east slabs (periodic in x) over the
+    whole local y extent so the corners carry the already exchanged / folded rows.  One message
+    per neighbour per direction per field batch."""
+    import torch.distributed as dist
+    if not fields:
+        return
+    arch = fields[0].grid.architecture
+    packer = packer or CudaPacker()
+
+    def exchange(pairs):
+        """pairs: list of (send_view or None, send_peer, recv_view or None, recv_peer)."""
+        ops, pending = [], []
+        for (sv, sp, rv, rp) in pairs:
+            if sv is not None:
+                sb = sv.contiguous()
+                ops.append(dist.P2POp(dist.isend, sb, sp, group))
+                pending.append(sb)
+            if rv is not None:
+                rb = torch.empty(rv.shape, dtype=rv.dtype, device=rv.device)
+                ops.append(dist.P2POp(dist.irecv, rb, rp, group))
+                pending.append((rv, rb))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for item in pending:
+            if isinstance(item, tuple):
+                packer.copy_rows(item[0], item[1])
+
+    # ---- y direction (interior columns and x halos alike: whole rows)
+    pairs = []
+    for f in fields:
+        g = f.grid
+        Hy, Ny = g.Hy, g.Ny
+        d = f.data
+        if arch.ry + 1 < arch.Ry:       # send my top interior rows north, receive my north halo
+            peer = arch.rank_of(arch.rx, arch.ry + 1)
+            pairs.append((d[:, Ny:Ny + Hy, :], peer, d[:, Ny + Hy:Ny + 2 * Hy, :], peer))
+        if arch.ry > 0:                 # send my bottom interior rows south, receive my south halo
+            peer = arch.rank_of(arch.rx, arch.ry - 1)
+            pairs.append((d[:, Hy:2 * Hy, :], peer, d[:, 0:Hy, :], peer))
+    exchange(pairs)
+
+    # ---- x direction, periodic
+    pairs = []
+    for f in fields:
+        g = f.grid
+        Hx, Nx = g.Hx, g.Nx
+        d = f.data
+        if arch.Rx == 1:
+            d[:, :, 0:Hx] = d[:, :, Nx:Nx + Hx]
+            d[:, :, Nx + Hx:Nx + 2 * Hx] = d[:, :, Hx:2 * Hx]
+            continue
+        east = arch.rank_of((arch.rx + 1) % arch.Rx, arch.ry)
+        west = arch.rank_of((arch.rx - 1) % arch.Rx, arch.ry)
+        pairs.append((d[:, :, Nx:Nx + Hx], east, d[:, :, 0:Hx], west))                     # my east interior -> east rank's west halo
+        pairs.append((d[:, :, Hx:2 * Hx], west, d[:, :, Nx + Hx:Nx + 2 * Hx], east))       # my west interior -> west rank's east halo
+    exchange(pairs)

@@ -1,0 +1,422 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libossg_b200.so (via the Python host mirror of the reference interface) and is compared with the
+CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): lam/phi and metrics <= 1e-12 relative in Float64 -- the
+implementation is designed to be bit-identical to the oracle's deterministic arithmetic, so the
+tests also report the number of differing bit patterns -- and the fold is bit-exact.
+Float32: FP64 compute rounded once, i.e. identical to rounding the oracle's FP64 result.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12          # north_star tolerance, Float64
+
+CONFIGS = [
+    # size, halo, kwargs                                                   (source)
+    ((60, 30, 1), (4, 4, 4), {}),                                         # README.md:54 / BASELINE config A
+    ((4, 5, 1), (4, 4, 4), dict(first_pole_longitude=75, north_poles_latitude=35)),    # test/runtests.jl:10-14
+    ((10, 10, 1), (4, 4, 4), {}),                                         # test_zipper_boundary_conditions.jl:6 (Nx % 4 != 0)
+    ((360, 180, 1), (4, 4, 4), dict(first_pole_longitude=75, north_poles_latitude=35)),  # test_tripolar_grid.jl:59
+    ((360, 180, 50), (4, 4, 4), {}),                                      # BASELINE config B
+    ((120, 60, 1), (5, 5, 5), dict(north_poles_latitude=45, first_pole_longitude=25)),  # examples/bickley_jet.jl:20-23
+    ((40, 34, 1), (5, 31, 5), dict(north_poles_latitude=45, first_pole_longitude=35)),  # large Hy (with_halo, runtests.jl:71)
+    ((12, 8, 1), (2, 7, 1), {}),                                          # Hy = Ny - 1 (degenerate fold sources)
+    ((66, 37, 1), (3, 2, 1), dict(southernmost_latitude=-75.5)),          # ragged sizes, non-integer south
+]
+
+
+def rel_err(got, want):
+    denom = np.maximum(np.abs(want), np.finfo(np.float64).tiny)
+    err = np.where(got == want, 0.0, np.abs(got - want) / denom)
+    err = np.where(np.isnan(got) & np.isnan(want), 0.0, err)
+    return err
+
+
+def lam_err(got, want):
+    """longitudes compare modulo 360"""
+    d = np.abs(got - want)
+    d = np.minimum(d, np.abs(360.0 - d))
+    return d / np.maximum(np.abs(want), 1.0)
+
+
+def assert_grid_matches(grid_arrays, ref, tol=REL_TOL):
+    nbits = 0
+    for name in orc.ALL_NAMES:
+        got = grid_arrays[name]
+        want = ref[name]
+        assert got.shape == want.shape, name
+        err = lam_err(got, want) if name.startswith("lam") else rel_err(got, want)
+        worst = float(err.max())
+        assert worst <= tol, f"{name}: max rel err {worst:.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+        # exact zeros must be exact (pole metrics), src/tripolar_grid.jl M2 consequence
+        assert np.array_equal(got == 0.0, want == 0.0), f"{name}: zero pattern differs"
+        nbits += int((got.view(np.uint64) != want.view(np.uint64)).sum())
+    return nbits
+
+
+def to_np(grid):
+    return {n: grid.arrays[n].parent.cpu().numpy() for n in orc.ALL_NAMES}
+
+
+@pytest.mark.parametrize("size,halo,kw", CONFIGS)
+def test_construction_matches_oracle_f64(ossg, oracle, size, halo, kw):
+    grid = ossg.TripolarGrid(ossg.GPU(), ossg.Float64, size=size, halo=halo, **kw)
+    ref = oracle.build(orc.make_params(size, halo, **kw))
+    nbits = assert_grid_matches(to_np(grid), ref)
+    assert nbits == 0, f"{nbits} elements are not bit-identical to the oracle"
+
+
+@pytest.mark.parametrize("size,halo,kw", CONFIGS[:5])
+def test_construction_matches_oracle_f32(ossg, oracle, size, halo, kw):
+    grid = ossg.TripolarGrid(ossg.GPU(), ossg.Float32, size=size, halo=halo, **kw)
+    assert grid.eltype() == torch.float32
+    ref = oracle.build(orc.make_params(size, halo, **kw), dtype=np.float32)
+    for name in orc.ALL_NAMES:
+        got = grid.arrays[name].parent.cpu().numpy()
+        assert got.dtype == np.float32
+        assert np.array_equal(got.view(np.uint32), ref[name].view(np.uint32)), name
+
+
+def test_readme_known_answers_on_gpu(ossg):
+    """README.md:54-59"""
+    grid = ossg.TripolarGrid(size=(60, 30, 1))
+    p = orc.make_params((60, 30, 1))
+    s = orc.readme_summary(to_np(grid), p)
+    assert round(s.centre[0], 4) == 70.0 and round(s.centre[1], 4) == 1.8005
+    assert f"{s.lon_extent:.6g}" == "359.885" and f"{s.lat_extent:.6g}" == "175.667"
+    assert f"{s.dlam_min:.6g}" == "0.279019" and f"{s.dlam_max:.6g}" == "6.32049"
+    assert f"{s.dphi_min:.6g}" == "0.429975" and f"{s.dphi_max:.6g}" == "5.86207"
+
+
+def _call_staged(ossg, params, coords_host, metrics_dtype=torch.float64):
+    """ossg_tripolar_metrics on coordinates supplied by the caller (here: the oracle's)."""
+    L = ossg._lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cin = [torch.as_tensor(coords_host[n], device=dev).contiguous() for n in orc.COORD_NAMES]
+    out = [torch.empty_like(cin[0], dtype=metrics_dtype) for _ in range(12)]
+    nbytes = L.ossg_tripolar_workspace_bytes(C.byref(params), ossg._lib.OSSG_F64)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    et = ossg._lib.OSSG_F64 if metrics_dtype == torch.float64 else ossg._lib.OSSG_F32
+    rc = L.ossg_tripolar_metrics(C.byref(params), ossg._lib.ptr_array([t.data_ptr() for t in cin]), et,
+                                 ossg._lib.ptr_array([t.data_ptr() for t in out]), ws.data_ptr(), ws.numel(),
+                                 torch.cuda.current_stream().cuda_stream)
+    ossg._lib.check(rc)
+    torch.cuda.synchronize()
+    return dict(zip(orc.METRIC_NAMES, [t.cpu().numpy() for t in out]))
+
+
+@pytest.mark.parametrize("size,halo,kw", [CONFIGS[0], CONFIGS[3], CONFIGS[6]])
+def test_staged_metrics_from_oracle_coordinates(ossg, oracle, oracle_libm, size, halo, kw):
+    """Metric kernels fed with coordinates that did NOT come from the GPU: the oracle's own, and
+    the glibc-libm oracle's (a different last-ulp rounding of every coordinate)."""
+    from ossg_b200.grids import make_params
+    for orac in (oracle, oracle_libm):
+        p = orc.make_params(size, halo, **kw)
+        coords = orac.coords(p)
+        want = oracle.metrics(p, coords)        # deterministic-math oracle on the same inputs
+        params = make_params(size, halo, kw.get("southernmost_latitude", -80), kw.get("north_poles_latitude", 55),
+                             kw.get("first_pole_longitude", 70), orc.R_EARTH)
+        got = _call_staged(ossg, params, coords)
+        for name in orc.METRIC_NAMES:
+            err = rel_err(got[name], want[name])
+            assert float(err.max()) <= REL_TOL, name
+            assert np.array_equal(got[name].view(np.uint64), want[name].view(np.uint64)), name
+
+
+def _call_coords(ossg, params):
+    L = ossg._lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nx, ny = params.nx or params.Nx, params.ny or params.Ny
+    out = [torch.empty((ny + 2 * params.Hy, nx + 2 * params.Hx), dtype=torch.float64, device=dev) for _ in range(8)]
+    nbytes = L.ossg_tripolar_workspace_bytes(C.byref(params), ossg._lib.OSSG_F64)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ossg._lib.check(L.ossg_tripolar_coords(C.byref(params), ossg._lib.ptr_array([t.data_ptr() for t in out]),
+                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return dict(zip(orc.COORD_NAMES, [t.cpu().numpy() for t in out]))
+
+
+def test_staged_coords(ossg, oracle):
+    from ossg_b200.grids import make_params
+    size, halo = (60, 30, 1), (4, 4, 4)
+    got = _call_coords(ossg, make_params(size, halo, -80, 55, 70, orc.R_EARTH))
+    want = oracle.coords(orc.make_params(size, halo))
+    for n in orc.COORD_NAMES:
+        assert np.array_equal(got[n].view(np.uint64), want[n].view(np.uint64)), n
+
+
+@pytest.mark.parametrize("Rx,Ry", [(1, 2), (2, 1), (2, 2), (4, 2), (3, 3), (1, 4)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_tiles_equal_slices_of_the_serial_grid(ossg, oracle, Rx, Ry, dtype):
+    """src/distributed_tripolar_grid.jl:41-49,112-120: a rank's arrays are the jrange (and, new,
+    irange) slice of the global padded arrays, offsets preserved."""
+    from ossg_b200.distributed import tile_of
+    from ossg_b200.grids import build_arrays, make_params
+    size, halo = (48, 40, 1), (4, 4, 4)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    ref = oracle.build(orc.make_params(size, halo), dtype=npdt)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for rx in range(Rx):
+        for ry in range(Ry):
+            i0, j0, nx, ny = tile_of(size[0], size[1], Rx, Ry, rx, ry)
+            params = make_params(size, halo, -80, 55, 70, orc.R_EARTH, tile=(i0, j0, nx, ny))
+            tiles = build_arrays(params, dtype, dev)
+            torch.cuda.synchronize()
+            for name, t in zip(orc.ALL_NAMES, tiles):
+                want = ref[name][j0 - 1:j0 - 1 + ny + 2 * halo[1], i0 - 1:i0 - 1 + nx + 2 * halo[0]]
+                got = t.cpu().numpy()
+                assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)), (name, rx, ry)
+
+
+# ------------------------------------------------------------------ zipper
+LOCS = {"cc": (0, 0), "fc": (1, 0), "cf": (0, 1), "ff": (1, 1)}
+
+
+def _poisoned_field(shape, Nx, Ny, Nz, Hx, Hy, Hz, npdt, seed):
+    rng = np.random.default_rng(seed)
+    c = np.full(shape, np.nan, dtype=npdt)
+    c[Hz:Hz + Nz, Hy:Hy + Ny, Hx:Hx + Nx] = rng.uniform(-1, 1, (Nz, Ny, Nx)).astype(npdt)
+    return c
+
+
+def _desc(ossg, t, dims, loc, sign, k0=0, nk=0):
+    Nx, Ny, Nz, Hx, Hy, Hz = dims
+    et = ossg._lib.OSSG_F64 if t.dtype == torch.float64 else ossg._lib.OSSG_F32
+    return ossg._lib.FieldDesc(t.data_ptr(), et, Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], k0, nk, float(sign))
+
+
+def _same_bits(a, b):
+    u = np.uint64 if a.dtype == np.float64 else np.uint32
+    return np.array_equal(a.view(u), b.view(u))
+
+
+@pytest.mark.parametrize("locname", list(LOCS))
+@pytest.mark.parametrize("npdt", [np.float64, np.float32])
+@pytest.mark.parametrize("sign", [1, -1])
+@pytest.mark.parametrize("dims", [(10, 10, 1, 4, 4, 4), (60, 30, 3, 4, 4, 2), (360, 180, 5, 4, 4, 4), (34, 17, 2, 3, 9, 1), (4, 5, 1, 4, 4, 4)])
+def test_zipper_fill_bit_exact(ossg, oracle, locname, npdt, sign, dims):
+    """src/zipper_boundary_condition.jl:70-138 on NaN-poisoned halos: exactly the fold targets are
+    written, everything else (other halos, interior) is untouched, bit for bit."""
+    Nx, Ny, Nz, Hx, Hy, Hz = dims
+    loc = LOCS[locname]
+    shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
+    host = _poisoned_field(shape, Nx, Ny, Nz, Hx, Hy, Hz, npdt, seed=hash((locname, sign)) % 1000)
+    dev = torch.as_tensor(host).cuda()
+    d = _desc(ossg, dev, dims, loc, sign)
+    ossg._lib.check(ossg._lib.lib().ossg_zipper_fill(C.byref(d), None))
+    torch.cuda.synchronize()
+    want = oracle.zipper(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+    assert _same_bits(dev.cpu().numpy(), want)
+    # zipper + periodic x (fill_halo_regions!)
+    dev2 = torch.as_tensor(host).cuda()
+    d2 = _desc(ossg, dev2, dims, loc, sign)
+    ossg._lib.check(ossg._lib.lib().ossg_fill_halo_regions_batch(C.byref(d2), 1, None))
+    torch.cuda.synchronize()
+    want2 = oracle.fill_halo_regions(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+    assert _same_bits(dev2.cpu().numpy(), want2)
+
+
+def test_zipper_batch_mixed_fields_one_launch(ossg, oracle):
+    dims = (60, 30, 4, 4, 4, 3)
+    Nx, Ny, Nz, Hx, Hy, Hz = dims
+    shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
+    specs = [("cc", 1, np.float64), ("fc", -1, np.float64), ("cf", -1, np.float32), ("ff", 1, np.float32),
+             ("fc", -1, np.float32), ("cc", 1, np.float32)]
+    hosts = [_poisoned_field(shape, *dims, npdt, seed=k) for k, (_, _, npdt) in enumerate(specs)]
+    devs = [torch.as_tensor(h).cuda() for h in hosts]
+    arr = (ossg._lib.FieldDesc * len(specs))(*[_desc(ossg, t, dims, LOCS[l], s) for t, (l, s, _) in zip(devs, specs)])
+    ossg._lib.check(ossg._lib.lib().ossg_zipper_fill_batch(arr, len(specs), None))
+    torch.cuda.synchronize()
+    for t, h, (l, s, _) in zip(devs, hosts, specs):
+        want = oracle.zipper(h.copy(), Nx, Ny, Nz, Hx, Hy, Hz, LOCS[l][0], LOCS[l][1], s)
+        assert _same_bits(t.cpu().numpy(), want), l
+
+
+def test_zipper_k_range(ossg, oracle):
+    dims = (20, 12, 6, 2, 3, 2)
+    Nx, Ny, Nz, Hx, Hy, Hz = dims
+    shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
+    host = _poisoned_field(shape, *dims, np.float64, seed=3)
+    dev = torch.as_tensor(host).cuda()
+    d = _desc(ossg, dev, dims, (1, 0), -1, k0=3, nk=4)
+    ossg._lib.check(ossg._lib.lib().ossg_zipper_fill(C.byref(d), None))
+    torch.cuda.synchronize()
+    want = oracle.zipper(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, 1, 0, -1, k0=3, nk=4)
+    assert _same_bits(dev.cpu().numpy(), want)
+
+
+def test_reference_zipper_testset(ossg):
+    """test/test_zipper_boundary_conditions.jl:5-45 through the mirrored API."""
+    grid = ossg.TripolarGrid(size=(10, 10, 1))
+    Nx, Ny, _ = grid.size
+    Hx, Hy, _ = grid.halo
+    c, u, v = ossg.CenterField(grid), ossg.XFaceField(grid), ossg.YFaceField(grid)
+    for f, s in ((c, 1), (u, -1), (v, -1)):
+        assert isinstance(f.boundary_conditions.north.classification, ossg.Zipper)      # :14-16
+        assert f.boundary_conditions.north.condition == s                               # :21-23
+    for f in (c, u, v):
+        ossg.set_(f, 1)
+    ossg.fill_halo_regions(c)
+    ossg.fill_halo_regions(u)
+    ossg.fill_halo_regions(v)
+    torch.cuda.synchronize()
+    assert bool((c[slice(None, None), slice(Ny + 1, Ny + Hy), 1] == 1).all())             # :35
+    assert bool((v[slice(None, None), slice(Ny + 1, Ny + Hy), 1] == -1).all())            # :36
+    assert bool((u[slice(2, Nx - 1), slice(Ny + 1, Ny + Hy), 1] == -1).all())             # :39-40
+    assert bool((u[1, slice(Ny + 1, Ny + Hy), 1] == 1).all())                             # :42,44
+    assert bool((u[Nx + 1, slice(Ny + 1, Ny + Hy), 1] == 1).all())                        # :43,45
+
+
+def test_reference_zipper_testset_fold_row(ossg):
+    """test/test_zipper_boundary_conditions.jl:56-72: c = u = x, row Ny after the fill."""
+    grid = ossg.TripolarGrid(size=(10, 10, 1))
+    c, u = ossg.CenterField(grid), ossg.XFaceField(grid)
+    ossg.set_(c, lambda lam, phi, z: lam + 0 * phi + 0 * z)
+    ossg.set_(u, lambda lam, phi, z: lam + 0 * phi + 0 * z)
+    ossg.fill_halo_regions([c, u])
+    torch.cuda.synchronize()
+    row = c.interior()[0, 9, :].cpu().numpy()
+    assert np.array_equal(row, row[::-1])                                                # :65
+    urow = u.interior()[0, 9, :].cpu().numpy()
+    assert np.array_equal(urow[1:5], -urow[6:10][::-1])                                  # :68-72
+
+
+def test_fold_quirk_sign_flip_is_reproduced(ossg, oracle):
+    """for (Face, Center), sign -1, c[Nx/2+1, Ny] flips on EVERY fill
+    (src/zipper_boundary_condition.jl:102 with i' == i); a drop-in must do the same."""
+    dims = (12, 9, 1, 2, 2, 1)
+    Nx, Ny, Nz, Hx, Hy, Hz = dims
+    host = _poisoned_field((Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx), *dims, np.float64, seed=11)
+    dev = torch.as_tensor(host).cuda()
+    d = _desc(ossg, dev, dims, (1, 0), -1)
+    want = host.copy()
+    for _ in range(3):
+        ossg._lib.check(ossg._lib.lib().ossg_zipper_fill(C.byref(d), None))
+        oracle.zipper(want, Nx, Ny, Nz, Hx, Hy, Hz, 1, 0, -1)
+    torch.cuda.synchronize()
+    assert _same_bits(dev.cpu().numpy(), want)
+    v0 = host[Hz, Ny + Hy - 1, Nx // 2 + Hx]
+    assert dev.cpu().numpy()[Hz, Ny + Hy - 1, Nx // 2 + Hx] == -v0
+
+
+def test_fold_pack_unpack_equals_zipper(ossg, oracle):
+    """An (x)-partitioned top row assembled from pack/unpack messages equals the serial zipper."""
+    from ossg_b200.distributed import fold_plan, local_sizes
+    gNx, Ny, Nz, Hx, Hy, Hz = 24, 10, 2, 3, 3, 1
+    for Rx in (1, 2, 3, 4):
+        for locname, loc in LOCS.items():
+            for sign in (1, -1):
+                host = _poisoned_field((Nz + 2 * Hz, Ny + 2 * Hy, gNx + 2 * Hx), gNx, Ny, Nz, Hx, Hy, Hz, np.float64, seed=5)
+                want = oracle.zipper(host.copy(), gNx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+                sx = local_sizes(gNx, Rx)
+                starts = [1 + sum(sx[:r]) for r in range(Rx)]
+                tiles = []
+                for r in range(Rx):      # local tiles: interior columns + (stale) x halos
+                    t = np.ascontiguousarray(host[:, :, starts[r] - 1:starts[r] - 1 + sx[r] + 2 * Hx])
+                    tiles.append(torch.as_tensor(t).cuda())
+                L = ossg._lib.lib()
+                for msg in fold_plan(gNx, Rx, 1, loc[0]):
+                    src, dst = msg.src, msg.dst
+                    fs = _desc(ossg, tiles[src], (sx[src], Ny, Nz, Hx, Hy, Hz), loc, sign)
+                    fd = _desc(ossg, tiles[dst], (sx[dst], Ny, Nz, Hx, Hy, Hz), loc, sign)
+                    ws = ossg._lib.FoldWindow(gNx, starts[src], sx[src], msg.src_i0, msg.n)
+                    wd = ossg._lib.FoldWindow(gNx, starts[dst], sx[dst], msg.src_i0, msg.n)
+                    ne = L.ossg_fold_buffer_elems(C.byref(fs), C.byref(ws))
+                    buf = torch.empty(ne, dtype=torch.float64, device="cuda")
+                    ossg._lib.check(L.ossg_fold_pack(C.byref(fs), C.byref(ws), buf.data_ptr(), None))
+                    ossg._lib.check(L.ossg_fold_unpack(C.byref(fd), C.byref(wd), buf.data_ptr(), None))
+                torch.cuda.synchronize()
+                for r in range(Rx):
+                    got = tiles[r].cpu().numpy()[:, :, Hx:Hx + sx[r]]
+                    exp = want[:, :, starts[r] - 1 + Hx:starts[r] - 1 + Hx + sx[r]]
+                    assert _same_bits(np.ascontiguousarray(got), np.ascontiguousarray(exp)), (Rx, locname, sign, r)
+
+
+# ------------------------------------------------------------------ argument errors through the ABI
+def test_abi_argument_errors(ossg):
+    from ossg_b200.grids import make_params
+    L = ossg._lib.lib()
+    p = make_params((61, 30, 1), (4, 4, 4), -80, 55, 70, orc.R_EARTH)
+    out = ossg._lib.ptr_array([8] * 20)
+    assert L.ossg_tripolar_build(C.byref(p), 0, out, 16, 1 << 20, None) == ossg._lib.OSSG_EODD_NX
+    assert b"should be even" in L.ossg_last_error()
+    p = make_params((60, 30, 1), (4, 30, 4), -80, 55, 70, orc.R_EARTH)
+    assert L.ossg_tripolar_build(C.byref(p), 0, out, 16, 1 << 20, None) == ossg._lib.OSSG_EHALO
+    with pytest.raises(ValueError, match="should be even"):
+        ossg.TripolarGrid(size=(61, 30, 1))
+
+
+# ------------------------------------------------------------------ full-size properties (no oracle)
+@pytest.mark.parametrize("size", [(1440, 720, 75), (4320, 2160, 100)])
+def test_full_size_structural_invariants(ossg, size):
+    """Size-independent properties of the constructor at BASELINE sizes C and D
+    (SURVEY section 8c 'structural invariants')."""
+    grid = ossg.TripolarGrid(ossg.GPU(), size=size)
+    Nx, Ny, _ = size
+    H = 4
+    a = {n: grid.arrays[n] for n in orc.ALL_NAMES}
+    for n in orc.ALL_NAMES:
+        p = a[n].parent
+        assert bool(torch.isfinite(p).all()), n
+        # periodic x halos over all rows
+        assert torch.equal(p[:, :H], p[:, Nx:Nx + H]) and torch.equal(p[:, Nx + H:], p[:, H:2 * H]), n
+    for n in ("lam_cc", "phi_cc", "dx_cc", "dy_cc", "az_cc"):        # x-Center, y-Center: row Ny mirror symmetric
+        row = a[n][slice(1, Nx), Ny]
+        assert torch.equal(row, row.flip(0)), n
+    for n in ("lam_fc", "phi_fc", "dx_fc", "dy_fc", "az_fc"):        # x-Face: i <-> Nx - i + 2
+        row = a[n][slice(2, Nx), Ny]
+        assert torch.equal(row, row.flip(0)), n
+    for n in ("dx_fc", "dy_fc", "az_fc"):                            # exact zeros at the two pole points
+        assert float(a[n][1, Ny]) == 0.0 and float(a[n][Nx // 2 + 1, Ny]) == 0.0, n
+    for n in orc.COORD_NAMES:                                        # south halo of coordinates stays 0 (south = nothing)
+        assert float(a[n].parent[:H, :].abs().max()) == 0.0, n
+    lam = a["lam_cc"].interior(Nx, Ny)
+    phi = a["phi_cc"].interior(Nx, Ny)
+    assert float(lam.min()) >= 0 and float(lam.max()) <= 360 and float(phi.max()) <= 90      # runtests.jl:32-34
+    # north halo = fold image: lam_cc[i, Ny + j] == lam_cc[Nx - i + 1, Ny - j]
+    for j in range(1, H + 1):
+        assert torch.equal(a["lam_cc"][slice(1, Nx), Ny + j], a["lam_cc"][slice(1, Nx), Ny - j].flip(0))
+        assert torch.equal(a["az_cf"][slice(1, Nx), Ny + j], a["az_cf"][slice(1, Nx), Ny - j + 1].flip(0))
+    # metrics positive in the interior above the south continuation row
+    for n in ("dx_cc", "dy_cc", "az_cc", "dx_ff", "dy_ff", "az_ff"):
+        assert float(a[n][slice(1, Nx), slice(2, Ny - 1)].min()) > 0, n
+
+
+def test_full_size_fill_round_trip(ossg):
+    """Fold applied twice is the identity on the halo (fold o fold = id for sign^2 = 1), except
+    the reference's (Face, Center) pole quirk; checked on a D-sized slab of 4 levels."""
+    Nx, Ny, Nz, H = 4320, 2160, 4, 4
+    L = ossg._lib.lib()
+    for loc, sign in (((0, 0), 1), ((1, 0), -1), ((0, 1), -1), ((1, 1), 1)):
+        t = torch.empty((Nz + 2 * H, Ny + 2 * H, Nx + 2 * H), dtype=torch.float64, device="cuda")
+        d = _desc(ossg, t, (Nx, Ny, Nz, H, H, H), loc, sign)
+        ossg._lib.check(L.ossg_synth_field(C.byref(d), 0x5EED, 1, 1, None))
+        before = t.clone()
+        ossg._lib.check(L.ossg_fill_halo_regions_batch(C.byref(d), 1, None))
+        once = t.clone()
+        ossg._lib.check(L.ossg_fill_halo_regions_batch(C.byref(d), 1, None))
+        torch.cuda.synchronize()
+        k = slice(H, H + Nz)
+        # interior below row Ny untouched
+        assert torch.equal(before[k, H:H + Ny - 1, H:H + Nx], t[k, H:H + Ny - 1, H:H + Nx])
+        # halos of interior levels are fully written (no NaN left) and stable under a second fill
+        assert bool(torch.isfinite(once[k, H + Ny:, :]).all())
+        assert torch.equal(once[k, H + Ny:, :], t[k, H + Ny:, :])
+        # fold image: c[i, Ny+1] = s c[i', Ny - 1 (+1)]
+        js = Ny - 1 if loc[1] == 0 else Ny
+        src = before[k, H + js - 1, H:H + Nx]
+        if loc[0] == 0:
+            img = src.flip(-1)
+            assert torch.equal(once[k, H + Ny, H:H + Nx], sign * img)
+        else:
+            img = src[:, 1:].flip(-1)                  # i = 2..Nx  <-  i' = Nx..2
+            assert torch.equal(once[k, H + Ny, H + 1:H + Nx], sign * img)
+            assert torch.equal(once[k, H + Ny, H], abs(sign) * src[:, 0])   # i = 1 wraps: |sign|
