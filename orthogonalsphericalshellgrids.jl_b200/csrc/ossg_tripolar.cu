@@ -114,51 +114,77 @@ __global__ void __launch_bounds__(256) coords_kernel(BuildArgs a)
 }
 
 // ------------------------------------------------------------------ K2 (tile)
-constexpr int TX = 32, TY = 8;
-constexpr int PX = TX + 2, PY = TY + 2, PTS = PX * PY;
+// Tile of TX x TY cells.  Each staggering needs its coordinate on a (TX+1) x (TY+1) patch
+// (tripolar_grid_utils.jl:13-43):
+//     FC: i..i+1, j-1..j      CC: i-1..i, j-1..j      FF: i..i+1, j..j+1      CF: i-1..i, j..j+1
+// The patch is staged in shared memory once together with everything that depends on one point
+// only -- deg2rad(phi), cos(deg2rad(phi)) for the haversines and, for CC and FF, the unit vector
+// of lat_lon_to_cartesian -- so that the four (resp. up to six) cells sharing a point do not
+// repeat its trigonometry.
+constexpr int TX = 32, TY = 8, NT = TX * TY;
+constexpr int QX = TX + 1, QY = TY + 1, QPTS = QX * QY;
 // shared arrays: lam, phr, cosphi per staggering (12) + unit vectors of CC and FF (6)
 constexpr int N_SMEM_ARRAYS = 18;
-constexpr size_t TILE_SMEM_BYTES = (size_t)N_SMEM_ARRAYS * PTS * sizeof(double);
+constexpr size_t TILE_SMEM_BYTES = (size_t)N_SMEM_ARRAYS * QPTS * sizeof(double);
+constexpr int TASKS = 4 * QPTS, TASKS_PER_THREAD = (TASKS + NT - 1) / NT;
 
 struct FastRect { int I0, J0, nx, ny; };   // global indices of the first fast cell, extents
 
+// patch origin (offset of patch point (0,0) from tile cell (0,0)) per staggering
+__device__ __forceinline__ int patch_di(int loc) { return (loc == CC || loc == CF) ? -1 : 0; }
+__device__ __forceinline__ int patch_dj(int loc) { return (loc == CC || loc == FC) ? -1 : 0; }
+
 template <typename FT>
-__global__ void __launch_bounds__(TX * TY, 2) metrics_tile_kernel(BuildArgs a, FastRect fr)
+__global__ void __launch_bounds__(NT, 3) metrics_tile_kernel(BuildArgs a, FastRect fr)
 {
     extern __shared__ __align__(16) double smem[];
-    double* s_lam = smem;                    // [4][PTS]
-    double* s_phr = smem + 4 * PTS;          // [4][PTS]  deg2rad(phi)
-    double* s_cos = smem + 8 * PTS;          // [4][PTS]  cos(deg2rad(phi))
-    double* s_ux = smem + 12 * PTS;          // [2][PTS]  unit vectors: slot 0 = CC, slot 1 = FF
-    double* s_uy = smem + 14 * PTS;
-    double* s_uz = smem + 16 * PTS;
+    double* s_lam = smem;                     // [4][QPTS]
+    double* s_phr = smem + 4 * QPTS;          // [4][QPTS]  deg2rad(phi)
+    double* s_cos = smem + 8 * QPTS;          // [4][QPTS]  cos(deg2rad(phi))
+    double* s_ux = smem + 12 * QPTS;          // [2][QPTS]  unit vectors: slot 0 = CC, slot 1 = FF
+    double* s_uy = smem + 14 * QPTS;
+    double* s_uz = smem + 16 * QPTS;
 
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
     const Window w = a.w;
 
-    // ---- point stage: load the coordinate tile + apron once, hoist per-point trig
-    // task order: CC, FF (unit vectors needed), then FC, CF
-    for (int t = tid; t < 4 * PTS; t += TX * TY) {
-        const int q = t / PTS, p = t - q * PTS;
-        const int loc = (q == 0) ? CC : (q == 1) ? FF : (q == 2) ? FC : CF;
-        const int pj = p / PX, pi = p - pj * PX;
-        const int iw = It0 - 1 + pi - w.I0, jw = Jt0 - 1 + pj - w.J0;
-        double lam = 0.0, phi = 0.0;
-        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
-            const size_t o = (size_t)jw * w.wnx + iw;
-            lam = a.coords64[loc][o];
-            phi = a.coords64[4 + loc][o];
+    // ---- point stage.  Task t -> (q, p): q = 0: CC, 1: FF (unit vectors needed), 2: FC, 3: CF.
+    // All of a thread's loads are issued before any trigonometry (latency overlap).
+    double t_lam[TASKS_PER_THREAD], t_phi[TASKS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < TASKS_PER_THREAD; ++k) {
+        const int t = tid + k * NT;
+        t_lam[k] = 0.0; t_phi[k] = 0.0;
+        if (t < TASKS) {
+            const int q = t / QPTS, p = t - q * QPTS;
+            const int loc = (q == 0) ? CC : (q == 1) ? FF : (q == 2) ? FC : CF;
+            const int pj = p / QX, pi = p - pj * QX;
+            const int iw = It0 + patch_di(loc) + pi - w.I0, jw = Jt0 + patch_dj(loc) + pj - w.J0;
+            if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
+                const size_t o = (size_t)jw * w.wnx + iw;
+                t_lam[k] = __ldg(a.coords64[loc] + o);
+                t_phi[k] = __ldg(a.coords64[4 + loc] + o);
+            }
         }
-        const double phr = phi * D2R;
-        s_lam[loc * PTS + p] = lam;
-        s_phr[loc * PTS + p] = phr;
-        s_cos[loc * PTS + p] = m::cos_rad(phr);
-        if (q < 2) {
-            const Vec3 u = lat_lon_to_cartesian(phi, lam);
-            s_ux[q * PTS + p] = u.x;
-            s_uy[q * PTS + p] = u.y;
-            s_uz[q * PTS + p] = u.z;
+    }
+#pragma unroll
+    for (int k = 0; k < TASKS_PER_THREAD; ++k) {
+        const int t = tid + k * NT;
+        if (t < TASKS) {
+            const int q = t / QPTS, p = t - q * QPTS;
+            const int loc = (q == 0) ? CC : (q == 1) ? FF : (q == 2) ? FC : CF;
+            const double lam = t_lam[k], phi = t_phi[k];
+            const double phr = phi * D2R;
+            s_lam[loc * QPTS + p] = lam;
+            s_phr[loc * QPTS + p] = phr;
+            s_cos[loc * QPTS + p] = m::cos_rad(phr);
+            if (q < 2) {
+                const Vec3 u = lat_lon_to_cartesian(phi, lam);
+                s_ux[q * QPTS + p] = u.x;
+                s_uy[q * QPTS + p] = u.y;
+                s_uz[q * QPTS + p] = u.z;
+            }
         }
     }
     __syncthreads();
@@ -166,29 +192,30 @@ __global__ void __launch_bounds__(TX * TY, 2) metrics_tile_kernel(BuildArgs a, F
     const int ci = blockIdx.x * TX + threadIdx.x, cj = blockIdx.y * TY + threadIdx.y;
     if (ci >= fr.nx || cj >= fr.ny) return;
     const double R = a.radius;
-    const int p00 = (threadIdx.y + 1) * PX + (threadIdx.x + 1);
-    const int p10 = p00 + 1, pm0 = p00 - 1, p01 = p00 + PX, p0m = p00 - PX, p11 = p01 + 1, pmm = p0m - 1;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    // patch indices of this cell's own point per staggering
+    const int fc = (ty + 1) * QX + tx, cc = (ty + 1) * QX + tx + 1, ff = ty * QX + tx, cf = ty * QX + tx + 1;
 
-#define HAV(L, px, py) haversine_pre(s_lam[(L) * PTS + (px)], s_phr[(L) * PTS + (px)], s_cos[(L) * PTS + (px)], \
-                                     s_lam[(L) * PTS + (py)], s_phr[(L) * PTS + (py)], s_cos[(L) * PTS + (py)], R)
-#define UV(slot, px) Vec3{ s_ux[(slot) * PTS + (px)], s_uy[(slot) * PTS + (px)], s_uz[(slot) * PTS + (px)] }
+#define HAV(L, px, py) haversine_pre(s_lam[(L) * QPTS + (px)], s_phr[(L) * QPTS + (px)], s_cos[(L) * QPTS + (px)], \
+                                     s_lam[(L) * QPTS + (py)], s_phr[(L) * QPTS + (py)], s_cos[(L) * QPTS + (py)], R)
+#define UV(slot, px) Vec3{ s_ux[(slot) * QPTS + (px)], s_uy[(slot) * QPTS + (px)], s_uz[(slot) * QPTS + (px)] }
 
-    const double dx_cc = HAV(FC, p10, p00);      // tripolar_grid_utils.jl:13
-    const double dx_fc = HAV(CC, p00, pm0);      // :14
-    const double dx_cf = HAV(FF, p10, p00);      // :15
-    const double dx_ff = HAV(CF, p00, pm0);      // :16
-    const double dy_cc = HAV(CF, p01, p00);      // :18
-    const double dy_fc = HAV(FF, p01, p00);      // :19
-    const double dy_cf = HAV(CC, p00, p0m);      // :20
-    const double dy_ff = HAV(FC, p00, p0m);      // :21
-    const double az_cc = spherical_area_quadrilateral(UV(1, p00), UV(1, p10), UV(1, p11), UV(1, p01)) * (R * R);   // :23-28
-    const double az_fc = dy_fc * dx_fc;          // :34
-    const double az_cf = dy_cf * dx_cf;          // :35
-    const double az_ff = spherical_area_quadrilateral(UV(0, pmm), UV(0, p0m), UV(0, p00), UV(0, pm0)) * (R * R);   // :38-43
+    const double dx_cc = HAV(FC, fc + 1, fc);        // tripolar_grid_utils.jl:13
+    const double dx_fc = HAV(CC, cc, cc - 1);        // :14
+    const double dx_cf = HAV(FF, ff + 1, ff);        // :15
+    const double dx_ff = HAV(CF, cf, cf - 1);        // :16
+    const double dy_cc = HAV(CF, cf + QX, cf);       // :18
+    const double dy_fc = HAV(FF, ff + QX, ff);       // :19
+    const double dy_cf = HAV(CC, cc, cc - QX);       // :20
+    const double dy_ff = HAV(FC, fc, fc - QX);       // :21
+    const double az_cc = spherical_area_quadrilateral(UV(1, ff), UV(1, ff + 1), UV(1, ff + QX + 1), UV(1, ff + QX)) * (R * R);   // :23-28
+    const double az_fc = dy_fc * dx_fc;              // :34
+    const double az_cf = dy_cf * dx_cf;              // :35
+    const double az_ff = spherical_area_quadrilateral(UV(0, cc - QX - 1), UV(0, cc - QX), UV(0, cc), UV(0, cc - 1)) * (R * R);   // :38-43
 #undef HAV
 #undef UV
 
-    const size_t o = (size_t)(Jt0 + threadIdx.y - w.J0) * w.wnx + (It0 + threadIdx.x - w.I0);
+    const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
     static_cast<FT*>(a.metrics_out[DX_CC])[o] = (FT)dx_cc;
     static_cast<FT*>(a.metrics_out[DX_FC])[o] = (FT)dx_fc;
     static_cast<FT*>(a.metrics_out[DX_CF])[o] = (FT)dx_cf;

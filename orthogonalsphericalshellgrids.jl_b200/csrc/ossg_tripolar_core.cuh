@@ -42,7 +42,7 @@ struct Tables {
 };
 enum LLCol : int { LL_DX_FC = 0, LL_DX_CF, LL_DX_FF, LL_DX_CC, LL_DY, LL_AZ_FC, LL_AZ_CF, LL_AZ_FF, LL_AZ_CC, LL_NCOL };
 
-OSSG_HD size_t tables_doubles(int Nx, int Ny, int Hy) { return 4 * (size_t)Nx + 4 * (size_t)Ny + (size_t)LL_NCOL * (Hy + 1); }
+OSSG_HOSTDEV size_t tables_doubles(int Nx, int Ny, int Hy) { return 4 * (size_t)Nx + 4 * (size_t)Ny + (size_t)LL_NCOL * (Hy + 1); }
 
 // ---------------------------------------------------------------- C0: 1-D coordinates
 // longitude = (-180, 180), Periodic, regular: faces -180 + (i-1) 360/Nx, centres half a cell on
@@ -122,9 +122,10 @@ OSSG_HD void tripolar_point(double as_i, double ac_i, double ch_j, double sh_j, 
     l += ip_le_half ? -90.0 : 90.0;                                           // :82
     l += first_pole_longitude + 90.0;                                         // :86
     // convert_to_0_360, src/OrthogonalSphericalShellGrids.jl:24 (fmod(l,360) == l when |l| < 360)
+    // (r in [360, 720): r - 360 is exact by Sterbenz and equals fmod(r, 360))
     double r = (fabs(l) < 360.0) ? l : fmod(l, 360.0);
     r += 360.0;
-    lam = (r < 360.0) ? r : fmod(r, 360.0);
+    lam = (r < 360.0) ? r : (r < 720.0) ? (r - 360.0) : fmod(r, 360.0);
 }
 
 // ---------------------------------------------------------------- C3 / M2 index maps
