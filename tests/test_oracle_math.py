@@ -1,0 +1,79 @@
+"""Elementary functions of the oracle (oracle/ossg_oracle_math.h) and of the product
+(csrc/ossg_math.cuh, through the test-only host build) against 60-digit mpmath and glibc, and
+against each other bit for bit.  CPU only."""
+import mpmath as mp
+import numpy as np
+import pytest
+
+import host_mirror as hm
+from oracle import oracle as orc
+
+mp.mp.prec = 200
+RNG = np.random.default_rng(20261018)
+
+
+def ulp_errors(ys, xs, f):
+    worst = 0.0
+    for x, y in zip(xs, ys):
+        t = f(mp.mpf(float(x)))
+        if t == 0:
+            assert y == 0
+            continue
+        u = abs(np.spacing(float(t)))
+        worst = max(worst, float(abs((mp.mpf(float(y)) - t) / mp.mpf(float(u)))))
+    return worst
+
+
+deg = lambda f: (lambda x: f(x * mp.pi / 180))
+CASES = [
+    # name, inputs, exact function, ulp bound
+    ("sind", RNG.uniform(-720, 720, 1500), deg(mp.sin), 0.8),
+    ("cosd", RNG.uniform(-720, 720, 1500), deg(mp.cos), 0.8),
+    ("sind", RNG.uniform(-1e-3, 1e-3, 500), deg(mp.sin), 0.8),
+    ("tand", RNG.uniform(0, 89.9, 1000), deg(mp.tan), 2.0),
+    ("sin", RNG.uniform(-7, 7, 1500), mp.sin, 0.8),
+    ("cos", RNG.uniform(-7, 7, 1500), mp.cos, 0.8),
+    ("sin", np.array([np.pi, np.pi / 2, -np.pi, 2 * np.pi, 1e-9, 3.0e-3]), mp.sin, 0.8),
+    ("cos", np.array([np.pi / 2, 3 * np.pi / 2, 1.5707963267948966]), mp.cos, 0.8),
+    ("atan", np.concatenate([RNG.uniform(-5, 5, 1500), 10.0 ** RNG.uniform(-10, 10, 1000)]), mp.atan, 0.8),
+    ("asin", np.concatenate([RNG.uniform(-1, 1, 1500), 10.0 ** RNG.uniform(-9, 0, 1000), [1.0, -1.0, 0.5, 0.975]]), mp.asin, 0.8),
+    ("asinh", 10.0 ** RNG.uniform(-8, 3, 300), mp.asinh, 0.501),
+    ("sinh", np.concatenate([10.0 ** RNG.uniform(-8, 1, 200), RNG.uniform(0, 8, 200)]), mp.sinh, 0.501),
+    ("cosh", np.concatenate([10.0 ** RNG.uniform(-8, 1, 200), RNG.uniform(0, 8, 200)]), mp.cosh, 0.501),
+]
+
+
+@pytest.mark.parametrize("name,xs,f,bound", CASES, ids=[f"{c[0]}-{k}" for k, c in enumerate(CASES)])
+def test_oracle_functions_against_mpmath(oracle, name, xs, f, bound):
+    assert ulp_errors(oracle.math(name, xs), xs, f) <= bound
+
+
+@pytest.mark.parametrize("name,xs,f,bound", CASES, ids=[f"{c[0]}-{k}" for k, c in enumerate(CASES)])
+def test_product_functions_are_bit_identical_to_the_oracle(oracle, mirror, name, xs, f, bound):
+    a = oracle.math(name, xs)
+    b = hm.math(mirror, orc.MATH_FN[name], xs)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_degree_trig_special_values(oracle, mirror):
+    """Julia Base semantics the pole meridians depend on."""
+    for fn in (lambda n, x: oracle.math(n, x), lambda n, x: hm.math(mirror, orc.MATH_FN[n], x)):
+        s = fn("sind", [-180.0, 0.0, 180.0, -0.0, 360.0, -360.0, 90.0, 270.0, 30.0])
+        assert np.array_equal(np.signbit(s[:6]), [True, False, False, True, False, True])
+        assert (s[:6] == 0).all() and s[6] == 1.0 and s[7] == -1.0 and abs(s[8] - 0.5) < 1e-16
+        c = fn("cosd", [90.0, -90.0, 270.0, 180.0, 0.0, 60.0])
+        assert (c[:3] == 0).all() and not np.signbit(c[:3]).any() and c[3] == -1.0 and c[4] == 1.0 and abs(c[5] - 0.5) < 1.2e-16
+        assert np.isnan(fn("sind", [np.inf, np.nan])).all() and np.isnan(fn("cosd", [np.inf])).all()
+        a = fn("atan", [np.inf, -np.inf, 0.0, -0.0])
+        assert a[0] == np.pi / 2 and a[1] == -np.pi / 2 and a[2] == 0 and np.signbit(a[3])
+        assert fn("asin", [1.0])[0] == np.pi / 2 and np.isnan(fn("asin", [1.0000001])[0])
+        assert fn("sinh", [0.0])[0] == 0.0 and fn("cosh", [0.0])[0] == 1.0 and fn("asinh", [0.0])[0] == 0.0
+
+
+def test_functions_agree_with_glibc_within_one_ulp(oracle, oracle_libm):
+    for name, xs in (("sin", RNG.uniform(-7, 7, 20000)), ("cos", RNG.uniform(-7, 7, 20000)),
+                     ("atan", RNG.uniform(-50, 50, 20000)), ("asin", RNG.uniform(-1, 1, 20000)),
+                     ("sinh", RNG.uniform(0, 8, 2000)), ("asinh", RNG.uniform(0, 100, 2000))):
+        a, b = oracle.math(name, xs), oracle_libm.math(name, xs)
+        ulps = np.abs(a - b) / np.spacing(np.maximum(np.abs(b), 1e-300))
+        assert ulps.max() <= 1.0, name
