@@ -1,0 +1,135 @@
+"""Multi-GPU check, launched as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tests/run_distributed_gpu.py [--bench]
+One rank per GPU over NCCL.  For every (Rx, Ry) factorisation of N:
+  * DistributedTripolarGrid tiles == slices of the serial oracle grid (bit for bit);
+  * distributed fill_halo_regions (fold pack -> NCCL send/recv -> unpack, then ordinary halos) of
+    c, u, v, zeta == slices of the serial oracle fill (bit for bit).
+With --bench it also times the fold exchange on the 1/12 degree fields.
+Used by tests/test_gpu_distributed.py (skipped on a single-GPU box) and by hand through gpurun."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import ossg_b200 as ossg                                    # noqa: E402
+from ossg_b200.distributed import distributed_fill_halo_regions, fold_exchange, tile_of   # noqa: E402
+from oracle import oracle as orc                            # noqa: E402
+
+
+def factorisations(n):
+    return [(rx, n // rx) for rx in range(1, n + 1) if n % rx == 0]
+
+
+def check(world, rank, dev):
+    o = orc.Oracle()
+    size, halo = (48, 40, 3), (4, 4, 2)
+    Nx, Ny, Nz = size
+    Hx, Hy, Hz = halo
+    ref = o.build(orc.make_params(size, halo))
+    failures = []
+    for (Rx, Ry) in factorisations(world):
+        arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(Rx, Ry))
+        grid = ossg.TripolarGrid(arch, ossg.Float64, size=size, halo=halo)
+        i0, j0, nx, ny = tile_of(Nx, Ny, Rx, Ry, arch.rx, arch.ry)
+        assert (grid.Nx, grid.Ny, grid.i0, grid.j0) == (nx, ny, i0, j0)
+        for n in orc.ALL_NAMES:
+            want = ref[n][j0 - 1:j0 - 1 + ny + 2 * Hy, i0 - 1:i0 - 1 + nx + 2 * Hx]
+            got = grid.arrays[n].parent.cpu().numpy()
+            if not np.array_equal(got.view(np.uint64), np.ascontiguousarray(want).view(np.uint64)):
+                failures.append(f"({Rx},{Ry}) rank {rank}: grid array {n} differs")
+        C_, F_ = ossg.Center, ossg.Face
+        specs = [((C_, C_, C_), (0, 0)), ((F_, C_, C_), (1, 0)), ((C_, F_, C_), (0, 1)), ((F_, F_, C_), (1, 1))]
+        fields, wants = [], []
+        for k, (loc, code) in enumerate(specs):
+            rng = np.random.default_rng(100 + k)
+            G = np.full((Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx), np.nan)
+            G[Hz:Hz + Nz, Hy:Hy + Ny, Hx:Hx + Nx] = rng.uniform(-1, 1, (Nz, Ny, Nx))
+            local = np.full((Nz + 2 * Hz, ny + 2 * Hy, nx + 2 * Hx), np.nan)
+            local[Hz:Hz + Nz, Hy:Hy + ny, Hx:Hx + nx] = G[Hz:Hz + Nz, j0 - 1 + Hy:j0 - 1 + Hy + ny, i0 - 1 + Hx:i0 - 1 + Hx + nx]
+            f = ossg.Field(loc, grid, data=torch.from_numpy(local).to(dev))
+            want = o.fill_halo_regions(G.copy(), Nx, Ny, Nz, Hx, Hy, Hz, code[0], code[1], ossg.sign(loc[0], loc[1]))
+            fields.append(f)
+            wants.append(want[:, j0 - 1:j0 - 1 + ny + 2 * Hy, i0 - 1:i0 - 1 + nx + 2 * Hx])
+        distributed_fill_halo_regions(fields)
+        torch.cuda.synchronize(dev)
+        for f, want, (loc, code) in zip(fields, wants, specs):
+            a, b = f.data.cpu().numpy()[Hz:Hz + Nz], want[Hz:Hz + Nz]
+            same = (a == b) | (np.isnan(a) & np.isnan(b))
+            if not same.all():
+                bad = np.argwhere(~same)[0]
+                failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: fill differs at {bad.tolist()}")
+        dist.barrier()
+    return failures
+
+
+def bench_fold(world, rank, dev):
+    """Fold exchange of c,u,v,zeta (FP64, Nz=100, Hy=4) on the 1/12 degree grid split (N,1)."""
+    from ossg_b200 import _lib
+    import ctypes as C
+    Nx, Ny, Nz, H = 4320, 2160, 100, 4
+    arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(world, 1))
+    i0, j0, nx, ny = tile_of(Nx, Ny, world, 1, arch.rx, arch.ry)
+
+    class G:        # grid stub: only sizes are needed by Field / fold_exchange
+        pass
+    g = G()
+    g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz = nx, ny, Nz, H, H, H
+    g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
+    g.size, g.halo = (nx, ny, Nz), (H, H, H)
+    C_, F_ = ossg.Center, ossg.Face
+    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)]
+    shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
+    fields = [ossg.Field(loc, g, data=torch.empty(shape, dtype=torch.float64, device=dev)) for loc in locs]
+    L = _lib.lib()
+    for k, f in enumerate(fields):
+        d = f.descriptor()
+        _lib.check(L.ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
+    for _ in range(3):
+        fold_exchange(fields)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fold_exchange(fields)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # bytes each rank receives per exchange: Hy rows (+1 for y-Center) x nx columns x Nz levels per field
+    recv = sum((H + (1 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fields)
+    return {"partition": f"({world},1)", "fields": 4, "ms_per_exchange": float(ms.item()),
+            "recv_bytes_per_rank": recv, "gbs_per_direction_per_gpu": recv / (float(ms.item()) * 1e-3) / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bench", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    failures = check(world, rank, dev)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, failures)
+    out = {"world": world, "failures": [x for fl in gathered for x in fl]}
+    if args.bench:
+        out["fold_exchange"] = bench_fold(world, rank, dev)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if out["failures"] else 0)
+
+
+if __name__ == "__main__":
+    main()
