@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, d
 
 // ------------------------------------------------------------------ K1
 template <typename FT>
-__global__ void __launch_bounds__(256) coords_kernel(BuildArgs a)
+__global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ BuildArgs a)
 {
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
     const int jw = blockIdx.y;
@@ -86,29 +86,31 @@ __global__ void __launch_bounds__(256) coords_kernel(BuildArgs a)
     const GridDims g = a.g;
     const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
     const size_t o = (size_t)jw * a.w.wnx + iw;
-    double lam[4], phi[4];
-    if (I >= 1 && I <= g.Nx && J >= 1 && J < g.Ny) {
-        // bulk: all four staggerings sit at their own (I, J)
+    const bool bulk = I >= 1 && I <= g.Nx && J >= 1 && J < g.Ny;   // all four staggerings sit at their own (I, J)
+    double asF = 0, acF = 0, asC = 0, acC = 0, chF = 0, shF = 0, chC = 0, shC = 0;
+    bool one = false, half = false;
+    if (bulk) {
         const int ip = preshift(I, g.Nx);
-        const bool one = ip == 1, half = ip <= g.Nx / 2;
-        const double asF = tb.asF[I - 1], acF = tb.acF[I - 1], asC = tb.asC[I - 1], acC = tb.acC[I - 1];
-        const double chF = tb.chF[J - 1], shF = tb.shF[J - 1], chC = tb.chC[J - 1], shC = tb.shC[J - 1];
-        tripolar_point(asC, acC, chC, shC, one, half, a.first_pole_longitude, lam[CC], phi[CC]);
-        tripolar_point(asF, acF, chC, shC, one, half, a.first_pole_longitude, lam[FC], phi[FC]);
-        tripolar_point(asC, acC, chF, shF, one, half, a.first_pole_longitude, lam[CF], phi[CF]);
-        tripolar_point(asF, acF, chF, shF, one, half, a.first_pole_longitude, lam[FF], phi[FF]);
-    } else {
-#pragma unroll
-        for (int loc = 0; loc < 4; ++loc)
-            coord_at(tb, g, a.first_pole_longitude, loc, I, J, lam[loc], phi[loc]);
+        one = ip == 1; half = ip <= g.Nx / 2;
+        asF = __ldg(tb.asF + I - 1); acF = __ldg(tb.acF + I - 1); asC = __ldg(tb.asC + I - 1); acC = __ldg(tb.acC + I - 1);
+        chF = __ldg(tb.chF + J - 1); shF = __ldg(tb.shF + J - 1); chC = __ldg(tb.chC + J - 1); shC = __ldg(tb.shC + J - 1);
     }
-#pragma unroll
+    // the four staggerings as a rolled loop: one copy of the point code in the instruction cache
+#pragma unroll 1
     for (int loc = 0; loc < 4; ++loc) {
-        a.coords64[loc][o] = lam[loc];
-        a.coords64[4 + loc][o] = phi[loc];
+        double lam, phi;
+        if (bulk) {
+            const bool fx = loc & 1, fy = loc & 2;
+            tripolar_point(fx ? asF : asC, fx ? acF : acC, fy ? chF : chC, fy ? shF : shC, one, half,
+                           a.first_pole_longitude, lam, phi);
+        } else {
+            coord_at(tb, g, a.first_pole_longitude, loc, I, J, lam, phi);
+        }
+        a.coords64[loc][o] = lam;
+        a.coords64[4 + loc][o] = phi;
         if (sizeof(FT) == 4) {
-            static_cast<FT*>(a.coords_out[loc])[o] = (FT)lam[loc];
-            static_cast<FT*>(a.coords_out[4 + loc])[o] = (FT)phi[loc];
+            static_cast<FT*>(a.coords_out[loc])[o] = (FT)lam;
+            static_cast<FT*>(a.coords_out[4 + loc])[o] = (FT)phi;
         }
     }
 }
@@ -126,7 +128,7 @@ constexpr int QX = TX + 1, QY = TY + 1, QPTS = QX * QY;
 // shared arrays: lam, phr, cosphi per staggering (12) + unit vectors of CC and FF (6)
 constexpr int N_SMEM_ARRAYS = 18;
 constexpr size_t TILE_SMEM_BYTES = (size_t)N_SMEM_ARRAYS * QPTS * sizeof(double);
-constexpr int TASKS = 4 * QPTS, TASKS_PER_THREAD = (TASKS + NT - 1) / NT;
+constexpr int TASKS = 4 * QPTS;
 
 struct FastRect { int I0, J0, nx, ny; };   // global indices of the first fast cell, extents
 
@@ -134,12 +136,28 @@ struct FastRect { int I0, J0, nx, ny; };   // global indices of the first fast c
 __device__ __forceinline__ int patch_di(int loc) { return (loc == CC || loc == CF) ? -1 : 0; }
 __device__ __forceinline__ int patch_dj(int loc) { return (loc == CC || loc == FC) ? -1 : 0; }
 
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <typename FT>
-__global__ void __launch_bounds__(NT, 3) metrics_tile_kernel(BuildArgs a, FastRect fr)
+__device__ __forceinline__ void store_metric(const BuildArgs& a, int id, size_t o, double v)
+{
+    static_cast<FT*>(a.metrics_out[id])[o] = (FT)v;
+}
+
+template <typename FT>
+__global__ void __launch_bounds__(NT, 3) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
 {
     extern __shared__ __align__(16) double smem[];
-    double* s_lam = smem;                     // [4][QPTS]
-    double* s_phr = smem + 4 * QPTS;          // [4][QPTS]  deg2rad(phi)
+    double* s_lam = smem;                     // [4][QPTS]  lambda (degrees)
+    double* s_phr = smem + 4 * QPTS;          // [4][QPTS]  phi (degrees) during staging, then deg2rad(phi)
     double* s_cos = smem + 8 * QPTS;          // [4][QPTS]  cos(deg2rad(phi))
     double* s_ux = smem + 12 * QPTS;          // [2][QPTS]  unit vectors: slot 0 = CC, slot 1 = FF
     double* s_uy = smem + 14 * QPTS;
@@ -149,43 +167,40 @@ __global__ void __launch_bounds__(NT, 3) metrics_tile_kernel(BuildArgs a, FastRe
     const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
     const Window w = a.w;
 
-    // ---- point stage.  Task t -> (q, p): q = 0: CC, 1: FF (unit vectors needed), 2: FC, 3: CF.
-    // All of a thread's loads are issued before any trigonometry (latency overlap).
-    double t_lam[TASKS_PER_THREAD], t_phi[TASKS_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < TASKS_PER_THREAD; ++k) {
-        const int t = tid + k * NT;
-        t_lam[k] = 0.0; t_phi[k] = 0.0;
-        if (t < TASKS) {
-            const int q = t / QPTS, p = t - q * QPTS;
-            const int loc = (q == 0) ? CC : (q == 1) ? FF : (q == 2) ? FC : CF;
-            const int pj = p / QX, pi = p - pj * QX;
-            const int iw = It0 + patch_di(loc) + pi - w.I0, jw = Jt0 + patch_dj(loc) + pj - w.J0;
-            if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
-                const size_t o = (size_t)jw * w.wnx + iw;
-                t_lam[k] = __ldg(a.coords64[loc] + o);
-                t_phi[k] = __ldg(a.coords64[4 + loc] + o);
-            }
+    // ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers
+    for (int t = tid; t < TASKS; t += NT) {
+        const int loc = t / QPTS, p = t - loc * QPTS;
+        const int pj = p / QX, pi = p - pj * QX;
+        const int iw = It0 + patch_di(loc) + pi - w.I0, jw = Jt0 + patch_dj(loc) + pj - w.J0;
+        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
+            const size_t o = (size_t)jw * w.wnx + iw;
+            cp_async_8(&s_lam[t], a.coords64[loc] + o);
+            cp_async_8(&s_phr[t], a.coords64[4 + loc] + o);
+        } else {
+            s_lam[t] = 0.0;
+            s_phr[t] = 0.0;
         }
     }
-#pragma unroll
-    for (int k = 0; k < TASKS_PER_THREAD; ++k) {
-        const int t = tid + k * NT;
-        if (t < TASKS) {
-            const int q = t / QPTS, p = t - q * QPTS;
-            const int loc = (q == 0) ? CC : (q == 1) ? FF : (q == 2) ? FC : CF;
-            const double lam = t_lam[k], phi = t_phi[k];
-            const double phr = phi * D2R;
-            s_lam[loc * QPTS + p] = lam;
-            s_phr[loc * QPTS + p] = phr;
-            s_cos[loc * QPTS + p] = m::cos_rad(phr);
-            if (q < 2) {
-                const Vec3 u = lat_lon_to_cartesian(phi, lam);
-                s_ux[q * QPTS + p] = u.x;
-                s_uy[q * QPTS + p] = u.y;
-                s_uz[q * QPTS + p] = u.z;
-            }
-        }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- point stage: everything that depends on one point only, once per patch point.
+    // Unit vectors (CC, FF) first so that whole warps take the same branch.
+#pragma unroll 1
+    for (int t = tid; t < 2 * QPTS; t += NT) {
+        const int q = t / QPTS, p = t - q * QPTS;         // q = 0: CC, 1: FF
+        const int loc = q ? FF : CC;
+        const Vec3 u = lat_lon_to_cartesian(s_phr[loc * QPTS + p], s_lam[loc * QPTS + p]);
+        s_ux[t] = u.x;
+        s_uy[t] = u.y;
+        s_uz[t] = u.z;
+    }
+    __syncthreads();                                      // s_phr is rewritten below
+#pragma unroll 1
+    for (int t = tid; t < TASKS; t += NT) {
+        const double phr = s_phr[t] * D2R;
+        s_phr[t] = phr;
+        s_cos[t] = m::cos_rad(phr);
     }
     __syncthreads();
 
@@ -193,58 +208,66 @@ __global__ void __launch_bounds__(NT, 3) metrics_tile_kernel(BuildArgs a, FastRe
     if (ci >= fr.nx || cj >= fr.ny) return;
     const double R = a.radius;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    // patch indices of this cell's own point per staggering
-    const int fc = (ty + 1) * QX + tx, cc = (ty + 1) * QX + tx + 1, ff = ty * QX + tx, cf = ty * QX + tx + 1;
+    const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
+    // patch index of this cell's own point per staggering (index = loc)
+    const int own_cc = (ty + 1) * QX + tx + 1, own_fc = (ty + 1) * QX + tx, own_cf = ty * QX + tx + 1, own_ff = ty * QX + tx;
 
 #define HAV(L, px, py) haversine_pre(s_lam[(L) * QPTS + (px)], s_phr[(L) * QPTS + (px)], s_cos[(L) * QPTS + (px)], \
                                      s_lam[(L) * QPTS + (py)], s_phr[(L) * QPTS + (py)], s_cos[(L) * QPTS + (py)], R)
-#define UV(slot, px) Vec3{ s_ux[(slot) * QPTS + (px)], s_uy[(slot) * QPTS + (px)], s_uz[(slot) * QPTS + (px)] }
-
-    const double dx_cc = HAV(FC, fc + 1, fc);        // tripolar_grid_utils.jl:13
-    const double dx_fc = HAV(CC, cc, cc - 1);        // :14
-    const double dx_cf = HAV(FF, ff + 1, ff);        // :15
-    const double dx_ff = HAV(CF, cf, cf - 1);        // :16
-    const double dy_cc = HAV(CF, cf + QX, cf);       // :18
-    const double dy_fc = HAV(FF, ff + QX, ff);       // :19
-    const double dy_cf = HAV(CC, cc, cc - QX);       // :20
-    const double dy_ff = HAV(FC, fc, fc - QX);       // :21
-    const double az_cc = spherical_area_quadrilateral(UV(1, ff), UV(1, ff + 1), UV(1, ff + QX + 1), UV(1, ff + QX)) * (R * R);   // :23-28
-    const double az_fc = dy_fc * dx_fc;              // :34
-    const double az_cf = dy_cf * dx_cf;              // :35
-    const double az_ff = spherical_area_quadrilateral(UV(0, cc - QX - 1), UV(0, cc - QX), UV(0, cc), UV(0, cc - 1)) * (R * R);   // :38-43
+    // ---- 8 haversines as 4 rolled iterations of 2 (one copy of the code in the instruction cache)
+    //   it 0: dx_fc = hav(CC[i,j], CC[i-1,j])   dy_fc = hav(FF[i,j+1], FF[i,j])   az_fc = dy_fc * dx_fc   (:14,:19,:34)
+    //   it 1: dy_cf = hav(CC[i,j], CC[i,j-1])   dx_cf = hav(FF[i+1,j], FF[i,j])   az_cf = dy_cf * dx_cf   (:20,:15,:35)
+    //   it 2: dy_ff = hav(FC[i,j], FC[i,j-1])   dy_cc = hav(CF[i,j+1], CF[i,j])                           (:21,:18)
+    //   it 3: dx_ff = hav(CF[i,j], CF[i-1,j])   dx_cc = hav(FC[i+1,j], FC[i,j])                           (:16,:13)
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        // first haversine: x = own point, y = own - step        (CC, CC, FC, CF)
+        const int locA = (it < 2) ? CC : (it == 2) ? FC : CF;
+        const int ownA = (it < 2) ? own_cc : (it == 2) ? own_fc : own_cf;
+        const int stepA = (it == 0 || it == 3) ? 1 : QX;
+        // second haversine: x = own + step, y = own point       (FF, FF, CF, FC)
+        const int locB = (it < 2) ? FF : (it == 2) ? CF : FC;
+        const int ownB = (it < 2) ? own_ff : (it == 2) ? own_cf : own_fc;
+        const int stepB = (it == 0 || it == 2) ? QX : 1;
+        const double hA = HAV(locA, ownA, ownA - stepA);
+        const double hB = HAV(locB, ownB + stepB, ownB);
+        const int idA = (it == 0) ? DX_FC : (it == 1) ? DY_CF : (it == 2) ? DY_FF : DX_FF;
+        const int idB = (it == 0) ? DY_FC : (it == 1) ? DX_CF : (it == 2) ? DY_CC : DX_CC;
+        store_metric<FT>(a, idA, o, hA);
+        store_metric<FT>(a, idB, o, hB);
+        if (it < 2) store_metric<FT>(a, it == 0 ? AZ_FC : AZ_CF, o, it == 0 ? hB * hA : hA * hB);
+    }
 #undef HAV
-#undef UV
-
-    const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
-    static_cast<FT*>(a.metrics_out[DX_CC])[o] = (FT)dx_cc;
-    static_cast<FT*>(a.metrics_out[DX_FC])[o] = (FT)dx_fc;
-    static_cast<FT*>(a.metrics_out[DX_CF])[o] = (FT)dx_cf;
-    static_cast<FT*>(a.metrics_out[DX_FF])[o] = (FT)dx_ff;
-    static_cast<FT*>(a.metrics_out[DY_CC])[o] = (FT)dy_cc;
-    static_cast<FT*>(a.metrics_out[DY_CF])[o] = (FT)dy_cf;
-    static_cast<FT*>(a.metrics_out[DY_FC])[o] = (FT)dy_fc;
-    static_cast<FT*>(a.metrics_out[DY_FF])[o] = (FT)dy_ff;
-    static_cast<FT*>(a.metrics_out[AZ_CC])[o] = (FT)az_cc;
-    static_cast<FT*>(a.metrics_out[AZ_FC])[o] = (FT)az_fc;
-    static_cast<FT*>(a.metrics_out[AZ_CF])[o] = (FT)az_cf;
-    static_cast<FT*>(a.metrics_out[AZ_FF])[o] = (FT)az_ff;
+    // ---- 2 spherical quadrilaterals, rolled
+    //   q = 0: az_ff from CC[i-1,j-1], CC[i,j-1], CC[i,j], CC[i-1,j]      (:38-43)
+    //   q = 1: az_cc from FF[i,j], FF[i+1,j], FF[i+1,j+1], FF[i,j+1]      (:23-28)
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+        const int b = q * QPTS + (q ? own_ff : own_cc - QX - 1);      // lower-left corner of the quadrilateral
+        const Vec3 va{ s_ux[b], s_uy[b], s_uz[b] };
+        const Vec3 vb{ s_ux[b + 1], s_uy[b + 1], s_uz[b + 1] };
+        const Vec3 vc{ s_ux[b + QX + 1], s_uy[b + QX + 1], s_uz[b + QX + 1] };
+        const Vec3 vd{ s_ux[b + QX], s_uy[b + QX], s_uz[b + QX] };
+        store_metric<FT>(a, q ? AZ_CC : AZ_FF, o, spherical_area_quadrilateral(va, vb, vc, vd) * (R * R));
+    }
 }
 
 // ------------------------------------------------------------------ K2f (frame)
-struct GlobalAcc {          // read the window's coordinate arrays
-    const double* const* c; int I0, J0, pitch;
+// Coordinate accessor of the frame kernel: read the window's coordinate arrays where the point lies
+// inside the window, otherwise evaluate the coordinate at its source from the tables (the two
+// give the same bits; the second is needed on the ring of a tile window, whose stencil leaves it).
+struct FrameAcc {
+    const double* const* c; Window w; Tables tb; GridDims g; double fpl;
     __device__ void operator()(int loc, int I, int J, double& lam, double& phi) const
     {
-        const size_t o = (size_t)(J - J0) * pitch + (I - I0);
-        lam = c[loc][o];
-        phi = c[4 + loc][o];
-    }
-};
-struct ClosedFormAcc {      // evaluate the coordinate at its source from the tables
-    Tables tb; GridDims g; double fpl;
-    __device__ void operator()(int loc, int I, int J, double& lam, double& phi) const
-    {
-        coord_at(tb, g, fpl, loc, I, J, lam, phi);
+        const int iw = I - w.I0, jw = J - w.J0;
+        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
+            const size_t o = (size_t)jw * w.wnx + iw;
+            lam = __ldg(c[loc] + o);
+            phi = __ldg(c[4 + loc] + o);
+        } else {
+            coord_at(tb, g, fpl, loc, I, J, lam, phi);
+        }
     }
 };
 
@@ -266,7 +289,7 @@ __host__ __device__ inline Frame make_frame(const Window& w, const FastRect& fr)
     return f;
 }
 
-template <typename FT, bool CLOSED_FORM>
+template <typename FT>
 __global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,13 +306,8 @@ __global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f
     const GridDims g = a.g;
     const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
     double out[N_METRIC];
-    if (CLOSED_FORM) {
-        ClosedFormAcc acc{ tb, g, a.first_pole_longitude };
-        metrics_at_padded(acc, tb, g, a.radius, w.I0 + iw, w.J0 + jw, out);
-    } else {
-        GlobalAcc acc{ a.coords64, w.I0, w.J0, w.wnx };
-        metrics_at_padded(acc, tb, g, a.radius, w.I0 + iw, w.J0 + jw, out);
-    }
+    const FrameAcc acc{ a.coords64, w, tb, g, a.first_pole_longitude };
+    metrics_at_padded(acc, tb, g, a.radius, w.I0 + iw, w.J0 + jw, out);
     const size_t o = (size_t)jw * w.wnx + iw;
 #pragma unroll
     for (int k = 0; k < N_METRIC; ++k) static_cast<FT*>(a.metrics_out[k])[o] = (FT)out[k];
@@ -377,8 +395,8 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
     const Frame f = make_frame(w, fr);
     const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
     if (n > 0) {
-        if (whole_grid) metrics_frame_kernel<FT, false><<<ceil_div(n, 128), 128, 0, s>>>(a, f);
-        else metrics_frame_kernel<FT, true><<<ceil_div(n, 128), 128, 0, s>>>(a, f);
+        (void)whole_grid;
+        metrics_frame_kernel<FT><<<ceil_div(n, 128), 128, 0, s>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
     }
     return 0;
