@@ -153,7 +153,7 @@ __device__ __forceinline__ void store_metric(const BuildArgs& a, int id, size_t 
 }
 
 template <typename FT>
-__global__ void __launch_bounds__(NT, 3) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
+__global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
 {
     extern __shared__ __align__(16) double smem[];
     double* s_lam = smem;                     // [4][QPTS]  lambda (degrees)
