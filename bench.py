@@ -30,9 +30,14 @@ CPU_SAMPLE = dict(Nx=1440, Ny=720)          # 1/9 of the workload's cells per CP
 METRIC = "grid cells/s for coords+metrics (FP64)"
 UNIT = "cells/s"
 
-# FP64 work of the metrics tile kernel per cell, from the committed ncu capture
-# (profiles/): filled in by DESIGN.md section "Kernels"; None until measured.
-FP64_INST_PER_CELL_TILE = None
+# FP64 pipe work per launch, counted by ncu on the 1/12 degree workload (SASS opcode mix of the
+# committed capture profiles/r01c_*_opcodes.md: DFMA + DMUL + DADD + DSETP thread-instructions):
+#   metrics_tile_kernel : 1386.1 per tile cell (4320 x 2158 cells)
+#   coords_kernel       :  405.7 per padded element (4328 x 2168 elements)
+# These are properties of the code, not of the timing; refresh them whenever the kernels change.
+FP64_INST_PER_CELL_TILE = 1386.1
+FP64_INST_PER_ELEM_COORDS = 405.7
+PROFILE_TAG = "r01c"
 
 
 def partition_for(n):
@@ -294,9 +299,16 @@ def run_own(args):
                      "peak_source": "ossg_fp64_peak_probe on this device, same run",
                      "tile_ns_per_cell": tile_ms * 1e6 / tile_cells}
     if FP64_INST_PER_CELL_TILE:
-        inst_rate = FP64_INST_PER_CELL_TILE * tile_cells / (tile_ms * 1e-3)
-        roofline_fp64.update({"achieved_fp64_inst_per_s": inst_rate,
-                              "frac": inst_rate / (fp64_peak_tflops * 1e12 / 2)})
+        peak_inst = fp64_peak_tflops * 1e12 / 2            # FP64 thread-instructions per second
+        inst_tile = FP64_INST_PER_CELL_TILE * tile_cells
+        inst_coords = FP64_INST_PER_ELEM_COORDS * shape[0] * shape[1]
+        roofline_fp64.update({
+            "kernel": "metrics_tile_kernel<double>",
+            "achieved": 2 * inst_tile / (tile_ms * 1e-3) / 1e12,       # DFMA-equivalent TFLOP/s
+            "frac": inst_tile / (tile_ms * 1e-3) / peak_inst,
+            "coords_kernel_frac": inst_coords / (kernel_ms["coords"] * 1e-3) / peak_inst,
+            "whole_step_frac": (inst_tile + inst_coords) / (ms_step * 1e-3) / peak_inst,
+            "fp64_inst_source": f"ncu SASS opcode counts, profiles/{PROFILE_TAG}_*_opcodes.md"})
 
     cpu_threads = os.cpu_count() or 1
     cpu_rate, cpu_dt = cpu_construct_rate(cpu_threads, 2, 1)
