@@ -29,38 +29,46 @@ __device__ __forceinline__ T apply_sign(T v, double s)
 // rows handled per level: Hy halo rows (+1 for y-Center: the redundant half of row Ny)
 __device__ __host__ inline int fold_rows(const ossg_field_desc& f) { return f.Hy + (f.locy == OSSG_CENTER ? 1 : 0); }
 
+// One thread serves one (i, level): it issues the loads of all Hy source rows (in chunks of 4)
+// before any store, so that every warp keeps 4 x 256 B in flight -- the fill is a pure
+// latency/bandwidth problem (zero flops).
 template <typename T>
-__device__ __forceinline__ void zipper_element(const ossg_field_desc& f, int i /*1..Nx*/, int r, int kk)
+__device__ __forceinline__ void zipper_column(const ossg_field_desc& f, int i /*1..Nx*/, int kk)
 {
-    const int Nx = f.Nx, Ny = f.Ny;
-    const size_t sx = (size_t)(Nx + 2 * f.Hx), sxy = sx * (size_t)(Ny + 2 * f.Hy);
+    const int Nx = f.Nx, Ny = f.Ny, Hy = f.Hy;
+    const size_t sx = (size_t)(Nx + 2 * f.Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
     T* c = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
     double s = f.sign;
     int ip = f.locx ? Nx - i + 2 : Nx - i + 1;                 // zipper_boundary_condition.jl:73,90,110,125
     if (ip > Nx) { s = fabs(s); ip -= Nx; }                     // :74-75, :91-92
-    int jd, js;
-    if (r < f.Hy) {                                            // halo row j = r + 1
-        jd = Ny + r + 1;
-        js = f.locy ? Ny - r : Ny - r - 1;                      // :80, :97, :115, :130
-    } else {                                                   // redundant part of row Ny, :102, :135
-        if (i <= Nx / 2) return;
-        jd = Ny; js = Ny;
+    // halo row j = r + 1 (r = 0..Hy-1):  dst row Ny + j, src row Ny - j (y-Center) or Ny - j + 1 (y-Face)
+    const T* src = c + (size_t)((f.locy ? Ny : Ny - 1) + Hy - 1) * sx + (ip + f.Hx - 1);   // r = 0, then -sx per row
+    T* dst = c + (size_t)(Ny + Hy) * sx + (i + f.Hx - 1);                                   // r = 0, then +sx per row
+    // redundant part of row Ny (y-Center fields, i > Nx/2), :102, :135 -- read before the halo stores
+    const bool fix_row = (f.locy == OSSG_CENTER) && (i > Nx / 2);
+    T vrow = T(0);
+    if (fix_row) vrow = c[(size_t)(Ny + Hy - 1) * sx + (ip + f.Hx - 1)];
+    int r = 0;
+    for (; r + 4 <= Hy; r += 4) {
+        const T v0 = src[-(ptrdiff_t)((r + 0) * sx)], v1 = src[-(ptrdiff_t)((r + 1) * sx)];
+        const T v2 = src[-(ptrdiff_t)((r + 2) * sx)], v3 = src[-(ptrdiff_t)((r + 3) * sx)];
+        dst[(size_t)(r + 0) * sx] = apply_sign(v0, s);
+        dst[(size_t)(r + 1) * sx] = apply_sign(v1, s);
+        dst[(size_t)(r + 2) * sx] = apply_sign(v2, s);
+        dst[(size_t)(r + 3) * sx] = apply_sign(v3, s);
     }
-    const T v = c[(size_t)(js + f.Hy - 1) * sx + (ip + f.Hx - 1)];
-    c[(size_t)(jd + f.Hy - 1) * sx + (i + f.Hx - 1)] = apply_sign(v, s);
+    for (; r < Hy; ++r) dst[(size_t)r * sx] = apply_sign(src[-(ptrdiff_t)(r * sx)], s);
+    if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + f.Hx - 1)] = apply_sign(vrow, s);
 }
 
 __global__ void __launch_bounds__(ZB) zipper_kernel(const __grid_constant__ FieldBatch b)
 {
     const ossg_field_desc& f = b.f[blockIdx.z];
     const int i = blockIdx.x * ZB + threadIdx.x + 1;
-    if (i > f.Nx) return;
-    const int rows = fold_rows(f);
-    const int row = blockIdx.y;                 // row = kk * rows + r
-    if (row >= rows * f.nk) return;
-    const int kk = row / rows, r = row - kk * rows;
-    if (f.elem_type == OSSG_F64) zipper_element<double>(f, i, r, kk);
-    else zipper_element<float>(f, i, r, kk);
+    const int kk = blockIdx.y;
+    if (i > f.Nx || kk >= f.nk) return;
+    if (f.elem_type == OSSG_F64) zipper_column<double>(f, i, kk);
+    else zipper_column<float>(f, i, kk);
 }
 
 // periodic west/east fill over the whole (y, z) parent extent (external Oceananigans periodic
@@ -182,12 +190,12 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
             if (rc) return rc;
             if (b.f[k].Hy == 0) continue;
             gx = max(gx, ceil_div(b.f[k].Nx, ZB));
-            gy = max(gy, fold_rows(b.f[k]) * b.f[k].nk);
+            gy = max(gy, b.f[k].nk);
             const size_t prow = (size_t)(b.f[k].Ny + 2 * b.f[k].Hy) * (size_t)(b.f[k].Nz + 2 * b.f[k].Hz) * (size_t)(2 * b.f[k].Hx);
             pmax = pmax > prow ? pmax : prow;
         }
         if (gx > 0 && gy > 0) {
-            if (gy > 65535) return set_error(OSSG_EINVAL, "too many (row, level) pairs for one launch: %d", gy);
+            if (gy > 65535) return set_error(OSSG_EINVAL, "too many levels for one launch: %d", gy);
             zipper_kernel<<<dim3(gx, gy, b.n), ZB, 0, s>>>(b);
             OSSG_LAUNCH_CHECK("zipper_kernel");
         }
