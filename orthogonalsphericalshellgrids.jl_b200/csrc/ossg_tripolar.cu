@@ -115,6 +115,96 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ Bui
     }
 }
 
+// ------------------------------------------------------------------ K1 (mirror pairs)
+// Used when the window spans the whole x extent (serial grids and Y-slab ranks).  In rows
+// 1..Ny-1 a thread evaluates the map once per staggering for pre-shift column ip = 1+u and
+// writes both ip and its mirror column (see tripolar_core): half the transcendental work of the
+// per-element kernel.  The x halos of those rows, row Ny (whose y-Center fields carry the fold
+// overwrite), the north halo and the south halo go through the per-element source map.
+template <typename FT>
+__device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t o, double lam, double phi)
+{
+    a.coords64[loc][o] = lam;
+    a.coords64[4 + loc][o] = phi;
+    if (sizeof(FT) == 4) {
+        static_cast<FT*>(a.coords_out[loc])[o] = (FT)lam;
+        static_cast<FT*>(a.coords_out[4 + loc])[o] = (FT)phi;
+    }
+}
+
+template <typename FT>
+__global__ void __launch_bounds__(256) coords_pair_kernel(const __grid_constant__ BuildArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jw = blockIdx.y;
+    const GridDims g = a.g;
+    const int Nx = g.Nx, Hx = g.Hx;
+    const int J = a.w.J0 + jw;
+    const Tables tb = make_tables(a.tables, Nx, g.Ny);
+    const size_t row = (size_t)jw * a.w.wnx;
+    const double fpl = a.first_pole_longitude;
+    if (J >= 1 && J < g.Ny) {
+        const int half = Nx / 2;
+        if (t <= half) {
+            const int ip = 1 + t;                               // pre-shift column of this pair
+            const int shift = Nx / 4;
+            int i = ip + shift; if (i > Nx) i -= Nx;            // its post-shift column
+            const double chF = __ldg(tb.chF + J - 1), shF = __ldg(tb.shF + J - 1);
+            const double chC = __ldg(tb.chC + J - 1), shC = __ldg(tb.shC + J - 1);
+            const size_t o = row + (size_t)(i + Hx - 1);
+            {   // x-Face: ip <-> Nx+2-ip ; ip = 1 and ip = Nx/2+1 are their own mirrors
+                const double as = __ldg(tb.asF + i - 1), ac = __ldg(tb.acF + i - 1);
+                const int ipm = Nx + 2 - ip;
+                const bool has_mirror = (t != 0) && (t != half);
+                int im = ipm + shift; if (im > Nx) im -= Nx;
+                const size_t om = row + (size_t)(im + Hx - 1);
+#pragma unroll 1
+                for (int fy = 0; fy < 2; ++fy) {                // fy = 0: FC (y-Center), 1: FF
+                    const PointCore c = tripolar_core(as, ac, fy ? chF : chC, fy ? shF : shC);
+                    const int loc = fy ? FF : FC;
+                    store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
+                    if (has_mirror)
+                        store_coord<FT>(a, loc, om, tripolar_finish(-c.lam_a, c.pole, false, ipm <= half, fpl), c.phi);
+                }
+            }
+            if (t < half) {   // x-Center: ip <-> Nx+1-ip, never self-paired
+                const double as = __ldg(tb.asC + i - 1), ac = __ldg(tb.acC + i - 1);
+                const int ipm = Nx + 1 - ip;
+                int im = ipm + shift; if (im > Nx) im -= Nx;
+                const size_t om = row + (size_t)(im + Hx - 1);
+#pragma unroll 1
+                for (int fy = 0; fy < 2; ++fy) {                // fy = 0: CC, 1: CF
+                    const PointCore c = tripolar_core(as, ac, fy ? chF : chC, fy ? shF : shC);
+                    const int loc = fy ? CF : CC;
+                    store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
+                    store_coord<FT>(a, loc, om, tripolar_finish(-c.lam_a, c.pole, false, ipm <= half, fpl), c.phi);
+                }
+            }
+        } else if (t <= half + 2 * Hx) {
+            // x halo element of this row: columns 1-Hx..0 and Nx+1..Nx+Hx
+            const int h = t - half - 1;                         // 0 .. 2Hx-1
+            const int I = h < Hx ? 1 - Hx + h : Nx + 1 + (h - Hx);
+            const size_t o = row + (size_t)(I + Hx - 1);
+#pragma unroll 1
+            for (int loc = 0; loc < 4; ++loc) {
+                double lam, phi;
+                coord_at(tb, g, fpl, loc, I, J, lam, phi);
+                store_coord<FT>(a, loc, o, lam, phi);
+            }
+        }
+        return;
+    }
+    // rows outside 1..Ny-1: one padded element per thread through the source map
+    if (t >= a.w.wnx) return;
+    const int I = a.w.I0 + t;
+#pragma unroll 1
+    for (int loc = 0; loc < 4; ++loc) {
+        double lam, phi;
+        coord_at(tb, g, fpl, loc, I, J, lam, phi);
+        store_coord<FT>(a, loc, row + t, lam, phi);
+    }
+}
+
 // ------------------------------------------------------------------ K2 (tile)
 // Tile of TX x TY cells.  Each staggering needs its coordinate on a (TX+1) x (TY+1) patch
 // (tripolar_grid_utils.jl:13-43):
@@ -366,8 +456,14 @@ template <typename FT>
 static int launch_coords(const BuildArgs& a, cudaStream_t s)
 {
     dim3 block(256), grid(ceil_div(a.w.wnx, 256), a.w.wny);
-    coords_kernel<FT><<<grid, block, 0, s>>>(a);
-    OSSG_LAUNCH_CHECK("coords_kernel");
+    const bool full_x = a.w.I0 == 1 - a.g.Hx && a.w.wnx == a.g.Nx + 2 * a.g.Hx;
+    if (full_x && a.g.Hx <= a.g.Nx / 2) {       // (wnx >= Nx/2 + 1 + 2Hx threads per row are available)
+        coords_pair_kernel<FT><<<grid, block, 0, s>>>(a);
+        OSSG_LAUNCH_CHECK("coords_pair_kernel");
+    } else {
+        coords_kernel<FT><<<grid, block, 0, s>>>(a);
+        OSSG_LAUNCH_CHECK("coords_kernel");
+    }
     return 0;
 }
 

@@ -108,24 +108,50 @@ OSSG_HD void latlon_row(int j, int Nx, int Ny, int Hy, double south, double R, d
 
 // ---------------------------------------------------------------- C1: one staggering point
 // as_i = a*sind(lam1D[ip]), ac_i = a*cosd(lam1D[ip]) (ip = pre-shift index), ch_j/sh_j = cosh/sinh psi_j
-OSSG_HD void tripolar_point(double as_i, double ac_i, double ch_j, double sh_j, bool ip_is_one,
-                            bool ip_le_half, double first_pole_longitude, double& lam, double& phi)
+//
+// Split in two so that the coordinate kernel can exploit the mirror symmetry of the map:
+// lam1D[ip'] = -lam1D[ip] (ip' = Nx+2-ip for faces, Nx+1-ip for centres) gives x' = -x, y' = y
+// EXACTLY (sind is odd, cosd even, to the last bit), hence atan(y'/x') = -atan(y/x) and the same
+// phi; only the cheap tail (hemisphere shift, pole shift, wrap) differs between the two points.
+struct PointCore {
+    double lam_a;     // -(180/pi) atan(y/x)             (:77, before the pole special case)
+    double phi;       // 90 - (360/pi) atan(sqrt(y^2+x^2)) (:78)
+    bool pole;        // on_the_north_pole                (:74)
+};
+
+OSSG_HD PointCore tripolar_core(double as_i, double ac_i, double ch_j, double sh_j)
 {
     const double x = as_i * ch_j;                                             // :67
     const double y = ac_i * sh_j;                                             // :68
-    const bool on_the_north_pole = (x == 0.0) & (y == 0.0);                   // :74
-    const double north_pole_value = ip_is_one ? -90.0 : 90.0;                 // :75
     constexpr double m180_pi = -180.0 / m::PI_F64;
     constexpr double p360_pi = 360.0 / m::PI_F64;
-    double l = on_the_north_pole ? north_pole_value : m180_pi * m::atan_f(y / x);   // :77
-    phi = 90.0 - p360_pi * m::atan_f(sqrt(y * y + x * x));                    // :78
+    PointCore c;
+    c.pole = (x == 0.0) & (y == 0.0);                                         // :74
+    c.lam_a = m180_pi * m::atan_f(y / x);                                     // :77
+    c.phi = 90.0 - p360_pi * m::atan_f(sqrt(y * y + x * x));                  // :78
+    return c;
+}
+
+// tail of the point: pole value (:75-77), hemisphere shift (:82), pole-longitude shift (:86), wrap (:87)
+OSSG_HD double tripolar_finish(double lam_a, bool pole, bool ip_is_one, bool ip_le_half, double first_pole_longitude)
+{
+    const double north_pole_value = ip_is_one ? -90.0 : 90.0;                 // :75
+    double l = pole ? north_pole_value : lam_a;                               // :77
     l += ip_le_half ? -90.0 : 90.0;                                           // :82
     l += first_pole_longitude + 90.0;                                         // :86
-    // convert_to_0_360, src/OrthogonalSphericalShellGrids.jl:24 (fmod(l,360) == l when |l| < 360)
-    // (r in [360, 720): r - 360 is exact by Sterbenz and equals fmod(r, 360))
+    // convert_to_0_360, src/OrthogonalSphericalShellGrids.jl:24 (fmod(l,360) == l when |l| < 360;
+    // r in [360, 720): r - 360 is exact by Sterbenz and equals fmod(r, 360))
     double r = (fabs(l) < 360.0) ? l : fmod(l, 360.0);
     r += 360.0;
-    lam = (r < 360.0) ? r : (r < 720.0) ? (r - 360.0) : fmod(r, 360.0);
+    return (r < 360.0) ? r : (r < 720.0) ? (r - 360.0) : fmod(r, 360.0);
+}
+
+OSSG_HD void tripolar_point(double as_i, double ac_i, double ch_j, double sh_j, bool ip_is_one,
+                            bool ip_le_half, double first_pole_longitude, double& lam, double& phi)
+{
+    const PointCore c = tripolar_core(as_i, ac_i, ch_j, sh_j);
+    phi = c.phi;
+    lam = tripolar_finish(c.lam_a, c.pole, ip_is_one, ip_le_half, first_pole_longitude);
 }
 
 // ---------------------------------------------------------------- C3 / M2 index maps
