@@ -67,8 +67,10 @@ __global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, d
         const double phi = face ? phi_face(j, Ny, south) : phi_center(j, Ny, south);
         const double psi = m::asinh_cr(m::tand((90.0 - phi) / 2) / a);   // :66
         const int o = face ? 0 : 2;
-        ys[(size_t)(o + 0) * Ny + (j - 1)] = m::cosh_cr(psi);
-        ys[(size_t)(o + 1) * Ny + (j - 1)] = m::sinh_cr(psi);
+        double sh, ch;
+        m::sinh_cosh_cr(psi, sh, ch);
+        ys[(size_t)(o + 0) * Ny + (j - 1)] = ch;
+        ys[(size_t)(o + 1) * Ny + (j - 1)] = sh;
     } else if (t < 2 * Nx + 2 * Ny + g.Hy + 1) {
         const int r = t - 2 * Nx - 2 * Ny;                  // row r <-> j = r + 1 - Hy
         latlon_row(r + 1 - g.Hy, Nx, Ny, g.Hy, south, radius, ll + (size_t)r * LL_NCOL);
@@ -133,7 +135,7 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
 }
 
 template <typename FT>
-__global__ void __launch_bounds__(256) coords_pair_kernel(const __grid_constant__ BuildArgs a)
+__global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_constant__ BuildArgs a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int jw = blockIdx.y;

@@ -154,6 +154,12 @@ OSSG_HD void tripolar_point(double as_i, double ac_i, double ch_j, double sh_j, 
     lam = tripolar_finish(c.lam_a, c.pole, ip_is_one, ip_le_half, first_pole_longitude);
 }
 
+OSSG_HD_NOINLINE void tripolar_point_ool(double as_i, double ac_i, double ch_j, double sh_j, bool ip_is_one,
+                                         bool ip_le_half, double first_pole_longitude, double& lam, double& phi)
+{
+    tripolar_point(as_i, ac_i, ch_j, sh_j, ip_is_one, ip_le_half, first_pole_longitude, lam, phi);
+}
+
 // ---------------------------------------------------------------- C3 / M2 index maps
 // Source of the padded element (I, J) of a field at (locx, locy) after
 //   zipper north fill over i in 1..Nx (src/zipper_boundary_condition.jl:70-138, sign handled by
@@ -194,7 +200,7 @@ OSSG_HD void coord_at(const Tables& tb, const GridDims& g, double first_pole_lon
     const double ac_i = fx ? tb.acF[i - 1] : tb.acC[i - 1];
     const double ch_j = fy ? tb.chF[j - 1] : tb.chC[j - 1];
     const double sh_j = fy ? tb.shF[j - 1] : tb.shC[j - 1];
-    tripolar_point(as_i, ac_i, ch_j, sh_j, ip == 1, ip <= g.Nx / 2, first_pole_longitude, lam, phi);
+    tripolar_point_ool(as_i, ac_i, ch_j, sh_j, ip == 1, ip <= g.Nx / 2, first_pole_longitude, lam, phi);
 }
 
 // ---------------------------------------------------------------- M1 formulas
@@ -251,6 +257,20 @@ OSSG_HD double spherical_area_quadrilateral(const Vec3& a, const Vec3& b, const 
     return 0.5 * (2 * m::atan_f(t_abc) + 2 * m::atan_f(t_abd) + 2 * m::atan_f(t_acd) + 2 * m::atan_f(t_bcd));
 }
 
+// Out-of-line copies for the generic (cold) per-element path: the halo-frame kernel evaluates
+// metrics_cell up to four times per element, fully inlined that is ~17k SASS instructions which
+// run once each -- an instruction-cache miss per line.  Same arithmetic, one copy of the code.
+OSSG_HD_NOINLINE double haversine_pre_ool(double lam_x, double phi1r, double c1, double lam_y, double phi2r, double c2, double radius)
+{
+    return haversine_pre(lam_x, phi1r, c1, lam_y, phi2r, c2, radius);
+}
+OSSG_HD_NOINLINE double cos_rad_ool(double x) { return m::cos_rad(x); }
+OSSG_HD_NOINLINE Vec3 lat_lon_to_cartesian_ool(double lat, double lon) { return lat_lon_to_cartesian(lat, lon); }
+OSSG_HD_NOINLINE double spherical_area_quadrilateral_ool(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d)
+{
+    return spherical_area_quadrilateral(a, b, c, d);
+}
+
 // metric ids in C-ABI order
 enum Metric : int { DX_CC = 0, DX_FC, DX_CF, DX_FF, DY_CC, DY_CF, DY_FC, DY_FF, AZ_CC, AZ_FC, AZ_CF, AZ_FF, N_METRIC };
 // staggering class of each metric (which halo map applies to it in M2)
@@ -276,58 +296,58 @@ OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask,
     if (want_cf || want_fc || want_cc) {
         acc(FF, i, j, l0, p0); acc(FF, i + 1, j, l1, p1); acc(FF, i + 1, j + 1, l2, p2); acc(FF, i, j + 1, l3, p3);
         const double r0 = p0 * D2R, r1 = p1 * D2R, r3 = p3 * D2R;
-        const double c0 = m::cos_rad(r0);
-        if (want_cf) out[DX_CF] = haversine_pre(l1, r1, m::cos_rad(r1), l0, r0, c0, R);      // utils.jl:15
-        if (want_fc) out[DY_FC] = haversine_pre(l3, r3, m::cos_rad(r3), l0, r0, c0, R);      // :19
+        const double c0 = cos_rad_ool(r0);
+        if (want_cf) out[DX_CF] = haversine_pre_ool(l1, r1, cos_rad_ool(r1), l0, r0, c0, R);      // utils.jl:15
+        if (want_fc) out[DY_FC] = haversine_pre_ool(l3, r3, cos_rad_ool(r3), l0, r0, c0, R);      // :19
         if (want_cc) {
-            const Vec3 a = lat_lon_to_cartesian(p0, l0), b = lat_lon_to_cartesian(p1, l1);
-            const Vec3 c = lat_lon_to_cartesian(p2, l2), d = lat_lon_to_cartesian(p3, l3);
-            out[AZ_CC] = spherical_area_quadrilateral(a, b, c, d) * (R * R);               // :23-28
+            const Vec3 a = lat_lon_to_cartesian_ool(p0, l0), b = lat_lon_to_cartesian_ool(p1, l1);
+            const Vec3 c = lat_lon_to_cartesian_ool(p2, l2), d = lat_lon_to_cartesian_ool(p3, l3);
+            out[AZ_CC] = spherical_area_quadrilateral_ool(a, b, c, d) * (R * R);               // :23-28
         }
     }
     // CC points: (i,j) (i-1,j) (i,j-1) (i-1,j-1)     -> dx_fc, dy_cf, az_ff
     if (want_fc || want_cf || want_ff) {
         acc(CC, i, j, l0, p0); acc(CC, i - 1, j, l1, p1); acc(CC, i, j - 1, l2, p2); acc(CC, i - 1, j - 1, l3, p3);
         const double r0 = p0 * D2R, r1 = p1 * D2R, r2 = p2 * D2R;
-        const double c0 = m::cos_rad(r0);
-        if (want_fc) out[DX_FC] = haversine_pre(l0, r0, c0, l1, r1, m::cos_rad(r1), R);      // :14
-        if (want_cf) out[DY_CF] = haversine_pre(l0, r0, c0, l2, r2, m::cos_rad(r2), R);      // :20
+        const double c0 = cos_rad_ool(r0);
+        if (want_fc) out[DX_FC] = haversine_pre_ool(l0, r0, c0, l1, r1, cos_rad_ool(r1), R);      // :14
+        if (want_cf) out[DY_CF] = haversine_pre_ool(l0, r0, c0, l2, r2, cos_rad_ool(r2), R);      // :20
         if (want_ff) {
-            const Vec3 a = lat_lon_to_cartesian(p3, l3), b = lat_lon_to_cartesian(p2, l2);
-            const Vec3 c = lat_lon_to_cartesian(p0, l0), d = lat_lon_to_cartesian(p1, l1);
-            out[AZ_FF] = spherical_area_quadrilateral(a, b, c, d) * (R * R);               // :38-43
+            const Vec3 a = lat_lon_to_cartesian_ool(p3, l3), b = lat_lon_to_cartesian_ool(p2, l2);
+            const Vec3 c = lat_lon_to_cartesian_ool(p0, l0), d = lat_lon_to_cartesian_ool(p1, l1);
+            out[AZ_FF] = spherical_area_quadrilateral_ool(a, b, c, d) * (R * R);               // :38-43
         }
     }
     // FC points: (i,j) (i+1,j) (i,j-1)               -> dx_cc, dy_ff
     if (want_cc || want_ff) {
         acc(FC, i, j, l0, p0);
         const double r0 = p0 * D2R;
-        const double c0 = m::cos_rad(r0);
+        const double c0 = cos_rad_ool(r0);
         if (want_cc) {
             acc(FC, i + 1, j, l1, p1);
             const double r1 = p1 * D2R;
-            out[DX_CC] = haversine_pre(l1, r1, m::cos_rad(r1), l0, r0, c0, R);              // :13
+            out[DX_CC] = haversine_pre_ool(l1, r1, cos_rad_ool(r1), l0, r0, c0, R);              // :13
         }
         if (want_ff) {
             acc(FC, i, j - 1, l2, p2);
             const double r2 = p2 * D2R;
-            out[DY_FF] = haversine_pre(l0, r0, c0, l2, r2, m::cos_rad(r2), R);              // :21
+            out[DY_FF] = haversine_pre_ool(l0, r0, c0, l2, r2, cos_rad_ool(r2), R);              // :21
         }
     }
     // CF points: (i,j) (i-1,j) (i,j+1)               -> dx_ff, dy_cc
     if (want_ff || want_cc) {
         acc(CF, i, j, l0, p0);
         const double r0 = p0 * D2R;
-        const double c0 = m::cos_rad(r0);
+        const double c0 = cos_rad_ool(r0);
         if (want_ff) {
             acc(CF, i - 1, j, l1, p1);
             const double r1 = p1 * D2R;
-            out[DX_FF] = haversine_pre(l0, r0, c0, l1, r1, m::cos_rad(r1), R);              // :16
+            out[DX_FF] = haversine_pre_ool(l0, r0, c0, l1, r1, cos_rad_ool(r1), R);              // :16
         }
         if (want_cc) {
             acc(CF, i, j + 1, l3, p3);
             const double r3 = p3 * D2R;
-            out[DY_CC] = haversine_pre(l3, r3, m::cos_rad(r3), l0, r0, c0, R);              // :18
+            out[DY_CC] = haversine_pre_ool(l3, r3, cos_rad_ool(r3), l0, r0, c0, R);              // :18
         }
     }
     if (want_fc) out[AZ_FC] = out[DY_FC] * out[DX_FC];                                     // :34
