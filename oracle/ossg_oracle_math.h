@@ -160,9 +160,20 @@ static inline int om_rem_pio2(double x, double *y0, double *y1)
     return (int)fn;
 }
 
+/* |x| < 2^-5: Taylor through x^7 (truncation z^4/9! < 2.6e-18 relative, below 0.03 ulp);
+ * the haversine half-differences of every grid finer than ~3.5 degrees land here */
+#define OM_SMALL_ARG 0x1p-5
+static inline double om_sin_small(double x)
+{
+    const double T1 = -0x1.5555555555555p-3, T2 = 0x1.1111111111111p-7, T3 = -0x1.a01a01a01a01ap-13;
+    double z = x * x;
+    return fma(x * z, fma(z, fma(z, T3, T2), T1), x);
+}
+
 static inline double om_sin(double x)
 {
     if (isnan(x) || isinf(x)) return NAN;
+    if (fabs(x) < OM_SMALL_ARG) return om_sin_small(x);
     if (fabs(x) <= OM_PIO4_HI) return om_ksin(x, 0.0);
     double y0, y1;
     int n = om_rem_pio2(x, &y0, &y1);
@@ -250,10 +261,15 @@ static inline double om_asin(double x)
         if (ax == 1.0) return fma(x, OM_PIO2_HI, x * OM_PIO2_LO);
         return NAN;
     }
-    if (ax < 0.5) {
-        if (ax < 0x1p-26) return x;
-        return fma(x, om_asin_R(x * x), x);
+    if (ax < OM_SMALL_ARG) {
+        /* Taylor through x^11 (truncation (10395/599040) t^6 < 1.6e-20 relative) */
+        const double A1 = 0x1.5555555555555p-3, A2 = 0x1.3333333333333p-4, A3 = 0x1.6db6db6db6db7p-5,
+                     A4 = 0x1.f1c71c71c71c7p-6, A5 = 0x1.6e8ba2e8ba2e9p-6;
+        double t = x * x;
+        double p = fma(t, fma(t, fma(t, fma(t, A5, A4), A3), A2), A1);
+        return fma(x, t * p, x);
     }
+    if (ax < 0.5) return fma(x, om_asin_R(x * x), x);
     double w = 1.0 - ax;
     double t = w * 0.5;
     double r = om_asin_R(t);

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) double smem[];
     double* s_lam = smem;                     // [4][QPTS]  lambda (degrees)
-    double* s_phr = smem + 4 * QPTS;          // [4][QPTS]  phi (degrees) during staging, then deg2rad(phi)
+    double* s_phr = smem + 4 * QPTS;          // [4][QPTS]  phi (degrees) during staging, then deg2rad(phi)/2
     double* s_cos = smem + 8 * QPTS;          // [4][QPTS]  cos(deg2rad(phi))
     double* s_ux = smem + 12 * QPTS;          // [2][QPTS]  unit vectors: slot 0 = CC, slot 1 = FF
     double* s_uy = smem + 14 * QPTS;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
 #pragma unroll 1
     for (int t = tid; t < TASKS; t += NT) {
         const double phr = s_phr[t] * D2R;
-        s_phr[t] = phr;
+        s_phr[t] = 0.5 * phr;                             // the haversines want deg2rad(phi)/2
         s_cos[t] = m::cos_rad(phr);
     }
     __syncthreads();
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     // patch index of this cell's own point per staggering (index = loc)
     const int own_cc = (ty + 1) * QX + tx + 1, own_fc = (ty + 1) * QX + tx, own_cf = ty * QX + tx + 1, own_ff = ty * QX + tx;
 
-#define HAV(L, px, py) haversine_pre(s_lam[(L) * QPTS + (px)], s_phr[(L) * QPTS + (px)], s_cos[(L) * QPTS + (px)], \
+#define HAV(L, px, py) haversine_hot(s_lam[(L) * QPTS + (px)], s_phr[(L) * QPTS + (px)], s_cos[(L) * QPTS + (px)], \
                                      s_lam[(L) * QPTS + (py)], s_phr[(L) * QPTS + (py)], s_cos[(L) * QPTS + (py)], R)
     // ---- 8 haversines as 4 rolled iterations of 2 (one copy of the code in the instruction cache)
     //   it 0: dx_fc = hav(CC[i,j], CC[i-1,j])   dy_fc = hav(FF[i,j+1], FF[i,j])   az_fc = dy_fc * dx_fc   (:14,:19,:34)
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
         const Vec3 vb{ s_ux[b + 1], s_uy[b + 1], s_uz[b + 1] };
         const Vec3 vc{ s_ux[b + QX + 1], s_uy[b + QX + 1], s_uz[b + QX + 1] };
         const Vec3 vd{ s_ux[b + QX], s_uy[b + QX], s_uz[b + QX] };
-        store_metric<FT>(a, q ? AZ_CC : AZ_FF, o, spherical_area_quadrilateral(va, vb, vc, vd) * (R * R));
+        store_metric<FT>(a, q ? AZ_CC : AZ_FF, o, spherical_area_quadrilateral_hot(va, vb, vc, vd) * (R * R));
     }
 }
 

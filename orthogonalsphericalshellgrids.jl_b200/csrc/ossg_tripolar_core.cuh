@@ -204,32 +204,65 @@ OSSG_HD void coord_at(const Tables& tb, const GridDims& g, double first_pole_lon
 }
 
 // ---------------------------------------------------------------- M1 formulas
-// (external) Distances.jl 0.10 Haversine()(x, y): x = (lam, phi) of the first point.  phi1r, phi2r
-// are deg2rad(phi) = phi * (pi/180), c1, c2 their cosines (hoisted per point by the tile kernel).
+// (external) Distances.jl 0.10 Haversine()(x, y): x = (lam, phi) of the first point.
+//     dlam = deg2rad(lam_y - lam_x); dphi = phi2 - phi1 (radians)
+//     a = sin(dphi/2)^2 + cos(phi1) cos(phi2) sin(dlam/2)^2;  2 (R asin(min(sqrt(a), 1)))
+// Callers pass hphi = deg2rad(phi)/2 and c = cos(deg2rad(phi)) (hoisted per point by the tile
+// kernel).  Halving is exact, so hphi2 - hphi1 == (phi2 - phi1)/2 and
+// (lam_y - lam_x) * (D2R/2) == ((lam_y - lam_x) * D2R)/2 bit for bit.
 constexpr double D2R = m::PI_F64 / 180.0;
+constexpr double HALF_D2R = D2R * 0.5;
 
-OSSG_HD double haversine_pre(double lam_x, double phi1r, double c1, double lam_y, double phi2r, double c2, double radius)
+OSSG_HD double haversine_tail(double hdphi, double hdlam, double c1, double c2, double radius)
 {
-    const double dlam = (lam_y - lam_x) * D2R;
-    const double dphi = phi2r - phi1r;
-    const double s1 = m::sin_rad(dphi / 2);
-    const double s2 = m::sin_rad(dlam / 2);
+    const double s1 = m::sin_rad(hdphi);
+    const double s2 = m::sin_rad(hdlam);
     const double a = s1 * s1 + c1 * c2 * (s2 * s2);
     double r = sqrt(a);
     if (!(r < 1.0)) r = (r != r) ? r : 1.0;                 // min(sqrt(a), 1)
     return 2 * (radius * m::asin_f(r));
 }
+OSSG_HD_NOINLINE double haversine_tail_ool(double hdphi, double hdlam, double c1, double c2, double radius)
+{
+    return haversine_tail(hdphi, hdlam, c1, c2, radius);
+}
+
+OSSG_HD double haversine_pre(double lam_x, double hphi1, double c1, double lam_y, double hphi2, double c2, double radius)
+{
+    return haversine_tail(hphi2 - hphi1, (lam_y - lam_x) * HALF_D2R, c1, c2, radius);
+}
+
+// The same value for the tile kernel.  Both half-differences below 2^-6 (spacings under ~1.8
+// degrees): both sines take their small path, a <= 2^-12 (1 + c1 c2) keeps sqrt(a) below 2^-5, so
+// min(.,1) is the identity and asin takes its small path too -- one predicate, straight-line code.
+// Anything else (pole neighbourhoods, coarse grids, NaN) goes through the general function.
+constexpr double HAV_HOT = 0x1p-6;
+OSSG_HD double haversine_hot(double lam_x, double hphi1, double c1, double lam_y, double hphi2, double c2, double radius)
+{
+    const double hdphi = hphi2 - hphi1;
+    const double hdlam = (lam_y - lam_x) * HALF_D2R;
+    if ((fabs(hdphi) < HAV_HOT) & (fabs(hdlam) < HAV_HOT)) {
+        const double s1 = m::sin_small(hdphi);
+        const double s2 = m::sin_small(hdlam);
+        const double a = s1 * s1 + c1 * c2 * (s2 * s2);
+        return 2 * (radius * m::asin_small(sqrt(a)));
+    }
+    return haversine_tail_ool(hdphi, hdlam, c1, c2, radius);
+}
 
 struct Vec3 { double x, y, z; };
 
-// (external) Oceananigans.Grids.lat_lon_to_cartesian(lat, lon, 1)
+// (external) Oceananigans.Grids.lat_lon_to_cartesian(lat, lon, 1) =
+//     (cosd(lon) cosd(lat), sind(lon) cosd(lat), sind(lat))
 OSSG_HD Vec3 lat_lon_to_cartesian(double lat, double lon)
 {
-    const double cl = m::cosd(lat);
+    double sin_lat, cos_lat, sin_lon, cos_lon;
+    m::sincosd(lat, sin_lat, cos_lat);
+    m::sincosd(lon, sin_lon, cos_lon);
     Vec3 v;
-    v.x = m::cosd(lon) * cl;
-    v.y = m::sind(lon) * cl;
-    v.z = m::sind(lat);
+    v.x = cos_lon * cos_lat;
+    v.y = sin_lon * cos_lat;
+    v.z = sin_lat;
     return v;
 }
 OSSG_HD double dot3(const Vec3& a, const Vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -245,24 +278,43 @@ OSSG_HD Vec3 cross3(const Vec3& a, const Vec3& b)
 // (a,b,c), (a,b,d), (a,c,d), (b,c,d); triangle area = 2 atan(|a1.(a2 x a3)| / (1 + a1.a2 + a2.a3 + a1.a3)).
 // The six pair dot products and three cross products are shared between the triangles; each
 // value is produced by the same expression as in the unshared form.
-OSSG_HD double spherical_area_quadrilateral(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d)
+struct QuadTans { double abc, abd, acd, bcd; };
+OSSG_HD QuadTans quadrilateral_tangents(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d)
 {
     const double ab = dot3(a, b), ac = dot3(a, c), ad = dot3(a, d);
     const double bc = dot3(b, c), bd = dot3(b, d), cd = dot3(c, d);
     const Vec3 bxc = cross3(b, c), bxd = cross3(b, d), cxd = cross3(c, d);
-    const double t_abc = fabs(dot3(a, bxc)) / (1 + ab + bc + ac);
-    const double t_abd = fabs(dot3(a, bxd)) / (1 + ab + bd + ad);
-    const double t_acd = fabs(dot3(a, cxd)) / (1 + ac + cd + ad);
-    const double t_bcd = fabs(dot3(b, cxd)) / (1 + bc + cd + bd);
+    QuadTans t;
+    t.abc = fabs(dot3(a, bxc)) / (1 + ab + bc + ac);
+    t.abd = fabs(dot3(a, bxd)) / (1 + ab + bd + ad);
+    t.acd = fabs(dot3(a, cxd)) / (1 + ac + cd + ad);
+    t.bcd = fabs(dot3(b, cxd)) / (1 + bc + cd + bd);
+    return t;
+}
+OSSG_HD double spherical_area_quadrilateral(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d)
+{
+    const QuadTans t = quadrilateral_tangents(a, b, c, d);
+    return 0.5 * (2 * m::atan_f(t.abc) + 2 * m::atan_f(t.abd) + 2 * m::atan_f(t.acd) + 2 * m::atan_f(t.bcd));
+}
+OSSG_HD_NOINLINE double quadrilateral_from_tangents_ool(double t_abc, double t_abd, double t_acd, double t_bcd)
+{
     return 0.5 * (2 * m::atan_f(t_abc) + 2 * m::atan_f(t_abd) + 2 * m::atan_f(t_acd) + 2 * m::atan_f(t_bcd));
+}
+// tile-kernel form: all four tangents below ATAN_SHORT (cells under ~1.1 degrees) -> short atan
+OSSG_HD double spherical_area_quadrilateral_hot(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d)
+{
+    const QuadTans t = quadrilateral_tangents(a, b, c, d);
+    if ((fabs(t.abc) < m::ATAN_SHORT) & (fabs(t.abd) < m::ATAN_SHORT) & (fabs(t.acd) < m::ATAN_SHORT) & (fabs(t.bcd) < m::ATAN_SHORT))
+        return 0.5 * (2 * m::atan_short(t.abc) + 2 * m::atan_short(t.abd) + 2 * m::atan_short(t.acd) + 2 * m::atan_short(t.bcd));
+    return quadrilateral_from_tangents_ool(t.abc, t.abd, t.acd, t.bcd);
 }
 
 // Out-of-line copies for the generic (cold) per-element path: the halo-frame kernel evaluates
 // metrics_cell up to four times per element, fully inlined that is ~17k SASS instructions which
 // run once each -- an instruction-cache miss per line.  Same arithmetic, one copy of the code.
-OSSG_HD_NOINLINE double haversine_pre_ool(double lam_x, double phi1r, double c1, double lam_y, double phi2r, double c2, double radius)
+OSSG_HD_NOINLINE double haversine_pre_ool(double lam_x, double hphi1, double c1, double lam_y, double hphi2, double c2, double radius)
 {
-    return haversine_pre(lam_x, phi1r, c1, lam_y, phi2r, c2, radius);
+    return haversine_pre(lam_x, hphi1, c1, lam_y, hphi2, c2, radius);
 }
 OSSG_HD_NOINLINE double cos_rad_ool(double x) { return m::cos_rad(x); }
 OSSG_HD_NOINLINE Vec3 lat_lon_to_cartesian_ool(double lat, double lon) { return lat_lon_to_cartesian(lat, lon); }
@@ -297,8 +349,8 @@ OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask,
         acc(FF, i, j, l0, p0); acc(FF, i + 1, j, l1, p1); acc(FF, i + 1, j + 1, l2, p2); acc(FF, i, j + 1, l3, p3);
         const double r0 = p0 * D2R, r1 = p1 * D2R, r3 = p3 * D2R;
         const double c0 = cos_rad_ool(r0);
-        if (want_cf) out[DX_CF] = haversine_pre_ool(l1, r1, cos_rad_ool(r1), l0, r0, c0, R);      // utils.jl:15
-        if (want_fc) out[DY_FC] = haversine_pre_ool(l3, r3, cos_rad_ool(r3), l0, r0, c0, R);      // :19
+        if (want_cf) out[DX_CF] = haversine_pre_ool(l1, 0.5 * r1, cos_rad_ool(r1), l0, 0.5 * r0, c0, R);      // utils.jl:15
+        if (want_fc) out[DY_FC] = haversine_pre_ool(l3, 0.5 * r3, cos_rad_ool(r3), l0, 0.5 * r0, c0, R);      // :19
         if (want_cc) {
             const Vec3 a = lat_lon_to_cartesian_ool(p0, l0), b = lat_lon_to_cartesian_ool(p1, l1);
             const Vec3 c = lat_lon_to_cartesian_ool(p2, l2), d = lat_lon_to_cartesian_ool(p3, l3);
@@ -310,8 +362,8 @@ OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask,
         acc(CC, i, j, l0, p0); acc(CC, i - 1, j, l1, p1); acc(CC, i, j - 1, l2, p2); acc(CC, i - 1, j - 1, l3, p3);
         const double r0 = p0 * D2R, r1 = p1 * D2R, r2 = p2 * D2R;
         const double c0 = cos_rad_ool(r0);
-        if (want_fc) out[DX_FC] = haversine_pre_ool(l0, r0, c0, l1, r1, cos_rad_ool(r1), R);      // :14
-        if (want_cf) out[DY_CF] = haversine_pre_ool(l0, r0, c0, l2, r2, cos_rad_ool(r2), R);      // :20
+        if (want_fc) out[DX_FC] = haversine_pre_ool(l0, 0.5 * r0, c0, l1, 0.5 * r1, cos_rad_ool(r1), R);      // :14
+        if (want_cf) out[DY_CF] = haversine_pre_ool(l0, 0.5 * r0, c0, l2, 0.5 * r2, cos_rad_ool(r2), R);      // :20
         if (want_ff) {
             const Vec3 a = lat_lon_to_cartesian_ool(p3, l3), b = lat_lon_to_cartesian_ool(p2, l2);
             const Vec3 c = lat_lon_to_cartesian_ool(p0, l0), d = lat_lon_to_cartesian_ool(p1, l1);
@@ -326,12 +378,12 @@ OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask,
         if (want_cc) {
             acc(FC, i + 1, j, l1, p1);
             const double r1 = p1 * D2R;
-            out[DX_CC] = haversine_pre_ool(l1, r1, cos_rad_ool(r1), l0, r0, c0, R);              // :13
+            out[DX_CC] = haversine_pre_ool(l1, 0.5 * r1, cos_rad_ool(r1), l0, 0.5 * r0, c0, R);              // :13
         }
         if (want_ff) {
             acc(FC, i, j - 1, l2, p2);
             const double r2 = p2 * D2R;
-            out[DY_FF] = haversine_pre_ool(l0, r0, c0, l2, r2, cos_rad_ool(r2), R);              // :21
+            out[DY_FF] = haversine_pre_ool(l0, 0.5 * r0, c0, l2, 0.5 * r2, cos_rad_ool(r2), R);              // :21
         }
     }
     // CF points: (i,j) (i-1,j) (i,j+1)               -> dx_ff, dy_cc
@@ -342,12 +394,12 @@ OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask,
         if (want_ff) {
             acc(CF, i - 1, j, l1, p1);
             const double r1 = p1 * D2R;
-            out[DX_FF] = haversine_pre_ool(l0, r0, c0, l1, r1, cos_rad_ool(r1), R);              // :16
+            out[DX_FF] = haversine_pre_ool(l0, 0.5 * r0, c0, l1, 0.5 * r1, cos_rad_ool(r1), R);              // :16
         }
         if (want_cc) {
             acc(CF, i, j + 1, l3, p3);
             const double r3 = p3 * D2R;
-            out[DY_CC] = haversine_pre_ool(l3, r3, cos_rad_ool(r3), l0, r0, c0, R);              // :18
+            out[DY_CC] = haversine_pre_ool(l3, 0.5 * r3, cos_rad_ool(r3), l0, 0.5 * r0, c0, R);              // :18
         }
     }
     if (want_fc) out[AZ_FC] = out[DY_FC] * out[DX_FC];                                     // :34

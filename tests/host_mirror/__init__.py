@@ -35,6 +35,8 @@ def load():
     lib.hm_coords.argtypes = [C.POINTER(HMParams), vpp]
     lib.hm_metrics.argtypes = [C.POINTER(HMParams), vpp, vpp, C.c_int]
     lib.hm_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.hm_haversine.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.hm_quadrilateral.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.hm_halo_source.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_int)] * 3
     return lib
 
@@ -71,4 +73,20 @@ def math(lib, fn, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.empty_like(x)
     assert lib.hm_math_eval(fn, x.ctypes.data, y.ctypes.data, x.size) == 0
+    return y
+
+
+def haversine(lib, hot, rows):
+    """rows: n x 7 (lam_x, hphi1, c1, lam_y, hphi2, c2, R)"""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    y = np.empty(rows.shape[0])
+    assert lib.hm_haversine(int(hot), rows.ctypes.data, y.ctypes.data, rows.shape[0]) == 0
+    return y
+
+
+def quadrilateral(lib, hot, rows):
+    """rows: n x 8 (lat, lon of corners a, b, c, d in degrees)"""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    y = np.empty(rows.shape[0])
+    assert lib.hm_quadrilateral(int(hot), rows.ctypes.data, y.ctypes.data, rows.shape[0]) == 0
     return y

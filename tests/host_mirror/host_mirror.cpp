@@ -125,8 +125,33 @@ int hm_math_eval(int fn, const double* x, double* y, size_t n)
         case 7: y[e] = m::asinh_cr(x[e]); break;
         case 8: y[e] = m::sinh_cr(x[e]); break;
         case 9: y[e] = m::cosh_cr(x[e]); break;
+        case 10: { double sn, cs; m::sincosd(x[e], sn, cs); y[e] = sn; break; }
+        case 11: { double sn, cs; m::sincosd(x[e], sn, cs); y[e] = cs; break; }
+        case 12: y[e] = m::atan_short(x[e]); break;          // callers restrict |x| < ATAN_SHORT
         default: return -1;
         }
+    }
+    return 0;
+}
+
+// tile-kernel ("hot") forms against the general ones: in = n x 7 (lam_x, hphi1, c1, lam_y, hphi2, c2, R)
+int hm_haversine(int hot, const double* in, double* out, size_t n)
+{
+    for (size_t e = 0; e < n; ++e) {
+        const double* v = in + 7 * e;
+        out[e] = hot ? haversine_hot(v[0], v[1], v[2], v[3], v[4], v[5], v[6])
+                     : haversine_pre(v[0], v[1], v[2], v[3], v[4], v[5], v[6]);
+    }
+    return 0;
+}
+// in = n x 8 (lat, lon of the four corners a, b, c, d)
+int hm_quadrilateral(int hot, const double* in, double* out, size_t n)
+{
+    for (size_t e = 0; e < n; ++e) {
+        const double* v = in + 8 * e;
+        const Vec3 a = lat_lon_to_cartesian(v[0], v[1]), b = lat_lon_to_cartesian(v[2], v[3]);
+        const Vec3 c = lat_lon_to_cartesian(v[4], v[5]), d = lat_lon_to_cartesian(v[6], v[7]);
+        out[e] = hot ? spherical_area_quadrilateral_hot(a, b, c, d) : spherical_area_quadrilateral(a, b, c, d);
     }
     return 0;
 }

@@ -77,3 +77,69 @@ def test_functions_agree_with_glibc_within_one_ulp(oracle, oracle_libm):
         a, b = oracle.math(name, xs), oracle_libm.math(name, xs)
         ulps = np.abs(a - b) / np.spacing(np.maximum(np.abs(b), 1e-300))
         assert ulps.max() <= 1.0, name
+
+
+# ------------------------------------------------------------------ small-argument / hot paths
+def test_small_argument_paths_against_mpmath(oracle):
+    """sin and asin below 2^-5 use short Taylor forms (every grid finer than ~3.5 degrees lands
+    there); they must be as accurate as the fdlibm kernels they shortcut, on both sides of the
+    switch."""
+    xs = np.concatenate([RNG.uniform(-2.0 ** -5, 2.0 ** -5, 3000), 10.0 ** RNG.uniform(-12, -1.5, 2000),
+                         np.nextafter(2.0 ** -5, [0.0, 1.0]), [2.0 ** -5, -2.0 ** -5, 7.0e-4, 1.45e-3]])
+    assert ulp_errors(oracle.math("sin", xs), xs, mp.sin) <= 0.56
+    assert ulp_errors(oracle.math("asin", xs), xs, mp.asin) <= 0.56
+
+
+def test_sincosd_is_bit_identical_to_sind_and_cosd(mirror):
+    xs = np.concatenate([RNG.uniform(-720, 720, 200000), np.arange(-720.0, 721.0, 15.0),
+                         np.nextafter(np.arange(-360.0, 361.0, 45.0), np.inf), np.nextafter(np.arange(-360.0, 361.0, 45.0), -np.inf),
+                         [0.0, -0.0, 1e-300, -1e-300, np.inf, np.nan]])
+    for both, one in ((10, 0), (11, 1)):
+        a, b = hm.math(mirror, both, xs), hm.math(mirror, one, xs)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_atan_short_is_bit_identical_to_atan_below_its_threshold(mirror, oracle):
+    xs = np.concatenate([RNG.uniform(-1.0e-4, 1.0e-4, 300000), 10.0 ** RNG.uniform(-300, -4, 100000),
+                         -(10.0 ** RNG.uniform(-30, -4, 1000)), np.nextafter(1.0e-4, 0.0) * np.array([1.0, -1.0]),
+                         [0.0, -0.0, 2.0 ** -27, 2.0 ** -28, 5e-324]])
+    xs = xs[np.abs(xs) < 1.0e-4]
+    a = hm.math(mirror, 12, xs)
+    assert np.array_equal(a.view(np.uint64), hm.math(mirror, orc.MATH_FN["atan"], xs).view(np.uint64))
+    assert np.array_equal(a.view(np.uint64), oracle.math("atan", xs).view(np.uint64))
+
+
+def _haversine_rows(n, spread_deg):
+    lam_x = RNG.uniform(0, 360, n)
+    phi_x = RNG.uniform(-80, 90, n)
+    lam_y = lam_x + RNG.uniform(-spread_deg, spread_deg, n)
+    phi_y = np.clip(phi_x + RNG.uniform(-spread_deg, spread_deg, n), -90, 90)
+    d2r = np.pi / 180
+    r1, r2 = phi_x * d2r, phi_y * d2r
+    return np.stack([lam_x, 0.5 * r1, np.cos(r1), lam_y, 0.5 * r2, np.cos(r2), np.full(n, 6371.0e3)], axis=1)
+
+
+def test_tile_kernel_haversine_is_bit_identical_to_the_general_form(mirror):
+    """haversine_hot (one predicate, straight-line small paths) against haversine_pre across the
+    switch at 2^-6 rad half-difference (1.79 degrees), identical points and pole-like jumps."""
+    rows = np.concatenate([_haversine_rows(100000, s) for s in (1e-6, 0.08, 1.0, 3.4, 3.7, 8.0, 200.0)])
+    rows[:50, 3] = rows[:50, 0]; rows[:50, 4] = rows[:50, 1]; rows[:50, 5] = rows[:50, 2]   # identical points
+    a, b = hm.haversine(mirror, 1, rows), hm.haversine(mirror, 0, rows)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert (a[:50] == 0).all()
+
+
+def test_tile_kernel_quadrilateral_is_bit_identical_to_the_general_form(mirror):
+    """spherical_area_quadrilateral_hot (short atan when all four triangle tangents are below
+    1e-4) against the general form for cells from 1e-4 to 5 degrees, incl. degenerate ones."""
+    rows = []
+    for size in (1e-4, 1.0 / 12, 0.25, 0.9, 1.1, 1.3, 5.0):
+        n = 30000
+        lat = RNG.uniform(-80, 89, n); lon = RNG.uniform(0, 360, n)
+        j = lambda: RNG.uniform(-0.1, 0.1, n) * size
+        rows.append(np.stack([lat + j(), lon + j(), lat + j(), lon + size + j(), lat + size + j(), lon + size + j(),
+                              lat + size + j(), lon + j()], axis=1))
+    rows = np.concatenate(rows)
+    rows[:20, 2:4] = rows[:20, 0:2]                                      # two coincident corners
+    a, b = hm.quadrilateral(mirror, 1, rows), hm.quadrilateral(mirror, 0, rows)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
