@@ -167,6 +167,11 @@ int ossg_synth_field(const ossg_field_desc* f, uint64_t seed, int32_t gi0, int32
 /* sustained FP64 FMA rate of the current device: runs `iters` dependent-chain DFMA steps per
  * thread on a full grid; returns elapsed ms via *ms and executed flops via *flops              */
 int ossg_fp64_peak_probe(int iters, float* ms, double* flops, void* stream);
+/* device self-test of the branch-free sqrt / division used by the tile kernel's straight-line
+ * path (csrc/ossg_math.cuh sqrt_nb, div_nb) against the IEEE operators on n pseudo-random
+ * operands drawn from the ranges the kernel admits; mismatches[0] = sqrt, [1] = division
+ * (host pointers; the call synchronises the stream)                                            */
+int ossg_selftest_sqrt_div(uint64_t n, uint64_t seed, uint64_t mismatches[2], void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libossg_b200.so")
+LIB_PATH = os.environ.get("OSSG_B200_LIB") or os.path.join(_PKG, "libossg_b200.so")   # (override: kernel experiments)
 HEADER_PATH = os.path.join(_ROOT, "include", "ossg_b200.h")
 
 # error codes (include/ossg_b200.h)
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.ossg_fold_unpack.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow), C.c_void_p, C.c_void_p]
     L.ossg_synth_field.argtypes = [C.POINTER(FieldDesc), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
     L.ossg_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
+    L.ossg_selftest_sqrt_div.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
     _lib = L
     return L
 

@@ -304,44 +304,68 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     // patch index of this cell's own point per staggering (index = loc)
     const int own_cc = (ty + 1) * QX + tx + 1, own_fc = (ty + 1) * QX + tx, own_cf = ty * QX + tx + 1, own_ff = ty * QX + tx;
 
-#define HAV(L, px, py) haversine_hot(s_lam[(L) * QPTS + (px)], s_phr[(L) * QPTS + (px)], s_cos[(L) * QPTS + (px)], \
-                                     s_lam[(L) * QPTS + (py)], s_phr[(L) * QPTS + (py)], s_cos[(L) * QPTS + (py)], R)
-    // ---- 8 haversines as 4 rolled iterations of 2 (one copy of the code in the instruction cache)
-    //   it 0: dx_fc = hav(CC[i,j], CC[i-1,j])   dy_fc = hav(FF[i,j+1], FF[i,j])   az_fc = dy_fc * dx_fc   (:14,:19,:34)
-    //   it 1: dy_cf = hav(CC[i,j], CC[i,j-1])   dx_cf = hav(FF[i+1,j], FF[i,j])   az_cf = dy_cf * dx_cf   (:20,:15,:35)
-    //   it 2: dy_ff = hav(FC[i,j], FC[i,j-1])   dy_cc = hav(CF[i,j+1], CF[i,j])                           (:21,:18)
-    //   it 3: dx_ff = hav(CF[i,j], CF[i-1,j])   dx_cc = hav(FC[i+1,j], FC[i,j])                           (:16,:13)
+    // ---- cell stage, speculative straight-line form: the 8 haversines and 2 quadrilaterals are
+    // evaluated through their hot sequences in ONE basic block (branch-free sqrt / division, short
+    // atan), so ptxas interleaves the independent chains; `bad` collects every violated
+    // precondition (spacing above ~1.8 degrees, pole neighbourhoods, degenerate cells, NaN).  A bad
+    // cell is recomputed through the general functions below; its speculative stores are
+    // overwritten by the same thread.
+    const double R2 = 2 * R, RR = R * R;
+    bool bad = false;
+#define PT(L, p) s_lam[(L) * QPTS + (p)], s_phr[(L) * QPTS + (p)], s_cos[(L) * QPTS + (p)]
+    {
+        const double dx_fc = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - 1), R2, bad);        // utils.jl:14
+        const double dy_fc = haversine_spec(PT(FF, own_ff + QX), PT(FF, own_ff), R2, bad);       // :19
+        store_metric<FT>(a, DX_FC, o, dx_fc);
+        store_metric<FT>(a, DY_FC, o, dy_fc);
+        store_metric<FT>(a, AZ_FC, o, dy_fc * dx_fc);                                            // :34
+        const double dy_cf = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - QX), R2, bad);       // :20
+        const double dx_cf = haversine_spec(PT(FF, own_ff + 1), PT(FF, own_ff), R2, bad);        // :15
+        store_metric<FT>(a, DY_CF, o, dy_cf);
+        store_metric<FT>(a, DX_CF, o, dx_cf);
+        store_metric<FT>(a, AZ_CF, o, dy_cf * dx_cf);                                            // :35
+        store_metric<FT>(a, DY_FF, o, haversine_spec(PT(FC, own_fc), PT(FC, own_fc - QX), R2, bad));   // :21
+        store_metric<FT>(a, DY_CC, o, haversine_spec(PT(CF, own_cf + QX), PT(CF, own_cf), R2, bad));   // :18
+        store_metric<FT>(a, DX_FF, o, haversine_spec(PT(CF, own_cf), PT(CF, own_cf - 1), R2, bad));    // :16
+        store_metric<FT>(a, DX_CC, o, haversine_spec(PT(FC, own_fc + 1), PT(FC, own_fc), R2, bad));    // :13
+    }
+#define UV(q, p) Vec3{ s_ux[(q) * QPTS + (p)], s_uy[(q) * QPTS + (p)], s_uz[(q) * QPTS + (p)] }
+    {   // az_ff from CC[i-1,j-1], CC[i,j-1], CC[i,j], CC[i-1,j] (:38-43); az_cc from FF[i,j], FF[i+1,j], FF[i+1,j+1], FF[i,j+1] (:23-28)
+        const int b0 = own_cc - QX - 1, b1 = own_ff;
+        store_metric<FT>(a, AZ_FF, o, spherical_area_quadrilateral_spec(UV(0, b0), UV(0, b0 + 1), UV(0, b0 + QX + 1), UV(0, b0 + QX), bad) * RR);
+        store_metric<FT>(a, AZ_CC, o, spherical_area_quadrilateral_spec(UV(1, b1), UV(1, b1 + 1), UV(1, b1 + QX + 1), UV(1, b1 + QX), bad) * RR);
+    }
+    if (!bad) return;
+
+    // ---- general path (rare): rolled, out-of-line functions
+    //   it 0: dx_fc = hav(CC[i,j], CC[i-1,j])   dy_fc = hav(FF[i,j+1], FF[i,j])   az_fc = dy_fc * dx_fc
+    //   it 1: dy_cf = hav(CC[i,j], CC[i,j-1])   dx_cf = hav(FF[i+1,j], FF[i,j])   az_cf = dy_cf * dx_cf
+    //   it 2: dy_ff = hav(FC[i,j], FC[i,j-1])   dy_cc = hav(CF[i,j+1], CF[i,j])
+    //   it 3: dx_ff = hav(CF[i,j], CF[i-1,j])   dx_cc = hav(FC[i+1,j], FC[i,j])
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
-        // first haversine: x = own point, y = own - step        (CC, CC, FC, CF)
         const int locA = (it < 2) ? CC : (it == 2) ? FC : CF;
         const int ownA = (it < 2) ? own_cc : (it == 2) ? own_fc : own_cf;
         const int stepA = (it == 0 || it == 3) ? 1 : QX;
-        // second haversine: x = own + step, y = own point       (FF, FF, CF, FC)
         const int locB = (it < 2) ? FF : (it == 2) ? CF : FC;
         const int ownB = (it < 2) ? own_ff : (it == 2) ? own_cf : own_fc;
         const int stepB = (it == 0 || it == 2) ? QX : 1;
-        const double hA = HAV(locA, ownA, ownA - stepA);
-        const double hB = HAV(locB, ownB + stepB, ownB);
+        const double hA = haversine_pre_ool(PT(locA, ownA), PT(locA, ownA - stepA), R);
+        const double hB = haversine_pre_ool(PT(locB, ownB + stepB), PT(locB, ownB), R);
         const int idA = (it == 0) ? DX_FC : (it == 1) ? DY_CF : (it == 2) ? DY_FF : DX_FF;
         const int idB = (it == 0) ? DY_FC : (it == 1) ? DX_CF : (it == 2) ? DY_CC : DX_CC;
         store_metric<FT>(a, idA, o, hA);
         store_metric<FT>(a, idB, o, hB);
         if (it < 2) store_metric<FT>(a, it == 0 ? AZ_FC : AZ_CF, o, it == 0 ? hB * hA : hA * hB);
     }
-#undef HAV
-    // ---- 2 spherical quadrilaterals, rolled
-    //   q = 0: az_ff from CC[i-1,j-1], CC[i,j-1], CC[i,j], CC[i-1,j]      (:38-43)
-    //   q = 1: az_cc from FF[i,j], FF[i+1,j], FF[i+1,j+1], FF[i,j+1]      (:23-28)
 #pragma unroll 1
     for (int q = 0; q < 2; ++q) {
-        const int b = q * QPTS + (q ? own_ff : own_cc - QX - 1);      // lower-left corner of the quadrilateral
-        const Vec3 va{ s_ux[b], s_uy[b], s_uz[b] };
-        const Vec3 vb{ s_ux[b + 1], s_uy[b + 1], s_uz[b + 1] };
-        const Vec3 vc{ s_ux[b + QX + 1], s_uy[b + QX + 1], s_uz[b + QX + 1] };
-        const Vec3 vd{ s_ux[b + QX], s_uy[b + QX], s_uz[b + QX] };
-        store_metric<FT>(a, q ? AZ_CC : AZ_FF, o, spherical_area_quadrilateral_hot(va, vb, vc, vd) * (R * R));
+        const int b = q ? own_ff : own_cc - QX - 1;                   // lower-left corner of the quadrilateral
+        store_metric<FT>(a, q ? AZ_CC : AZ_FF, o,
+                         spherical_area_quadrilateral_ool(UV(q, b), UV(q, b + 1), UV(q, b + QX + 1), UV(q, b + QX)) * RR);
     }
+#undef PT
+#undef UV
 }
 
 // ------------------------------------------------------------------ K2f (frame)

@@ -245,9 +245,24 @@ OSSG_HD double haversine_hot(double lam_x, double hphi1, double c1, double lam_y
         const double s1 = m::sin_small(hdphi);
         const double s2 = m::sin_small(hdlam);
         const double a = s1 * s1 + c1 * c2 * (s2 * s2);
-        return 2 * (radius * m::asin_small(sqrt(a)));
+        return (2 * radius) * m::asin_small(sqrt(a));     // == 2 (R asin): doubling is exact
     }
     return haversine_tail_ool(hdphi, hdlam, c1, c2, radius);
+}
+
+// Speculative form for straight-line code: always evaluates the hot sequence (with the branch-free
+// sqrt) and ORs into `bad` whether its preconditions failed; the caller recomputes the cell through
+// the general functions when anything was bad.  Same bits as haversine_pre whenever !bad.
+OSSG_HD double haversine_spec(double lam_x, double hphi1, double c1, double lam_y, double hphi2, double c2,
+                              double radius2, bool& bad)
+{
+    const double hdphi = hphi2 - hphi1;
+    const double hdlam = (lam_y - lam_x) * HALF_D2R;
+    const double s1 = m::sin_small(hdphi);
+    const double s2 = m::sin_small(hdlam);
+    const double a = s1 * s1 + c1 * c2 * (s2 * s2);
+    bad |= !((fabs(hdphi) < HAV_HOT) & (fabs(hdlam) < HAV_HOT)) | (m::hi_abs(a) < m::SQRT_NB_MIN_HI);
+    return radius2 * m::asin_small(m::sqrt_nb(a));        // radius2 = 2 R: == 2 (R asin), doubling is exact
 }
 
 struct Vec3 { double x, y, z; };
@@ -305,8 +320,27 @@ OSSG_HD double spherical_area_quadrilateral_hot(const Vec3& a, const Vec3& b, co
 {
     const QuadTans t = quadrilateral_tangents(a, b, c, d);
     if ((fabs(t.abc) < m::ATAN_SHORT) & (fabs(t.abd) < m::ATAN_SHORT) & (fabs(t.acd) < m::ATAN_SHORT) & (fabs(t.bcd) < m::ATAN_SHORT))
-        return 0.5 * (2 * m::atan_short(t.abc) + 2 * m::atan_short(t.abd) + 2 * m::atan_short(t.acd) + 2 * m::atan_short(t.bcd));
+        // == 0.5 (2 atan + 2 atan + 2 atan + 2 atan): doubling and halving are exact
+        return m::atan_short(t.abc) + m::atan_short(t.abd) + m::atan_short(t.acd) + m::atan_short(t.bcd);
     return quadrilateral_from_tangents_ool(t.abc, t.abd, t.acd, t.bcd);
+}
+
+// Speculative form (see haversine_spec): branch-free divisions and short atans.
+OSSG_HD double spherical_area_quadrilateral_spec(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d, bool& bad)
+{
+    const double ab = dot3(a, b), ac = dot3(a, c), ad = dot3(a, d);
+    const double bc = dot3(b, c), bd = dot3(b, d), cd = dot3(c, d);
+    const Vec3 bxc = cross3(b, c), bxd = cross3(b, d), cxd = cross3(c, d);
+    const double n_abc = fabs(dot3(a, bxc)), n_abd = fabs(dot3(a, bxd)), n_acd = fabs(dot3(a, cxd)), n_bcd = fabs(dot3(b, cxd));
+    const double t_abc = m::div_nb(n_abc, 1 + ab + bc + ac);
+    const double t_abd = m::div_nb(n_abd, 1 + ab + bd + ad);
+    const double t_acd = m::div_nb(n_acd, 1 + ac + cd + ad);
+    const double t_bcd = m::div_nb(n_bcd, 1 + bc + cd + bd);
+    bad |= (m::hi_abs(n_abc) < m::DIV_NB_MIN_HI) | (m::hi_abs(n_abd) < m::DIV_NB_MIN_HI) |
+           (m::hi_abs(n_acd) < m::DIV_NB_MIN_HI) | (m::hi_abs(n_bcd) < m::DIV_NB_MIN_HI);
+    // (a tiny or non-finite denominator makes |t| huge or NaN and fails this test as well)
+    bad |= !((fabs(t_abc) < m::ATAN_SHORT) & (fabs(t_abd) < m::ATAN_SHORT) & (fabs(t_acd) < m::ATAN_SHORT) & (fabs(t_bcd) < m::ATAN_SHORT));
+    return m::atan_short(t_abc) + m::atan_short(t_abd) + m::atan_short(t_acd) + m::atan_short(t_bcd);
 }
 
 // Out-of-line copies for the generic (cold) per-element path: the halo-frame kernel evaluates

@@ -3,6 +3,7 @@
 // the roofline denominator for the coordinate/metric kernels (MEASURED_PEAKS.json has no FP64
 // figure).  Nothing here is on the reference's path.
 #include "ossg_common.cuh"
+#include "ossg_math.cuh"
 
 namespace ossg {
 
@@ -105,5 +106,58 @@ extern "C" int ossg_fp64_peak_probe(int iters, float* ms, double* flops, void* s
     *flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     OSSG_LAUNCH_CHECK("fp64_probe_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------ sqrt_nb / div_nb self-test
+namespace ossg {
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// double with a uniformly random mantissa and an exponent uniform in [elo, ehi]
+__device__ __forceinline__ double rand_double(uint64_t h, int elo, int ehi)
+{
+    const uint64_t mant = h & 0x000FFFFFFFFFFFFFull;
+    const uint64_t e = (uint64_t)(elo + (int)((h >> 52) % (uint64_t)(ehi - elo + 1)) + 1023);
+    return __longlong_as_double((long long)((e << 52) | mant));
+}
+__global__ void __launch_bounds__(256) selftest_sqrt_div_kernel(uint64_t n, uint64_t seed, unsigned long long* bad)
+{
+    unsigned long long bs = 0, bd = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h0 = mix64(seed + 3 * t), h1 = mix64(seed + 3 * t + 1), h2 = mix64(seed + 3 * t + 2);
+        // sqrt: alternate the whole admitted range [2^-970, 2^1000] and the kernel's own [2^-60, 2^-11]
+        const double a = (t & 1) ? rand_double(h0, -970, 1000) : rand_double(h0, -60, -11);
+        if (__double_as_longlong(m::sqrt_nb(a)) != __double_as_longlong(sqrt(a))) ++bs;
+        // division: numerators [2^-969, 2^0] (kernel: triple products), denominators [2^-3, 2^2] or [2^-100, 2^100]
+        const double nu = (t & 2) ? rand_double(h1, -969, 0) : rand_double(h1, -40, 0);
+        double de = (t & 4) ? rand_double(h2, -100, 100) : rand_double(h2, -3, 2);
+        if (h2 >> 63) de = -de;
+        if (__double_as_longlong(m::div_nb(nu, de)) != __double_as_longlong(nu / de)) ++bd;
+    }
+    if (bs) atomicAdd(&bad[0], bs);
+    if (bd) atomicAdd(&bad[1], bd);
+}
+}  // namespace ossg
+
+extern "C" int ossg_selftest_sqrt_div(uint64_t n, uint64_t seed, uint64_t mismatches[2], void* stream)
+{
+    if (!mismatches || n == 0) return set_error(OSSG_EINVAL, "bad arguments");
+    unsigned long long* d = nullptr;
+    OSSG_CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    cudaStream_t s = as_stream(stream);
+    OSSG_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), s));
+    ossg::selftest_sqrt_div_kernel<<<148 * 8, 256, 0, s>>>(n, seed, d);
+    unsigned long long h[2] = { 0, 0 };
+    cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "ossg_selftest_sqrt_div");
+    mismatches[0] = h[0];
+    mismatches[1] = h[1];
     return 0;
 }

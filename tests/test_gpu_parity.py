@@ -30,6 +30,8 @@ CONFIGS = [
     ((40, 34, 1), (5, 31, 5), dict(north_poles_latitude=45, first_pole_longitude=35)),  # large Hy (with_halo, runtests.jl:71)
     ((12, 8, 1), (2, 7, 1), {}),                                          # Hy = Ny - 1 (degenerate fold sources)
     ((66, 37, 1), (3, 2, 1), dict(southernmost_latitude=-75.5)),          # ragged sizes, non-integer south
+    ((1440, 720, 1), (4, 4, 4), {}),                                      # BASELINE config C: the tile kernel's straight-line path
+    ((2880, 1440, 1), (4, 4, 4), dict(north_poles_latitude=60, first_pole_longitude=-110)),   # 1/8 degree, other poles
 ]
 
 
@@ -352,6 +354,15 @@ def test_abi_argument_errors(ossg):
     assert L.ossg_tripolar_build(C.byref(p), 0, out, 16, 1 << 20, None) == ossg._lib.OSSG_EHALO
     with pytest.raises(ValueError, match="should be even"):
         ossg.TripolarGrid(size=(61, 30, 1))
+
+
+def test_branch_free_sqrt_div_match_ieee(ossg):
+    """sqrt_nb / div_nb (the tile kernel's straight-line path) against the device's IEEE sqrt and
+    division on 2^28 pseudo-random operands from the ranges the kernel admits."""
+    from ossg_b200 import _lib
+    bad = (C.c_uint64 * 2)()
+    _lib.check(_lib.lib().ossg_selftest_sqrt_div(1 << 28, 0x5EED, bad, None))
+    assert (bad[0], bad[1]) == (0, 0)
 
 
 # ------------------------------------------------------------------ full-size properties (no oracle)
