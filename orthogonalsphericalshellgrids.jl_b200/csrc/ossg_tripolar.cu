@@ -276,23 +276,45 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- point stage: everything that depends on one point only, once per patch point.
-    // Unit vectors (CC, FF) first so that whole warps take the same branch.
+    // ---- point stage: everything that depends on one point only, once per patch point, in ONE
+    // pass (every task reads and writes its own point only):
+    //   heavy task (CC and FF points, 2 QPTS of them): unit vector + deg2rad(phi)/2 + cos(deg2rad(phi))
+    //   light task (FC and CF points, 2 QPTS of them): deg2rad(phi)/2 + cos(deg2rad(phi))
+    // 32-task chunks are dealt statically so that the warps finish together: heavy chunks round-robin;
+    // the warps that got one heavy chunk fewer share the light chunks (a heavy task costs ~4 light ones).
+    {
+        constexpr int NW = NT / 32, HC = (2 * QPTS + 31) / 32, LC = HC;
+        constexpr int W0 = HC % NW;                        // warps below W0 carry an extra heavy chunk
+        constexpr int NLW = (W0 == 0) ? NW : NW - W0;      // warps sharing the light chunks
+        const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
-    for (int t = tid; t < 2 * QPTS; t += NT) {
-        const int q = t / QPTS, p = t - q * QPTS;         // q = 0: CC, 1: FF
-        const int loc = q ? FF : CC;
-        const Vec3 u = lat_lon_to_cartesian(s_phr[loc * QPTS + p], s_lam[loc * QPTS + p]);
-        s_ux[t] = u.x;
-        s_uy[t] = u.y;
-        s_uz[t] = u.z;
-    }
-    __syncthreads();                                      // s_phr is rewritten below
+        for (int h = warp; h < HC; h += NW) {
+            const int u = h * 32 + lane;                  // index into the unit-vector arrays
+            if (u < 2 * QPTS) {
+                const int t = u < QPTS ? u : u + 2 * QPTS;    // CC patch, then FF patch
+                const double lat = s_phr[t], lon = s_lam[t];
+                bool bad = false;
+                Vec3 v = lat_lon_to_cartesian_spec(lat, lon, bad);
+                if (bad) v = lat_lon_to_cartesian_ool(lat, lon);
+                s_ux[u] = v.x;
+                s_uy[u] = v.y;
+                s_uz[u] = v.z;
+                const double phr = lat * D2R;
+                s_phr[t] = 0.5 * phr;                     // the haversines want deg2rad(phi)/2
+                s_cos[t] = m::cos_rad_inl(phr);
+            }
+        }
+        if (W0 == 0 || warp >= W0) {
 #pragma unroll 1
-    for (int t = tid; t < TASKS; t += NT) {
-        const double phr = s_phr[t] * D2R;
-        s_phr[t] = 0.5 * phr;                             // the haversines want deg2rad(phi)/2
-        s_cos[t] = m::cos_rad(phr);
+            for (int l = (W0 == 0 ? warp : warp - W0); l < LC; l += NLW) {
+                const int t = QPTS + l * 32 + lane;       // FC patch, then CF patch
+                if (t < 3 * QPTS) {
+                    const double phr = s_phr[t] * D2R;
+                    s_phr[t] = 0.5 * phr;
+                    s_cos[t] = m::cos_rad_inl(phr);
+                }
+            }
+        }
     }
     __syncthreads();
 

@@ -280,6 +280,18 @@ OSSG_HD Vec3 lat_lon_to_cartesian(double lat, double lon)
     v.z = sin_lat;
     return v;
 }
+// straight-line form for the tile kernel: valid when |lat|, |lon| < 360, otherwise sets `bad`
+OSSG_HD Vec3 lat_lon_to_cartesian_spec(double lat, double lon, bool& bad)
+{
+    double sin_lat, cos_lat, sin_lon, cos_lon;
+    m::sincosd_spec(lat, sin_lat, cos_lat, bad);
+    m::sincosd_spec(lon, sin_lon, cos_lon, bad);
+    Vec3 v;
+    v.x = cos_lon * cos_lat;
+    v.y = sin_lon * cos_lat;
+    v.z = sin_lat;
+    return v;
+}
 OSSG_HD double dot3(const Vec3& a, const Vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 OSSG_HD Vec3 cross3(const Vec3& a, const Vec3& b)
 {
