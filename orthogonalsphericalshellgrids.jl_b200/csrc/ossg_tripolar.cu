@@ -259,19 +259,31 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
     const Window w = a.w;
 
-    // ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers
-    for (int t = tid; t < TASKS; t += NT) {
-        const int loc = t / QPTS, p = t - loc * QPTS;
-        const int pj = p / QX, pi = p - pj * QX;
-        const int iw = It0 + patch_di(loc) + pi - w.I0, jw = Jt0 + patch_dj(loc) + pj - w.J0;
-        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
-            const size_t o = (size_t)jw * w.wnx + iw;
-            cp_async_8(&s_lam[t], a.coords64[loc] + o);
-            cp_async_8(&s_phr[t], a.coords64[4 + loc] + o);
-        } else {
-            s_lam[t] = 0.0;
-            s_phr[t] = 0.0;
-        }
+    // ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers.
+    // Thread (tx, ty) copies patch point (tx, ty) of all four patches (one offset computation, the
+    // staggering shifts are constants); the first QY + TX threads then copy column TX and row TY.
+    {
+        auto stage_point = [&](int pi, int pj) {
+            const int iw = It0 + pi - w.I0, jw = Jt0 + pj - w.J0;
+            const long long o = (long long)jw * w.wnx + iw;
+            const int p = pj * QX + pi;
+#pragma unroll
+            for (int loc = 0; loc < 4; ++loc) {
+                const int di = patch_di(loc), dj = patch_dj(loc);
+                const int i2 = iw + di, j2 = jw + dj;
+                if (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny) {
+                    const long long o2 = o + (long long)dj * w.wnx + di;
+                    cp_async_8(&s_lam[loc * QPTS + p], a.coords64[loc] + o2);
+                    cp_async_8(&s_phr[loc * QPTS + p], a.coords64[4 + loc] + o2);
+                } else {
+                    s_lam[loc * QPTS + p] = 0.0;
+                    s_phr[loc * QPTS + p] = 0.0;
+                }
+            }
+        };
+        stage_point(threadIdx.x, threadIdx.y);
+        if (tid < QY) stage_point(TX, tid);
+        else if (tid < QY + TX) stage_point(tid - QY, TY);
     }
     cp_async_wait_all();
     __syncthreads();
