@@ -10,6 +10,8 @@
 //   K2f metrics_frame_kernel  the halo frame (north fold image, x halos, fold row Ny, south
 //                           continuation rows): each element evaluated at its source
 // Compile with -fmad=false: see ossg_math.cuh for the determinism contract.
+#include <mutex>
+
 #include "ossg_common.cuh"
 #include "ossg_tripolar_core.cuh"
 
@@ -527,16 +529,52 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
     return 0;
 }
 
+// Side stream of the current device (created once, never destroyed): the halo-frame kernel depends
+// on the coordinates only, so it runs next to the tile kernel instead of after it.
+static int side_stream(cudaStream_t* out)
+{
+    static std::mutex mu;
+    static cudaStream_t side[64] = {};
+    int dev = 0;
+    OSSG_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(OSSG_EINVAL, "device ordinal %d not supported", dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!side[dev]) OSSG_CUDA_TRY(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+    *out = side[dev];
+    return 0;
+}
+
 template <typename FT>
 static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, cudaEvent_t between = nullptr)
 {
+    (void)whole_grid;
     const Window& w = a.w;
     // fast rectangle: global interior rows 2..Ny-1, columns 1..Nx, one cell inside the window ring
     FastRect fr;
     const int Ilo = max(1, w.I0 + 1), Ihi = min(a.g.Nx, w.I0 + w.wnx - 2);
     const int Jlo = max(2, w.J0 + 1), Jhi = min(a.g.Ny - 1, w.J0 + w.wny - 2);
     fr.I0 = Ilo; fr.J0 = Jlo; fr.nx = Ihi - Ilo + 1; fr.ny = Jhi - Jlo + 1;
-    if (fr.nx > 0 && fr.ny > 0) {
+    const bool have_tile = fr.nx > 0 && fr.ny > 0;
+    const Frame f = make_frame(w, fr);
+    const long long nframe = f.n_south + f.n_north + f.n_west + f.n_east;
+
+    // frame kernel: forked onto the side stream when there is a tile kernel to overlap with (the
+    // profiled build keeps the two in sequence so that their times can be told apart)
+    const bool fork = have_tile && nframe > 0 && !between;
+    cudaStream_t fs = s;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (fork) {
+        int rc = side_stream(&fs);
+        if (rc) return rc;
+        OSSG_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        OSSG_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        OSSG_CUDA_TRY(cudaEventRecord(ev_fork, s));
+        OSSG_CUDA_TRY(cudaStreamWaitEvent(fs, ev_fork, 0));
+        metrics_frame_kernel<FT><<<ceil_div(nframe, 128), 128, 0, fs>>>(a, f);
+        OSSG_LAUNCH_CHECK("metrics_frame_kernel");
+        OSSG_CUDA_TRY(cudaEventRecord(ev_join, fs));
+    }
+    if (have_tile) {
         static bool attr_set[2] = { false, false };
         const int which = sizeof(FT) == 4;
         if (!attr_set[which]) {
@@ -548,11 +586,12 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         OSSG_LAUNCH_CHECK("metrics_tile_kernel");
     }
     if (between) OSSG_CUDA_TRY(cudaEventRecord(between, s));
-    const Frame f = make_frame(w, fr);
-    const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
-    if (n > 0) {
-        (void)whole_grid;
-        metrics_frame_kernel<FT><<<ceil_div(n, 128), 128, 0, s>>>(a, f);
+    if (fork) {
+        OSSG_CUDA_TRY(cudaStreamWaitEvent(s, ev_join, 0));
+        cudaEventDestroy(ev_fork);          // (released when the recorded work completes)
+        cudaEventDestroy(ev_join);
+    } else if (nframe > 0) {
+        metrics_frame_kernel<FT><<<ceil_div(nframe, 128), 128, 0, s>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
     }
     return 0;
