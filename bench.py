@@ -31,13 +31,16 @@ METRIC = "grid cells/s for coords+metrics (FP64)"
 UNIT = "cells/s"
 
 # FP64 pipe work per launch, counted by ncu on the 1/12 degree workload (SASS opcode mix of the
-# committed capture profiles/r01c_*_opcodes.md: DFMA + DMUL + DADD + DSETP thread-instructions):
-#   metrics_tile_kernel : 1386.1 per tile cell (4320 x 2158 cells)
-#   coords_kernel       :  405.7 per padded element (4328 x 2168 elements)
+# committed capture profiles/r01g_*_opcodes.md: DFMA + DMUL + DADD + DSETP thread-instructions):
+#   metrics_tile_kernel : 961.2 per tile cell (4320 x 2158 cells)
+#   coords_pair_kernel  : 216.4 per padded element (4328 x 2168 elements)
+# and the DRAM traffic of one metrics_tile_kernel launch from the same capture
+# (dram__bytes_read.sum + dram__bytes_write.sum = 601.3 MB + 848.5 MB; algorithmic 1491.6 MB).
 # These are properties of the code, not of the timing; refresh them whenever the kernels change.
-FP64_INST_PER_CELL_TILE = 1386.1
-FP64_INST_PER_ELEM_COORDS = 405.7
-PROFILE_TAG = "r01c"
+FP64_INST_PER_CELL_TILE = 961.2
+FP64_INST_PER_ELEM_COORDS = 216.4
+NCU_TRAFFIC_TILE_BYTES = 601288192 + 848534784
+PROFILE_TAG = "r01g"
 
 
 def partition_for(n):
@@ -292,7 +295,8 @@ def run_own(args):
     tile_ms = kernel_ms["metrics_tile"]
     achieved = tile_bytes / (tile_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "metrics_tile_kernel<double>", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": NCU_TRAFFIC_TILE_BYTES if world == 1 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": tile_bytes,
                 "note": "this kernel is FP64-pipe bound, not HBM bound; see roofline_fp64"}
     roofline_fp64 = {"bound": "fp64_pipe", "peak": fp64_peak_tflops, "unit": "TFLOP/s (DFMA = 2 flop)",

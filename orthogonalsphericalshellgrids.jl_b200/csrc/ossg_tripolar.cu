@@ -222,7 +222,6 @@ constexpr int QX = TX + 1, QY = TY + 1, QPTS = QX * QY;
 // shared arrays: lam, phr, cosphi per staggering (12) + unit vectors of CC and FF (6)
 constexpr int N_SMEM_ARRAYS = 18;
 constexpr size_t TILE_SMEM_BYTES = (size_t)N_SMEM_ARRAYS * QPTS * sizeof(double);
-constexpr int TASKS = 4 * QPTS;
 
 struct FastRect { int I0, J0, nx, ny; };   // global indices of the first fast cell, extents
 
