@@ -44,7 +44,11 @@ PROFILE_TAG = "r01g"
 
 
 def partition_for(n):
-    return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(n, (n, 1))
+    """Construction partition at N GPUs: Y slabs, the reference's own (and only) distributed layout
+    (src/distributed_tripolar_grid.jl:28-31).  Every rank keeps the full x extent, so the
+    coordinate kernel's mirror-pair form applies.  (x, y) partitions are exercised by the parity
+    tests (every factorisation of N) and by the fold-exchange benchmark below, which uses (N, 1)."""
+    return (1, n)
 
 
 # ------------------------------------------------------------------ clocks
@@ -270,7 +274,12 @@ def run_own(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- zipper halo fill (second half of the metric): 4 fields c,u,v,zeta on the local tile
-    zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny) if world == 1 else None
+    del out, ws
+    torch.cuda.empty_cache()
+    if world == 1:
+        zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny)
+    else:
+        zipper = {"fold_exchange": bench_fold_exchange(world, rank, dev)}
 
     # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels)
     ms = C.c_float(); fl = C.c_double()
@@ -375,6 +384,88 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
     res["config"] = f"{nx}x{ny}x{Nz} FP64 fields c,u,v,zeta, Hy=4, L2 flushed (256 MB write) before each timed fill"
     del fields
     return res
+
+
+# ------------------------------------------------------------------ fold exchange (N > 1)
+def bench_fold_exchange(world, rank, dev):
+    """Fold exchange of c,u,v,zeta (FP64, Nz=100, Hy=4) on the 1/12 degree grid split (N,1)."""
+    import torch
+    import torch.distributed as dist
+    import ossg_b200 as ossg
+    from ossg_b200 import _lib
+    from ossg_b200.distributed import PeerFold, fold_exchange, tile_of
+    Nx, Ny, Nz, H = 4320, 2160, 100, 4
+    arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(world, 1))
+    i0, j0, nx, ny = tile_of(Nx, Ny, world, 1, arch.rx, arch.ry)
+
+    class G:        # grid stub: only sizes are needed by Field / fold_exchange
+        pass
+    g = G()
+    g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz = nx, ny, Nz, H, H, H
+    g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
+    g.size, g.halo = (nx, ny, Nz), (H, H, H)
+    C_, F_ = ossg.Center, ossg.Face
+    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)] * 2      # c, u, v, zeta twice: batches of up to 8
+    shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
+    all_fields = [ossg.Field(loc, g, data=torch.empty(shape, dtype=torch.float64, device=dev)) for loc in locs]
+    fields = all_fields[:4]
+    L = _lib.lib()
+    for k, f in enumerate(all_fields):
+        d = f.descriptor()
+        _lib.check(L.ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
+    for _ in range(3):
+        fold_exchange(fields)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fold_exchange(fields)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # bytes each rank receives per exchange: Hy rows (+1 for y-Center) x nx columns x Nz levels per field
+    # (the row-Ny overwrite only concerns the right half of the globe: half the ranks on average)
+    recv = sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fields)
+    out = {"partition": f"({world},1)", "fields": 4, "recv_bytes_per_rank": recv,
+           "nccl_pack_send_unpack": {"ms_per_exchange": float(ms.item()),
+                                     "gbs_per_direction_per_gpu": recv / (float(ms.item()) * 1e-3) / 1e9}}
+    # ---- the same exchange as ONE kernel per rank over NVLink peer memory; 1, 2 and 4 fields per
+    # launch separate the fixed cost (launch + two flag barriers) from the bandwidth
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for push in (False, True):
+        res = {}
+        for nf in (1, 2, 4, 8):
+            t = timed(PeerFold(all_fields[:nf], push=push))
+            rb = sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in all_fields[:nf])
+            res[f"fields{nf}"] = {"ms_per_exchange": t, "recv_bytes_per_rank": rb, "gbs_per_direction_per_gpu": rb / (t * 1e-3) / 1e9}
+        t1, t8 = res["fields1"], res["fields8"]
+        slope = (t8["ms_per_exchange"] - t1["ms_per_exchange"]) / (t8["recv_bytes_per_rank"] - t1["recv_bytes_per_rank"])
+        res["marginal_gbs"] = 1e-6 / slope
+        res["fixed_us"] = 1e3 * (t1["ms_per_exchange"] - slope * t1["recv_bytes_per_rank"])
+        # NVLink 5 nominal 900 GB/s per direction; 735 GB/s is what a bidirectional cudaMemcpyPeer
+        # reaches on this pool (tools/p2p_probe.py, profiles/r01_p2p_probe.txt)
+        for key in ("fields4", "fields8"):
+            res[key]["frac_of_nvlink_900"] = res[key]["gbs_per_direction_per_gpu"] / 900.0
+            res[key]["frac_of_measured_copy_735"] = res[key]["gbs_per_direction_per_gpu"] / 735.0
+        out["peer_kernel_push" if push else "peer_kernel_pull"] = res
+    return out
 
 
 def main():

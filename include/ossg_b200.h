@@ -161,6 +161,51 @@ size_t ossg_fold_buffer_elems(const ossg_field_desc* f, const ossg_fold_window* 
 int ossg_fold_pack(const ossg_field_desc* f, const ossg_fold_window* w, void* buffer, void* stream);
 int ossg_fold_unpack(const ossg_field_desc* f, const ossg_fold_window* w, const void* buffer, void* stream);
 
+/* ---- (x, y)-partitioned fold over NVLink peer memory: ONE kernel per rank, no staging ------- *
+ * B200-native form of the exchange above for ranks of one NVSwitch node.  Every top-row rank maps
+ * the field arrays of the other top-row ranks (CUDA IPC, ossg_ipc_export / ossg_ipc_open) and its
+ * zipper kernel loads the source rows straight from the owner (the mirror rank; for x-Face fields
+ * also one column of its neighbour) while writing its own north halo -- each element crosses
+ * NVLink once.  Ranks order themselves with release/acquire epoch flags in IPC-mapped device
+ * memory (data-ready barrier at kernel start, read-done barrier at kernel end); the host never
+ * synchronises and no NCCL call is on this path.  Same result as ossg_zipper_fill on the global
+ * field (src/zipper_boundary_condition.jl:70-155), bit for bit.                                 */
+#define OSSG_MAX_PEERS 8
+#define OSSG_MAX_PEER_BATCH 8
+#define OSSG_IPC_HANDLE_BYTES 64
+typedef struct ossg_ipc_handle { unsigned char bytes[OSSG_IPC_HANDLE_BYTES]; } ossg_ipc_handle;
+/* handle of the device allocation that contains device_ptr, and device_ptr's offset inside it   */
+int ossg_ipc_export(const void* device_ptr, ossg_ipc_handle* handle, uint64_t* offset);
+/* maps a peer's allocation into this process (once per handle; cached) and returns base+offset  */
+int ossg_ipc_open(const ossg_ipc_handle* handle, uint64_t offset, void** peer_ptr);
+
+typedef struct ossg_peer_fold {
+    int32_t gNx;                            /* global Nx                                         */
+    int32_t me, nranks;                     /* this rank's x-index in the top row, Rx (<= 8)     */
+    int32_t i0[OSSG_MAX_PEERS];             /* global first interior column of top-row rank r    */
+    int32_t nx[OSSG_MAX_PEERS];             /* its width                                         */
+    void*   flags_local;                    /* this rank's flag block: 2*OSSG_MAX_PEERS uint64 +
+                                               uint32 block counter + uint32 error word (set to 1
+                                               when a peer did not show up within ~2 s), i.e.
+                                               2*OSSG_MAX_PEERS+1 uint64, zero-initialised once   */
+    void*   flags_peer[OSSG_MAX_PEERS];     /* the peers' flag blocks, peer-mapped ([me] unused)  */
+    uint64_t epoch;                         /* 1, 2, 3, ... one per call, the same on all ranks  */
+    int32_t push;                           /* 0: each rank loads its sources from the owners;
+                                               1: each rank stores its rows into the destinations'
+                                               halos (posted NVLink writes); same on all ranks    */
+    int32_t reserved;
+} ossg_peer_fold;
+
+typedef struct ossg_peer_field {
+    ossg_field_desc f;                      /* the LOCAL field (Nx = this rank's width)          */
+    const void* peer[OSSG_MAX_PEERS];       /* data pointer of the same field on top-row rank r
+                                               (peer-mapped; the local pointer for r == me)      */
+} ossg_peer_field;
+
+/* north-fold fill of up to OSSG_MAX_PEER_BATCH fields of a top-row rank; every top-row rank must
+ * make the matching call (same fields, same epoch) or the kernels wait for each other forever   */
+int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields, const ossg_peer_fold* fold, void* stream);
+
 /* ---- measurement / test utilities (not part of the reference surface) ---------------------- */
 /* interior(c)[i,j,k] = hash(seed, global i, j, k) in [-1, 1); halos are filled with a NaN payload */
 int ossg_synth_field(const ossg_field_desc* f, uint64_t seed, int32_t gi0, int32_t gj0, void* stream);

@@ -42,6 +42,24 @@ class FoldWindow(C.Structure):
                 ("src_i0", C.c_int32), ("src_n", C.c_int32)]
 
 
+OSSG_MAX_PEERS, OSSG_MAX_PEER_BATCH = 8, 8
+
+
+class IpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
+class PeerFoldDesc(C.Structure):
+    _fields_ = [("gNx", C.c_int32), ("me", C.c_int32), ("nranks", C.c_int32),
+                ("i0", C.c_int32 * OSSG_MAX_PEERS), ("nx", C.c_int32 * OSSG_MAX_PEERS),
+                ("flags_local", C.c_void_p), ("flags_peer", C.c_void_p * OSSG_MAX_PEERS),
+                ("epoch", C.c_uint64), ("push", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PeerField(C.Structure):
+    _fields_ = [("f", FieldDesc), ("peer", C.c_void_p * OSSG_MAX_PEERS)]
+
+
 class OSSGError(RuntimeError):
     """Non-argument failure reported by libossg_b200.so (a CUDA error)."""
 
@@ -87,6 +105,9 @@ def lib() -> C.CDLL:
     L.ossg_fold_unpack.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow), C.c_void_p, C.c_void_p]
     L.ossg_synth_field.argtypes = [C.POINTER(FieldDesc), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
     L.ossg_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
+    L.ossg_ipc_export.argtypes = [C.c_void_p, C.POINTER(IpcHandle), C.POINTER(C.c_uint64)]
+    L.ossg_ipc_open.argtypes = [C.POINTER(IpcHandle), C.c_uint64, C.POINTER(C.c_void_p)]
+    L.ossg_zipper_fill_peer.argtypes = [C.POINTER(PeerField), C.c_int, C.POINTER(PeerFoldDesc), C.c_void_p]
     L.ossg_selftest_sqrt_div.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
     _lib = L
     return L

@@ -1,0 +1,333 @@
+// csrc/ossg_peer.cu -- the fold across an x-partitioned top row as ONE kernel over NVLink peer memory.
+//
+// Reference: src/zipper_boundary_condition.jl:70-155 is the operation; the reference never splits x
+// (src/distributed_tripolar_grid.jl:28-31), so the fold never leaves a rank there.  With an (x, y)
+// partition the fold source of global column i is column Nx-i+1 (x-Center) or Nx-i+2 (x-Face), which
+// lives on the mirror rank of the top row (and, for x-Face, one column of its neighbour).  The
+// pack -> ncclSend/ncclRecv -> unpack exchange (ossg_fold_pack/unpack) moves every element three
+// times and pays two kernel launches plus the NCCL p2p latency.  On an NVSwitch node every GPU can
+// load from every peer at NVLink speed, so here each rank's zipper kernel simply READS its source
+// rows from the owner's field through a peer-mapped pointer (CUDA IPC) and writes its own halo: one
+// launch, every element crosses NVLink once and is written once, no staging buffer.
+//
+// Ordering between ranks (no host synchronisation, no NCCL call on this path):
+//   start: block 0 publishes epoch -> ready[me] on every peer (st.release.sys); every block waits
+//          until ready[r] >= epoch for all r (ld.acquire.sys).  A rank's kernel is stream-ordered
+//          after the kernels that produced its interior, so "kernel started" == "interior ready".
+//   end:   the last block to finish publishes epoch -> done[me] on every peer and waits for
+//          done[r] >= epoch from all r before it exits, so work queued behind this kernel cannot
+//          overwrite rows a peer is still reading.
+// Flags live in a small per-rank device array that is itself IPC-mapped by the peers; epochs only
+// grow, nothing is ever reset.
+#include <mutex>
+#include <vector>
+#include <cstring>
+
+#include "ossg_common.cuh"
+
+namespace ossg {
+
+constexpr int PB = 256;
+#ifndef PEER_BLOCKS_PER_SM
+#define PEER_BLOCKS_PER_SM 4
+#endif
+
+template <typename T>
+__device__ __forceinline__ T peer_sign(T v, double s)
+{
+    if (s == 1.0) return v;
+    if (s == -1.0) return -v;
+    return (T)(s * (double)v);
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Bounded wait for a peer's epoch: a missing partner (a rank that never made the matching call)
+// must not hang the GPU.  After ~2 s (4e9 cycles) the wait gives up and raises the error word in
+// this rank's flag block (uint32 right after the block counter); the fill is then incomplete.
+__device__ __forceinline__ void wait_epoch(const unsigned long long* flag, unsigned long long epoch, unsigned int* error_word)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (clock64() - t0 > 4000000000ll) { atomicExch(error_word, 1u); break; }
+    }
+}
+
+// loads of peer memory: system-scope relaxed, so that no non-coherent cache serves an older epoch
+__device__ __forceinline__ double peer_load(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float peer_load(const float* p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct PeerBatch {
+    ossg_peer_field pf[OSSG_MAX_PEER_BATCH];
+    ossg_peer_fold fold;
+    int n;
+    int chunks, levels;          // work items: n fields x levels x chunks of PB columns
+    long long nitems;
+};
+
+// one thread per (local column i, level): all Hy source rows are loaded (over NVLink) before any
+// store, as in the single-GPU zipper_column.
+template <typename T>
+__device__ __forceinline__ void peer_column(const ossg_peer_field& p, const ossg_peer_fold& fd, int i /*1..nx local*/, int kk)
+{
+    const ossg_field_desc& f = p.f;
+    const int gNx = fd.gNx, Ny = f.Ny, Hy = f.Hy, Hx = f.Hx;
+    const int ig = fd.i0[fd.me] + i - 1;                              // global destination column
+    double s = f.sign;
+    int ipg = f.locx ? gNx - ig + 2 : gNx - ig + 1;                   // zipper_boundary_condition.jl:73,90,110,125
+    if (ipg > gNx) { s = fabs(s); ipg -= gNx; }                       // :74-75, :91-92
+    int r = 0;
+#pragma unroll 1
+    for (; r < fd.nranks - 1; ++r)
+        if (ipg < fd.i0[r] + fd.nx[r]) break;                         // owner of the source column
+    const int li = ipg - fd.i0[r] + 1;                                // its local column there
+    const size_t sxr = (size_t)(fd.nx[r] + 2 * Hx), sxyr = sxr * (size_t)(Ny + 2 * Hy);
+    const T* srcb = static_cast<const T*>(p.peer[r]) + (size_t)(f.k0 + kk) * sxyr + (li + Hx - 1);
+    const size_t sx = (size_t)(f.Nx + 2 * Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
+    T* c = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
+    // halo row j = q + 1: dst row Ny + j, src row Ny - j (y-Center) or Ny - j + 1 (y-Face)
+    const T* src = srcb + (size_t)((f.locy ? Ny : Ny - 1) + Hy - 1) * sxr;
+    T* dst = c + (size_t)(Ny + Hy) * sx + (i + Hx - 1);
+    const bool fix_row = (f.locy == OSSG_CENTER) && (ig > gNx / 2);   // :102, :135 (global test)
+    T vrow = T(0);
+    if (fix_row) vrow = peer_load(srcb + (size_t)(Ny + Hy - 1) * sxr);
+    int q = 0;
+    for (; q + 4 <= Hy; q += 4) {
+        const T v0 = peer_load(src - (ptrdiff_t)((q + 0) * sxr)), v1 = peer_load(src - (ptrdiff_t)((q + 1) * sxr));
+        const T v2 = peer_load(src - (ptrdiff_t)((q + 2) * sxr)), v3 = peer_load(src - (ptrdiff_t)((q + 3) * sxr));
+        dst[(size_t)(q + 0) * sx] = peer_sign(v0, s);
+        dst[(size_t)(q + 1) * sx] = peer_sign(v1, s);
+        dst[(size_t)(q + 2) * sx] = peer_sign(v2, s);
+        dst[(size_t)(q + 3) * sx] = peer_sign(v3, s);
+    }
+    for (; q < Hy; ++q) dst[(size_t)q * sx] = peer_sign(peer_load(src - (ptrdiff_t)(q * sxr)), s);
+    if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + Hx - 1)] = peer_sign(vrow, s);
+}
+
+// push form: the thread owns SOURCE column i of this rank and stores the folded values into the
+// halo of the rank that owns the destination column (posted NVLink writes instead of round-trip
+// reads).  The fold map is an involution on 1..Nx (i <-> Nx-i+1, resp. Nx-i+2 with column 1 fixed),
+// so every destination receives exactly one value.
+template <typename T>
+__device__ __forceinline__ void peer_column_push(const ossg_peer_field& p, const ossg_peer_fold& fd, int i /*1..nx local*/, int kk)
+{
+    const ossg_field_desc& f = p.f;
+    const int gNx = fd.gNx, Ny = f.Ny, Hy = f.Hy, Hx = f.Hx;
+    const int isg = fd.i0[fd.me] + i - 1;                             // global source column
+    double s = f.sign;
+    int idg = f.locx ? gNx - isg + 2 : gNx - isg + 1;                 // destination column
+    if (idg > gNx) { s = fabs(s); idg -= gNx; }                       // x-Face column 1 folds onto itself with |s|
+    int r = 0;
+#pragma unroll 1
+    for (; r < fd.nranks - 1; ++r)
+        if (idg < fd.i0[r] + fd.nx[r]) break;                         // owner of the destination column
+    const int li = idg - fd.i0[r] + 1;
+    const size_t sxr = (size_t)(fd.nx[r] + 2 * Hx), sxyr = sxr * (size_t)(Ny + 2 * Hy);
+    T* dstb = static_cast<T*>(const_cast<void*>(p.peer[r])) + (size_t)(f.k0 + kk) * sxyr + (li + Hx - 1);
+    const size_t sx = (size_t)(f.Nx + 2 * Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
+    const T* c = static_cast<const T*>(f.data) + (size_t)(f.k0 + kk) * sxy + (i + Hx - 1);
+    const T* src = c + (size_t)((f.locy ? Ny : Ny - 1) + Hy - 1) * sx;    // q = 0, then -sx per row
+    T* dst = dstb + (size_t)(Ny + Hy) * sxr;                                // q = 0, then +sxr per row
+    const bool fix_row = (f.locy == OSSG_CENTER) && (idg > gNx / 2);
+    T vrow = T(0);
+    if (fix_row) vrow = c[(size_t)(Ny + Hy - 1) * sx];
+    int q = 0;
+    for (; q + 4 <= Hy; q += 4) {
+        const T v0 = src[-(ptrdiff_t)((q + 0) * sx)], v1 = src[-(ptrdiff_t)((q + 1) * sx)];
+        const T v2 = src[-(ptrdiff_t)((q + 2) * sx)], v3 = src[-(ptrdiff_t)((q + 3) * sx)];
+        dst[(size_t)(q + 0) * sxr] = peer_sign(v0, s);
+        dst[(size_t)(q + 1) * sxr] = peer_sign(v1, s);
+        dst[(size_t)(q + 2) * sxr] = peer_sign(v2, s);
+        dst[(size_t)(q + 3) * sxr] = peer_sign(v3, s);
+    }
+    for (; q < Hy; ++q) dst[(size_t)q * sxr] = peer_sign(src[-(ptrdiff_t)(q * sx)], s);
+    if (fix_row) dstb[(size_t)(Ny + Hy - 1) * sxr] = peer_sign(vrow, s);
+}
+
+__global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(const __grid_constant__ PeerBatch b)
+{
+    const ossg_peer_fold& fd = b.fold;
+    unsigned long long* mine = static_cast<unsigned long long*>(fd.flags_local);
+    // ---- start barrier
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < fd.nranks; ++r)
+                if (r != fd.me) st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[r]) + fd.me, fd.epoch);
+        }
+        for (int r = 0; r < fd.nranks; ++r)
+            if (r != fd.me) wait_epoch(mine + r, fd.epoch, reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1);
+    }
+    __syncthreads();
+
+    // persistent blocks: one flag wait per block, then a block-stride loop over the work items
+    // (field, level, chunk of PB columns) -- few waves, many NVLink loads in flight per SM
+    for (long long item = blockIdx.x; item < b.nitems; item += gridDim.x) {
+        const int chunk = (int)(item % b.chunks);
+        const long long rest = item / b.chunks;
+        const int kk = (int)(rest % b.levels), fi = (int)(rest / b.levels);
+        const ossg_peer_field& p = b.pf[fi];
+        const int i = chunk * PB + threadIdx.x + 1;
+        if (i <= p.f.Nx && kk < p.f.nk) {
+            if (fd.push) {
+                if (p.f.elem_type == OSSG_F64) peer_column_push<double>(p, fd, i, kk);
+                else peer_column_push<float>(p, fd, i, kk);
+            } else {
+                if (p.f.elem_type == OSSG_F64) peer_column<double>(p, fd, i, kk);
+                else peer_column<float>(p, fd, i, kk);
+            }
+        }
+    }
+
+    // ---- end barrier (last block only)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);
+        const unsigned int total = gridDim.x;
+        __threadfence();                                              // release this block's stores ...
+        if (atomicAdd(counter, 1u) == total - 1) {
+            __threadfence();                                          // ... and acquire everybody else's
+            atomicExch(counter, 0u);                                  // ready for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int r = 0; r < fd.nranks; ++r)
+                if (r != fd.me) st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[r]) + OSSG_MAX_PEERS + fd.me, fd.epoch);
+            for (int r = 0; r < fd.nranks; ++r)
+                if (r != fd.me) wait_epoch(mine + OSSG_MAX_PEERS + r, fd.epoch, counter + 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ CUDA IPC plumbing
+struct OpenedHandle { unsigned char h[64]; void* base; };
+static std::mutex g_ipc_mu;
+static std::vector<OpenedHandle> g_opened;
+
+typedef int (*PFN_cuMemGetAddressRange)(unsigned long long*, size_t*, unsigned long long);
+
+static int address_range(const void* ptr, void** base, size_t* size)
+{
+    static PFN_cuMemGetAddressRange fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        OSSG_CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q));
+        if (!sym || q != cudaDriverEntryPointSuccess) return set_error(OSSG_EINVAL, "cuMemGetAddressRange is not available from the driver");
+        fn = reinterpret_cast<PFN_cuMemGetAddressRange>(sym);
+    }
+    unsigned long long b = 0;
+    size_t n = 0;
+    const int rc = fn(&b, &n, (unsigned long long)reinterpret_cast<uintptr_t>(ptr));
+    if (rc != 0) return set_error(OSSG_EINVAL, "cuMemGetAddressRange failed with CUresult %d (not a device allocation?)", rc);
+    *base = reinterpret_cast<void*>(static_cast<uintptr_t>(b));
+    *size = n;
+    return 0;
+}
+
+}  // namespace ossg
+
+using namespace ossg;
+
+static_assert(sizeof(cudaIpcMemHandle_t) == OSSG_IPC_HANDLE_BYTES, "ossg_ipc_handle must hold a cudaIpcMemHandle_t");
+
+extern "C" int ossg_ipc_export(const void* device_ptr, ossg_ipc_handle* handle, uint64_t* offset)
+{
+    if (!device_ptr || !handle || !offset) return set_error(OSSG_EINVAL, "NULL argument");
+    void* base = nullptr;
+    size_t size = 0;
+    int rc = address_range(device_ptr, &base, &size);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    OSSG_CUDA_TRY(cudaIpcGetMemHandle(&h, base));
+    std::memcpy(handle->bytes, &h, sizeof(h));
+    *offset = (uint64_t)(static_cast<const char*>(device_ptr) - static_cast<const char*>(base));
+    return 0;
+}
+
+extern "C" int ossg_ipc_open(const ossg_ipc_handle* handle, uint64_t offset, void** peer_ptr)
+{
+    if (!handle || !peer_ptr) return set_error(OSSG_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(g_ipc_mu);
+    for (const OpenedHandle& o : g_opened)
+        if (std::memcmp(o.h, handle->bytes, 64) == 0) {
+            *peer_ptr = static_cast<char*>(o.base) + offset;
+            return 0;
+        }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle->bytes, sizeof(h));
+    void* base = nullptr;
+    OSSG_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    OpenedHandle o;
+    std::memcpy(o.h, handle->bytes, 64);
+    o.base = base;
+    g_opened.push_back(o);
+    *peer_ptr = static_cast<char*>(base) + offset;
+    return 0;
+}
+
+extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields, const ossg_peer_fold* fold, void* stream)
+{
+    if (!fields || !fold || nfields < 1) return set_error(OSSG_EINVAL, "fields/fold is NULL or nfields < 1");
+    if (nfields > OSSG_MAX_PEER_BATCH) return set_error(OSSG_EINVAL, "at most %d fields per peer launch, got %d", OSSG_MAX_PEER_BATCH, nfields);
+    const ossg_peer_fold& fd = *fold;
+    if (fd.nranks < 1 || fd.nranks > OSSG_MAX_PEERS || fd.me < 0 || fd.me >= fd.nranks)
+        return set_error(OSSG_EINVAL, "bad rank layout: me = %d of %d (max %d)", fd.me, fd.nranks, OSSG_MAX_PEERS);
+    if (fd.gNx < 2 || fd.gNx % 2) return set_error(OSSG_EODD_NX, "global Nx must be even, got %d", fd.gNx);
+    int next = 1;
+    for (int r = 0; r < fd.nranks; ++r) {
+        if (fd.i0[r] != next || fd.nx[r] < 1) return set_error(OSSG_EWINDOW, "top-row tiles must cover 1..Nx in rank order (rank %d: i0 = %d, nx = %d)", r, fd.i0[r], fd.nx[r]);
+        next += fd.nx[r];
+        if (r != fd.me && !fd.flags_peer[r]) return set_error(OSSG_EINVAL, "flags_peer[%d] is NULL", r);
+    }
+    if (next != fd.gNx + 1) return set_error(OSSG_EWINDOW, "top-row tiles cover %d columns, global Nx = %d", next - 1, fd.gNx);
+    if (!fd.flags_local || reinterpret_cast<uintptr_t>(fd.flags_local) % 8) return set_error(OSSG_EALIGN, "flags_local must be an 8-byte aligned device pointer");
+    if (fd.epoch == 0) return set_error(OSSG_EINVAL, "epoch must start at 1 and grow by one per call");
+    PeerBatch b;
+    b.fold = fd;
+    b.n = nfields;
+    int gx = 0, gy = 0;
+    for (int k = 0; k < nfields; ++k) {
+        b.pf[k] = fields[k];
+        ossg_field_desc& f = b.pf[k].f;
+        if (!f.data) return set_error(OSSG_EINVAL, "field %d: data is NULL", k);
+        if (f.elem_type != OSSG_F64 && f.elem_type != OSSG_F32) return set_error(OSSG_EINVAL, "field %d: bad elem_type", k);
+        if (f.Nx != fd.nx[fd.me]) return set_error(OSSG_EWINDOW, "field %d: local Nx (%d) differs from this rank's tile width (%d)", k, f.Nx, fd.nx[fd.me]);
+        if (f.Hy < 1 || f.Hy > f.Ny - 1 || f.Hx < 0) return set_error(OSSG_EHALO, "field %d: bad halo (%d, %d)", k, f.Hx, f.Hy);
+        if ((f.locx != OSSG_CENTER && f.locx != OSSG_FACE) || (f.locy != OSSG_CENTER && f.locy != OSSG_FACE))
+            return set_error(OSSG_ELOCATION, "field %d: location codes must be OSSG_CENTER or OSSG_FACE", k);
+        if (f.nk == 0) { f.k0 = f.Hz; f.nk = f.Nz; }
+        if (f.k0 < 0 || f.nk < 1 || f.k0 + f.nk > f.Nz + 2 * f.Hz) return set_error(OSSG_EINVAL, "field %d: bad k-range", k);
+        for (int r = 0; r < fd.nranks; ++r)
+            if (!b.pf[k].peer[r]) return set_error(OSSG_EINVAL, "field %d: peer[%d] is NULL", k, r);
+        gx = max(gx, ceil_div(f.Nx, PB));
+        gy = max(gy, f.nk);
+    }
+    b.chunks = gx;
+    b.levels = gy;
+    b.nitems = (long long)gx * gy * nfields;
+    int dev = 0, sms = 0;
+    OSSG_CUDA_TRY(cudaGetDevice(&dev));
+    OSSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long resident = (long long)sms * PEER_BLOCKS_PER_SM;
+    const int grid = (int)(b.nitems < resident ? b.nitems : resident);
+    zipper_peer_kernel<<<grid, PB, 0, as_stream(stream)>>>(b);
+    OSSG_LAUNCH_CHECK("zipper_peer_kernel");
+    return 0;
+}

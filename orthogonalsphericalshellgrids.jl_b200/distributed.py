@@ -252,6 +252,104 @@ def fold_exchange(fields: Sequence, packer=None, group=None) -> None:
             off += ne
 
 
+class PeerFold:
+    """The fold of an x-partitioned top row as ONE kernel per rank over NVLink peer memory
+    (ossg_zipper_fill_peer): every top-row rank maps the other ranks' field arrays through CUDA IPC
+    once, then each call launches a zipper kernel that loads its source rows from the owning rank
+    and orders itself with the peers through epoch flags in device memory -- no pack/unpack, no
+    staging buffer, no NCCL call and no host synchronisation per exchange.
+
+    Collective constructor: every rank of `group` must build it for the same list of fields (ranks
+    below the top row take part in the handle exchange only)."""
+
+    def __init__(self, fields: Sequence, group=None, push: bool = True):
+        import ctypes as C
+        import torch.distributed as dist
+        from .fields import is_zipper
+        self.push = bool(push)
+        self.fields = [f for f in fields if f.boundary_conditions is not None and is_zipper(f.boundary_conditions.north)]
+        arch = fields[0].grid.architecture
+        if arch.Rx > _lib.OSSG_MAX_PEERS:
+            raise ValueError(f"PeerFold supports at most {_lib.OSSG_MAX_PEERS} ranks in x, got {arch.Rx}")
+        self.arch, self.group, self.epoch = arch, group, 0
+        self._launches = None
+        self.active = arch.is_top_row() and bool(self.fields)
+        L = _lib.lib()
+        dev = fields[0].data.device
+        # flag block: ready[8], done[8] (uint64) + block counter; zero once, epochs only grow
+        self.flags = torch.zeros(2 * _lib.OSSG_MAX_PEERS + 1, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+
+        def export(ptr):
+            h, off = _lib.IpcHandle(), C.c_uint64()
+            _lib.check(L.ossg_ipc_export(ptr, C.byref(h), C.byref(off)))
+            return bytes(h.bytes), int(off.value)
+
+        mine = None
+        if self.active:
+            mine = {"rx": arch.rx, "flags": export(self.flags.data_ptr()),
+                    "fields": [export(f.data.data_ptr()) for f in self.fields]}
+        world = dist.get_world_size(group)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        if not self.active:
+            return
+        top = {g["rx"]: g for g in gathered if g is not None}
+        assert sorted(top) == list(range(arch.Rx)), "every top-row rank must construct the same PeerFold"
+
+        def open_(hb, off):
+            h, out = _lib.IpcHandle(), C.c_void_p()
+            C.memmove(h.bytes, hb, 64)
+            _lib.check(L.ossg_ipc_open(C.byref(h), off, C.byref(out)))
+            return out.value
+
+        gNx = self.fields[0].grid.global_size[0]
+        sx = local_sizes(gNx, arch.Rx)
+        fd = _lib.PeerFoldDesc()
+        fd.gNx, fd.me, fd.nranks, fd.push = gNx, arch.rx, arch.Rx, int(self.push)
+        for r in range(arch.Rx):
+            fd.i0[r], fd.nx[r] = 1 + sum(sx[:r]), sx[r]
+            fd.flags_peer[r] = None if r == arch.rx else open_(*top[r]["flags"])
+        fd.flags_local = self.flags.data_ptr()
+        self.fold = fd
+        self.peer_ptrs = []
+        for k, f in enumerate(self.fields):
+            self.peer_ptrs.append([f.data.data_ptr() if r == arch.rx else open_(*top[r]["fields"][k])
+                                   for r in range(arch.Rx)])
+
+    def __call__(self, stream=None) -> None:
+        """One fold exchange of all fields (collective over the top row; asynchronous)."""
+        import ctypes as C
+        if not self.active:
+            return
+        L = _lib.lib()
+        dev = self.fields[0].data.device
+        stream = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        if self._launches is None:          # descriptors are built once: a call is one ctypes call per batch
+            B = _lib.OSSG_MAX_PEER_BATCH
+            self._launches = []
+            for b0 in range(0, len(self.fields), B):
+                chunk = list(range(b0, min(b0 + B, len(self.fields))))
+                arr = (_lib.PeerField * len(chunk))()
+                for n, k in enumerate(chunk):
+                    arr[n].f = self.fields[k].descriptor()
+                    for r in range(self.arch.Rx):
+                        arr[n].peer[r] = self.peer_ptrs[k][r]
+                self._launches.append((arr, len(chunk)))
+        fold_ref = C.byref(self.fold)
+        for (arr, n) in self._launches:
+            self.epoch += 1
+            self.fold.epoch = self.epoch
+            rc = L.ossg_zipper_fill_peer(arr, n, fold_ref, stream)
+            if rc:
+                _lib.check(rc)
+
+    def timed_out(self) -> bool:
+        """True when a kernel of this rank gave up waiting for a peer (synchronises the device)."""
+        word = int(self.flags[2 * _lib.OSSG_MAX_PEERS].item())
+        return (word >> 32) != 0
+
+
 def distributed_fill_halo_regions(fields: Sequence, stream=None, packer=None, group=None) -> None:
     """fill_halo_regions! for fields on a distributed tripolar grid: fold exchange on the top row
     (interior columns), then -- when x is not partitioned -- the local periodic west/east fill.

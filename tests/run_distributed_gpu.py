@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import ossg_b200 as ossg                                    # noqa: E402
-from ossg_b200.distributed import distributed_fill_halo_regions, fold_exchange, tile_of   # noqa: E402
+from ossg_b200.distributed import (PeerFold, distributed_fill_halo_regions, fold_exchange,   # noqa: E402
+                                   ordinary_halo_exchange, tile_of)
 from oracle import oracle as orc                            # noqa: E402
 
 
@@ -58,6 +59,7 @@ def check(world, rank, dev):
             want = o.fill_halo_regions(G.copy(), Nx, Ny, Nz, Hx, Hy, Hz, code[0], code[1], ossg.sign(loc[0], loc[1]))
             fields.append(f)
             wants.append(want[:, j0 - 1:j0 - 1 + ny + 2 * Hy, i0 - 1:i0 - 1 + nx + 2 * Hx])
+        pristine = [f.data.clone() for f in fields]
         distributed_fill_halo_regions(fields)
         torch.cuda.synchronize(dev)
         for f, want, (loc, code) in zip(fields, wants, specs):
@@ -67,48 +69,37 @@ def check(world, rank, dev):
                 bad = np.argwhere(~same)[0]
                 failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: fill differs at {bad.tolist()}")
         dist.barrier()
+        # the same fill with the fold served by the one-kernel NVLink peer path (pull and push
+        # forms), three epochs each
+        for push in (False, True):
+            for f, p0 in zip(fields, pristine):
+                f.data.copy_(p0)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            peer = PeerFold(fields, push=push)
+            for rep in range(3):
+                if rep:
+                    for f, p0 in zip(fields, pristine):
+                        f.data.copy_(p0)
+                peer()
+                ordinary_halo_exchange(fields)
+                torch.cuda.synchronize(dev)
+                for f, want, (loc, code) in zip(fields, wants, specs):
+                    a, b = f.data.cpu().numpy()[Hz:Hz + Nz], want[Hz:Hz + Nz]
+                    same = (a == b) | (np.isnan(a) & np.isnan(b))
+                    if not same.all():
+                        bad = np.argwhere(~same)[0]
+                        failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: PEER fill push={push} (epoch {rep + 1}) "
+                                        f"differs at {bad.tolist()}")
+                if peer.active and peer.timed_out():
+                    failures.append(f"({Rx},{Ry}) rank {rank}: peer kernel timed out waiting for a partner")
+                dist.barrier()
     return failures
 
 
 def bench_fold(world, rank, dev):
-    """Fold exchange of c,u,v,zeta (FP64, Nz=100, Hy=4) on the 1/12 degree grid split (N,1)."""
-    from ossg_b200 import _lib
-    import ctypes as C
-    Nx, Ny, Nz, H = 4320, 2160, 100, 4
-    arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(world, 1))
-    i0, j0, nx, ny = tile_of(Nx, Ny, world, 1, arch.rx, arch.ry)
-
-    class G:        # grid stub: only sizes are needed by Field / fold_exchange
-        pass
-    g = G()
-    g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz = nx, ny, Nz, H, H, H
-    g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
-    g.size, g.halo = (nx, ny, Nz), (H, H, H)
-    C_, F_ = ossg.Center, ossg.Face
-    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)]
-    shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
-    fields = [ossg.Field(loc, g, data=torch.empty(shape, dtype=torch.float64, device=dev)) for loc in locs]
-    L = _lib.lib()
-    for k, f in enumerate(fields):
-        d = f.descriptor()
-        _lib.check(L.ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
-    for _ in range(3):
-        fold_exchange(fields)
-    torch.cuda.synchronize(dev)
-    dist.barrier()
-    reps = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fold_exchange(fields)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    # bytes each rank receives per exchange: Hy rows (+1 for y-Center) x nx columns x Nz levels per field
-    recv = sum((H + (1 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fields)
-    return {"partition": f"({world},1)", "fields": 4, "ms_per_exchange": float(ms.item()),
-            "recv_bytes_per_rank": recv, "gbs_per_direction_per_gpu": recv / (float(ms.item()) * 1e-3) / 1e9}
+    import bench
+    return bench.bench_fold_exchange(world, rank, dev)
 
 
 def main():

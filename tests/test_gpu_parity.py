@@ -342,6 +342,52 @@ def test_fold_pack_unpack_equals_zipper(ossg, oracle):
                     assert _same_bits(np.ascontiguousarray(got), np.ascontiguousarray(exp)), (Rx, locname, sign, r)
 
 
+def test_peer_fold_kernel_equals_zipper(ossg, oracle):
+    """ossg_zipper_fill_peer (the one-kernel NVLink fold) with the top-row "ranks" emulated on one
+    GPU: every rank's tile is its own array, peer pointers are plain device pointers and each
+    rank's kernel runs on its own stream (they wait for each other through the epoch flags).
+    Two epochs, all four staggerings in one batch, Rx = 1..4, both signs, FP64 and FP32, pull
+    (peer loads) and push (peer stores) forms."""
+    from ossg_b200.distributed import local_sizes
+    lib_ = ossg._lib
+    L = lib_.lib()
+    gNx, Ny, Nz, Hx, Hy, Hz = 24, 10, 2, 3, 3, 1
+    for npdt, push in ((np.float64, 0), (np.float32, 0), (np.float64, 1), (np.float32, 1)):
+        for Rx in (1, 2, 3, 4):
+            sx = local_sizes(gNx, Rx)
+            starts = [1 + sum(sx[:r]) for r in range(Rx)]
+            specs = [(loc, sign) for loc in LOCS.values() for sign in (1, -1)]
+            hosts = [_poisoned_field((Nz + 2 * Hz, Ny + 2 * Hy, gNx + 2 * Hx), gNx, Ny, Nz, Hx, Hy, Hz, npdt, seed=11 + k)
+                     for k in range(len(specs))]
+            tiles = [[torch.as_tensor(np.ascontiguousarray(h[:, :, starts[r] - 1:starts[r] - 1 + sx[r] + 2 * Hx])).cuda()
+                      for r in range(Rx)] for h in hosts]
+            flags = [torch.zeros(2 * lib_.OSSG_MAX_PEERS + 1, dtype=torch.int64, device="cuda") for _ in range(Rx)]
+            streams = [torch.cuda.Stream() for _ in range(Rx)]
+            torch.cuda.synchronize()
+            wants = [h.copy() for h in hosts]
+            for epoch in (1, 2):
+                for r in range(Rx):
+                    fd = lib_.PeerFoldDesc()
+                    fd.gNx, fd.me, fd.nranks, fd.epoch, fd.push = gNx, r, Rx, epoch, push
+                    for q in range(Rx):
+                        fd.i0[q], fd.nx[q] = starts[q], sx[q]
+                        fd.flags_peer[q] = None if q == r else flags[q].data_ptr()
+                    fd.flags_local = flags[r].data_ptr()
+                    arr = (lib_.PeerField * len(specs))()
+                    for k, (loc, sign) in enumerate(specs):
+                        arr[k].f = _desc(ossg, tiles[k][r], (sx[r], Ny, Nz, Hx, Hy, Hz), loc, sign)
+                        for q in range(Rx):
+                            arr[k].peer[q] = tiles[k][q].data_ptr()
+                    lib_.check(L.ossg_zipper_fill_peer(arr, len(specs), C.byref(fd), streams[r].cuda_stream))
+                torch.cuda.synchronize()
+                for k, (loc, sign) in enumerate(specs):
+                    oracle.zipper(wants[k], gNx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+                    for r in range(Rx):
+                        got = tiles[k][r].cpu().numpy()[:, :, Hx:Hx + sx[r]]
+                        exp = wants[k][:, :, starts[r] - 1 + Hx:starts[r] - 1 + Hx + sx[r]]
+                        assert _same_bits(np.ascontiguousarray(got), np.ascontiguousarray(exp)), (npdt, push, Rx, loc, sign, r, epoch)
+
+
 # ------------------------------------------------------------------ argument errors through the ABI
 def test_abi_argument_errors(ossg):
     from ossg_b200.grids import make_params
