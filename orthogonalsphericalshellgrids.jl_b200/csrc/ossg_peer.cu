@@ -79,6 +79,7 @@ struct PeerBatch {
     ossg_peer_field pf[OSSG_MAX_PEER_BATCH];
     ossg_peer_fold fold;
     int n;
+    unsigned int partners;       // bit r: rank r owns fold sources / destinations of this rank's columns
     int chunks, levels;          // work items: n fields x levels x chunks of PB columns
     long long nitems;
 };
@@ -166,15 +167,16 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
 {
     const ossg_peer_fold& fd = b.fold;
     unsigned long long* mine = static_cast<unsigned long long*>(fd.flags_local);
-    // ---- start barrier
-    if (threadIdx.x == 0) {
+    // ---- start barrier with the partner ranks (owners of the mirror columns): lane r talks to rank r
+    const int t = threadIdx.x;
+    const bool partner = t < fd.nranks && t != fd.me && ((b.partners >> t) & 1u);
+    unsigned int* error_word = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1;
+    if (partner) {
         if (blockIdx.x == 0) {
             __threadfence_system();
-            for (int r = 0; r < fd.nranks; ++r)
-                if (r != fd.me) st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[r]) + fd.me, fd.epoch);
+            st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[t]) + fd.me, fd.epoch);
         }
-        for (int r = 0; r < fd.nranks; ++r)
-            if (r != fd.me) wait_epoch(mine + r, fd.epoch, reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1);
+        wait_epoch(mine + t, fd.epoch, error_word);
     }
     __syncthreads();
 
@@ -197,21 +199,23 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
         }
     }
 
-    // ---- end barrier (last block only)
+    // ---- end barrier (last block only, lane r talks to rank r)
+    __shared__ int is_last;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (t == 0) {
         unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);
-        const unsigned int total = gridDim.x;
         __threadfence();                                              // release this block's stores ...
-        if (atomicAdd(counter, 1u) == total - 1) {
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (is_last) {
             __threadfence();                                          // ... and acquire everybody else's
             atomicExch(counter, 0u);                                  // ready for the next launch (stream-ordered)
-            __threadfence_system();
-            for (int r = 0; r < fd.nranks; ++r)
-                if (r != fd.me) st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[r]) + OSSG_MAX_PEERS + fd.me, fd.epoch);
-            for (int r = 0; r < fd.nranks; ++r)
-                if (r != fd.me) wait_epoch(mine + OSSG_MAX_PEERS + r, fd.epoch, counter + 1);
         }
+    }
+    __syncthreads();
+    if (is_last && partner) {
+        __threadfence_system();
+        st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[t]) + OSSG_MAX_PEERS + fd.me, fd.epoch);
+        wait_epoch(mine + OSSG_MAX_PEERS + t, fd.epoch, error_word);
     }
 }
 
@@ -318,6 +322,22 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
             if (!b.pf[k].peer[r]) return set_error(OSSG_EINVAL, "field %d: peer[%d] is NULL", k, r);
         gx = max(gx, ceil_div(f.Nx, PB));
         gy = max(gy, f.nk);
+    }
+    // partner ranks: owners of the images of this rank's columns under the fold map (an involution,
+    // so the relation is symmetric: r is my partner exactly when I am r's)
+    b.partners = 0;
+    {
+        const int lo = fd.i0[fd.me], hi = lo + fd.nx[fd.me] - 1;
+        for (int k = 0; k < nfields; ++k) {
+            const int c = b.pf[k].f.locx ? 2 : 1;
+            for (int r = 0; r < fd.nranks; ++r) {
+                const int rlo = fd.i0[r], rhi = rlo + fd.nx[r] - 1;
+                int a0 = fd.gNx - hi + c, a1 = fd.gNx - lo + c;               // image range, ascending
+                bool hit = a0 <= rhi && (a1 > fd.gNx ? fd.gNx : a1) >= rlo;
+                if (a1 > fd.gNx && rlo == 1) hit = true;                     // x-Face: column Nx+1 wraps onto column 1
+                if (hit) b.partners |= 1u << r;
+            }
+        }
     }
     b.chunks = gx;
     b.levels = gy;
