@@ -367,20 +367,26 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
     for (loc, _) in specs:
         algo += 2 * H * nx * Nz * 8 + (nx * Nz * 8 if loc[1] == 0 else 0)
     res = {}
-    for name, n in (("batch4", 4), ("single", 1)):
+    # periodic west/east fill over the whole (y, z) parent extent: read + write of 2 Hx elements per row
+    rows = (ny + 2 * H) * (Nz + 2 * H)
+    algo_full = algo + len(specs) * rows * 2 * (2 * H) * 8
+    for name, n, fn in (("batch4", 4, L.ossg_zipper_fill_batch), ("single", 1, L.ossg_zipper_fill_batch),
+                        ("fill_halo_regions_batch4", 4, L.ossg_fill_halo_regions_batch)):
         times = []
         for it in range(8):
             flush.fill_(it)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            _lib.check(L.ossg_zipper_fill_batch(descs, n, stream.cuda_stream))
+            _lib.check(fn(descs, n, stream.cuda_stream))
             e1.record(stream)
             torch.cuda.synchronize(dev)
             if it >= 3:
                 times.append(e0.elapsed_time(e1))
         ms = sum(times) / len(times)
-        b = algo if n == 4 else (2 * H * nx * Nz * 8 + nx * Nz * 8)
+        b = algo_full if name.startswith("fill") else algo if n == 4 else (2 * H * nx * Nz * 8 + nx * Nz * 8)
         res[name] = {"ms": ms, "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9}
+    res["fill_halo_regions_batch4"]["what"] = ("zipper north fill + periodic west/east fill of c,u,v,zeta in ONE launch "
+                                               "(fill_fused_kernel); the periodic part moves 32-byte pieces, one DRAM sector each way")
     res["config"] = f"{nx}x{ny}x{Nz} FP64 fields c,u,v,zeta, Hy=4, L2 flushed (256 MB write) before each timed fill"
     del fields
     return res

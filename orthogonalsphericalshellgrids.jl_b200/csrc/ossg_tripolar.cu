@@ -67,10 +67,9 @@ __global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, d
         const int j = face ? u + 1 : u - Ny + 1;
         const double a = focal_distance(north_poles_latitude);
         const double phi = face ? phi_face(j, Ny, south) : phi_center(j, Ny, south);
-        const double psi = m::asinh_cr(m::tand((90.0 - phi) / 2) / a);   // :66
         const int o = face ? 0 : 2;
-        double sh, ch;
-        m::sinh_cosh_cr(psi, sh, ch);
+        double psi, sh, ch;
+        m::asinh_sinh_cosh_cr(m::tand((90.0 - phi) / 2) / a, psi, sh, ch);   // :66-68
         ys[(size_t)(o + 0) * Ny + (j - 1)] = ch;
         ys[(size_t)(o + 1) * Ny + (j - 1)] = sh;
     } else if (t < 2 * Nx + 2 * Ny + g.Hy + 1) {

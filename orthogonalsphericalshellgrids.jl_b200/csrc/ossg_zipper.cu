@@ -95,6 +95,110 @@ __global__ void __launch_bounds__(ZB) periodic_x_kernel(const __grid_constant__ 
     else periodic_element<float>(f, h, row);
 }
 
+// ------------------------------------------------------------------ fused fill_halo_regions!
+// Zipper north fill AND periodic west/east fill in ONE launch (Oceananigans runs them as two
+// tasks, the periodic one second so that the NW/NE corners carry folded values).  The ordering is
+// removed instead of enforced: the thread that produces a folded value for an edge column
+// (i <= Hx or i > Nx-Hx) also stores its periodic image, so no thread ever reads what another
+// thread of the same launch writes:
+//   part A  one thread per (i, zipper level): the zipper column of zipper_column() plus the periodic
+//           images of the north-halo rows and -- y-Center fields -- of row Ny;
+//   part B  one thread per (row, side) for every other row of the parent (interior and south-halo
+//           rows, all rows of the z-halo levels): a plain periodic copy of Hx elements.
+// Requires Hx < Nx/2 (an edge column then has exactly one image and never is the self-mirrored
+// column Nx/2+1 of the (Face, Center) sign quirk); smaller grids use the two-launch form.
+template <typename T>
+__device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1..Nx*/, int kk)
+{
+    const int Nx = f.Nx, Ny = f.Ny, Hy = f.Hy, Hx = f.Hx;
+    const size_t sx = (size_t)(Nx + 2 * Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
+    T* c = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
+    double s = f.sign;
+    int ip = f.locx ? Nx - i + 2 : Nx - i + 1;
+    if (ip > Nx) { s = fabs(s); ip -= Nx; }
+    const T* src = c + (size_t)((f.locy ? Ny : Ny - 1) + Hy - 1) * sx + (ip + Hx - 1);
+    T* dst = c + (size_t)(Ny + Hy) * sx + (i + Hx - 1);
+    T* rowNy = c + (size_t)(Ny + Hy - 1) * sx + (i + Hx - 1);
+    const bool img_e = i <= Hx, img_w = i > Nx - Hx;                 // periodic image at i + Nx, resp. i - Nx
+    const ptrdiff_t img = img_e ? (ptrdiff_t)Nx : -(ptrdiff_t)Nx;
+    const bool has_img = img_e || img_w;
+    const bool fix_row = (f.locy == OSSG_CENTER) && (i > Nx / 2);
+    T vrow = T(0);
+    if (f.locy == OSSG_CENTER && (fix_row || has_img)) vrow = fix_row ? c[(size_t)(Ny + Hy - 1) * sx + (ip + Hx - 1)] : *rowNy;
+    int r = 0;
+    for (; r + 4 <= Hy; r += 4) {
+        T v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = src[-(ptrdiff_t)((r + u) * sx)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T o = apply_sign(v[u], s);
+            dst[(size_t)(r + u) * sx] = o;
+            if (has_img) dst[(ptrdiff_t)((r + u) * sx) + img] = o;
+        }
+    }
+    for (; r < Hy; ++r) {
+        const T o = apply_sign(src[-(ptrdiff_t)(r * sx)], s);
+        dst[(size_t)r * sx] = o;
+        if (has_img) dst[(ptrdiff_t)(r * sx) + img] = o;
+    }
+    if (f.locy == OSSG_CENTER) {
+        const T o = fix_row ? apply_sign(vrow, s) : vrow;
+        if (fix_row) *rowNy = o;
+        if (has_img) rowNy[img] = o;
+    }
+}
+
+// part B: one thread per (row, side), loads before stores
+template <typename T>
+__device__ __forceinline__ void fused_periodic_row(const ossg_field_desc& f, size_t row, int side)
+{
+    const int Nx = f.Nx, Hx = f.Hx;
+    T* c = static_cast<T*>(f.data) + row * (size_t)(Nx + 2 * Hx);
+    const T* src = side ? c + Hx : c + Nx;                           // east halo <- west interior ; west halo <- east interior
+    T* dst = side ? c + Nx + Hx : c;
+    int h = 0;
+    for (; h + 4 <= Hx; h += 4) {
+        const T v0 = src[h], v1 = src[h + 1], v2 = src[h + 2], v3 = src[h + 3];
+        dst[h] = v0; dst[h + 1] = v1; dst[h + 2] = v2; dst[h + 3] = v3;
+    }
+    for (; h < Hx; ++h) dst[h] = src[h];
+}
+
+struct FusedBatch {
+    FieldBatch b;
+    int blocksA[MAX_BATCH];          // part A blocks of field k: ceil(Nx / ZB) * nk
+    int chunksA[MAX_BATCH];          // ceil(Nx / ZB)
+};
+
+__global__ void __launch_bounds__(ZB) fill_fused_kernel(const __grid_constant__ FusedBatch fb)
+{
+    const int k = blockIdx.y;
+    const ossg_field_desc& f = fb.b.f[k];
+    const int nA = fb.blocksA[k];
+    if ((int)blockIdx.x < nA) {
+        const int chunk = blockIdx.x % fb.chunksA[k], kk = blockIdx.x / fb.chunksA[k];
+        const int i = chunk * ZB + threadIdx.x + 1;
+        if (i > f.Nx) return;
+        if (f.elem_type == OSSG_F64) fused_column<double>(f, i, kk);
+        else fused_column<float>(f, i, kk);
+        return;
+    }
+    const int sy = f.Ny + 2 * f.Hy;
+    const long long rows = (long long)sy * (f.Nz + 2 * f.Hz);
+    const long long t = (long long)(blockIdx.x - nA) * ZB + threadIdx.x;
+    // rows whose periodic images part A writes: north-halo rows (and row Ny of y-Center fields) of the zipper levels
+    auto part_a_row = [&](long long row) {
+        const int lev = (int)(row / sy), jrow = (int)(row - (long long)lev * sy);
+        return lev >= f.k0 && lev < f.k0 + f.nk && jrow >= f.Ny + f.Hy - (f.locy == OSSG_CENTER ? 1 : 0);
+    };
+    if (t >= 2 * rows) return;
+    const long long row = t >> 1;
+    if (part_a_row(row)) return;
+    if (f.elem_type == OSSG_F64) fused_periodic_row<double>(f, (size_t)row, (int)(t & 1));
+    else fused_periodic_row<float>(f, (size_t)row, (int)(t & 1));
+}
+
 // ------------------------------------------------------------------ (x,y)-partition fold: pack / unpack
 struct FoldArgs {
     ossg_field_desc f;
@@ -183,11 +287,32 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
         b.n = n - base < MAX_BATCH ? n - base : MAX_BATCH;
         int gx = 0, gy = 0;
         size_t pmax = 0;
+        bool fusable = with_periodic;
         for (int k = 0; k < b.n; ++k) {
             const ossg_field_desc& in = fields[base + k];
             if (in.Nx % 2 != 0) return set_error(OSSG_EODD_NX, "field %d: Nx must be even for the fold", base + k);
             int rc = check_field(in, b.f[k], base + k);
             if (rc) return rc;
+            if (b.f[k].Hy < 1 || b.f[k].Hx < 1 || 2 * b.f[k].Hx >= b.f[k].Nx || b.f[k].nk < 1) fusable = false;
+        }
+        if (fusable) {                       // zipper + periodic in one launch
+            FusedBatch fb;
+            fb.b = b;
+            long long gxf = 0;
+            for (int k = 0; k < b.n; ++k) {
+                const ossg_field_desc& f = b.f[k];
+                fb.chunksA[k] = ceil_div(f.Nx, ZB);
+                fb.blocksA[k] = fb.chunksA[k] * f.nk;
+                const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
+                const long long blocks = fb.blocksA[k] + (2 * rows + ZB - 1) / ZB;
+                gxf = gxf > blocks ? gxf : blocks;
+            }
+            if (gxf > 0x7fffffffLL) return set_error(OSSG_EINVAL, "field too large for one launch");
+            fill_fused_kernel<<<dim3((unsigned)gxf, b.n), ZB, 0, s>>>(fb);
+            OSSG_LAUNCH_CHECK("fill_fused_kernel");
+            continue;
+        }
+        for (int k = 0; k < b.n; ++k) {
             if (b.f[k].Hy == 0) continue;
             gx = max(gx, ceil_div(b.f[k].Nx, ZB));
             gy = max(gy, b.f[k].nk);

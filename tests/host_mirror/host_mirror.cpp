@@ -34,12 +34,13 @@ static void build_tables(const HMParams& p, std::vector<double>& buf)
     }
     for (int j = 1; j <= Ny; ++j) {
         const double pf = phi_face(j, Ny, p.south), pc = phi_center(j, Ny, p.south);
-        const double psf = m::asinh_cr(m::tand((90.0 - pf) / 2) / a);
-        const double psc = m::asinh_cr(m::tand((90.0 - pc) / 2) / a);
-        ys[0 * (size_t)Ny + j - 1] = m::cosh_cr(psf);
-        ys[1 * (size_t)Ny + j - 1] = m::sinh_cr(psf);
-        ys[2 * (size_t)Ny + j - 1] = m::cosh_cr(psc);
-        ys[3 * (size_t)Ny + j - 1] = m::sinh_cr(psc);
+        double psf, psc, shf, chf, shc, chc;                           // as the table kernel does
+        m::asinh_sinh_cosh_cr(m::tand((90.0 - pf) / 2) / a, psf, shf, chf);
+        m::asinh_sinh_cosh_cr(m::tand((90.0 - pc) / 2) / a, psc, shc, chc);
+        ys[0 * (size_t)Ny + j - 1] = chf;
+        ys[1 * (size_t)Ny + j - 1] = shf;
+        ys[2 * (size_t)Ny + j - 1] = chc;
+        ys[3 * (size_t)Ny + j - 1] = shc;
     }
     for (int r = 0; r <= p.Hy; ++r) latlon_row(r + 1 - p.Hy, Nx, Ny, p.Hy, p.south, p.radius, ll + (size_t)r * LL_NCOL);
 }
@@ -128,6 +129,9 @@ int hm_math_eval(int fn, const double* x, double* y, size_t n)
         case 10: { double sn, cs; m::sincosd(x[e], sn, cs); y[e] = sn; break; }
         case 11: { double sn, cs; m::sincosd(x[e], sn, cs); y[e] = cs; break; }
         case 12: y[e] = m::atan_short(x[e]); break;          // callers restrict |x| < ATAN_SHORT
+        case 13: { double p, sh, ch; m::asinh_sinh_cosh_cr(x[e], p, sh, ch); y[e] = p; break; }
+        case 14: { double p, sh, ch; m::asinh_sinh_cosh_cr(x[e], p, sh, ch); y[e] = sh; break; }
+        case 15: { double p, sh, ch; m::asinh_sinh_cosh_cr(x[e], p, sh, ch); y[e] = ch; break; }
         default: return -1;
         }
     }

@@ -143,3 +143,13 @@ def test_tile_kernel_quadrilateral_is_bit_identical_to_the_general_form(mirror):
     rows[:20, 2:4] = rows[:20, 0:2]                                      # two coincident corners
     a, b = hm.quadrilateral(mirror, 1, rows), hm.quadrilateral(mirror, 0, rows)
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_fused_asinh_sinh_cosh_equals_the_separate_functions(mirror, oracle):
+    """The table kernel derives psi = asinh(t), sinh(psi), cosh(psi) from one double-double
+    exponential; the doubles must be those of the oracle's three separate functions."""
+    ts = np.concatenate([10.0 ** RNG.uniform(-9, 2.5, 60000), -(10.0 ** RNG.uniform(-3, 2, 2000)), [0.0, -0.0, 1.0, 35.7]])
+    psi = hm.math(mirror, 13, ts)
+    assert np.array_equal(psi.view(np.uint64), oracle.math("asinh", ts).view(np.uint64))
+    assert np.array_equal(hm.math(mirror, 14, ts).view(np.uint64), oracle.math("sinh", psi).view(np.uint64))
+    assert np.array_equal(hm.math(mirror, 15, ts).view(np.uint64), oracle.math("cosh", psi).view(np.uint64))
