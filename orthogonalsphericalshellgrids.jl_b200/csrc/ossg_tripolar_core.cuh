@@ -280,12 +280,12 @@ OSSG_HD Vec3 lat_lon_to_cartesian(double lat, double lon)
     v.z = sin_lat;
     return v;
 }
-// straight-line form for the tile kernel: valid when |lat|, |lon| < 360, otherwise sets `bad`
+// straight-line form for the tile kernel: valid for |lat| <= 90 and 0 <= lon < 360, otherwise sets `bad`
 OSSG_HD Vec3 lat_lon_to_cartesian_spec(double lat, double lon, bool& bad)
 {
     double sin_lat, cos_lat, sin_lon, cos_lon;
-    m::sincosd_spec(lat, sin_lat, cos_lat, bad);
-    m::sincosd_spec(lon, sin_lon, cos_lon, bad);
+    m::sincosd_lat_spec(lat, sin_lat, cos_lat, bad);
+    m::sincosd_lon_spec(lon, sin_lon, cos_lon, bad);
     Vec3 v;
     v.x = cos_lon * cos_lat;
     v.y = sin_lon * cos_lat;

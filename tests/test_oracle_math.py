@@ -153,3 +153,17 @@ def test_fused_asinh_sinh_cosh_equals_the_separate_functions(mirror, oracle):
     assert np.array_equal(psi.view(np.uint64), oracle.math("asinh", ts).view(np.uint64))
     assert np.array_equal(hm.math(mirror, 14, ts).view(np.uint64), oracle.math("sinh", psi).view(np.uint64))
     assert np.array_equal(hm.math(mirror, 15, ts).view(np.uint64), oracle.math("cosh", psi).view(np.uint64))
+
+
+def test_specialised_unit_vector_trig_is_bit_identical(mirror):
+    """sincosd_lat_spec (|x| <= 90) and sincosd_lon_spec (0 <= x < 360) -- the tile kernel's
+    straight-line forms -- against sind / cosd, inside their ranges, at every octant boundary and
+    (through the `bad` fallback) outside."""
+    edges = np.arange(-360.0, 361.0, 45.0)
+    lat = np.concatenate([RNG.uniform(-90, 90, 200000), edges, np.nextafter(edges, np.inf), np.nextafter(edges, -np.inf),
+                          [0.0, -0.0, 1e-300, -1e-300, 90.0, -90.0, 91.0, np.nan, np.inf]])
+    lon = np.concatenate([RNG.uniform(0, 360, 200000), edges, np.nextafter(edges, np.inf), np.nextafter(edges, -np.inf),
+                          [0.0, -0.0, 1e-300, 359.99999999999994, 360.0, -1.0, np.nan]])
+    for xs, (fs, fc) in ((lat, (16, 17)), (lon, (18, 19))):
+        assert np.array_equal(hm.math(mirror, fs, xs).view(np.uint64), hm.math(mirror, 0, xs).view(np.uint64))
+        assert np.array_equal(hm.math(mirror, fc, xs).view(np.uint64), hm.math(mirror, 1, xs).view(np.uint64))
