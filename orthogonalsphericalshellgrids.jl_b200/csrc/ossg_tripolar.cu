@@ -135,11 +135,31 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
     }
 }
 
+// 1-D grid of coords_pair_kernel: the pair rows (J = 1..Ny-1) need Nx/2 + 1 + 2Hx threads, the other
+// rows one thread per padded element; a 2-D grid sized for the latter would launch an empty
+// second half for every pair row.
+struct PairGrid { int jw_lo, n_pair_rows, chunks_pair, chunks_full; };
+
 template <typename FT>
-__global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_constant__ BuildArgs a)
+__global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int jw = blockIdx.y;
+    int jw, chunk;
+    {
+        const int b = blockIdx.x, nb_pair = pg.n_pair_rows * pg.chunks_pair;
+        if (b < nb_pair) {
+            const int r = b / pg.chunks_pair;
+            jw = pg.jw_lo + r;
+            chunk = b - r * pg.chunks_pair;
+        } else {
+            const int r = (b - nb_pair) / pg.chunks_full;
+            chunk = (b - nb_pair) - r * pg.chunks_full;
+            jw = r < pg.jw_lo ? r : r + pg.n_pair_rows;
+        }
+    }
+    __shared__ double s_atan[24];                            // atan reduction table (ossg_math.cuh)
+    if (threadIdx.x < 24) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
+    __syncthreads();
+    const int t = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
     const int Nx = g.Nx, Hx = g.Hx;
     const int J = a.w.J0 + jw;
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
                 const size_t om = row + (size_t)(im + Hx - 1);
 #pragma unroll 1
                 for (int fy = 0; fy < 2; ++fy) {                // fy = 0: FC (y-Center), 1: FF
-                    const PointCore c = tripolar_core(as, ac, fy ? chF : chC, fy ? shF : shC);
+                    const PointCore c = tripolar_core_lut(as, ac, fy ? chF : chC, fy ? shF : shC, s_atan);
                     const int loc = fy ? FF : FC;
                     store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
                     if (has_mirror)
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
                 const size_t om = row + (size_t)(im + Hx - 1);
 #pragma unroll 1
                 for (int fy = 0; fy < 2; ++fy) {                // fy = 0: CC, 1: CF
-                    const PointCore c = tripolar_core(as, ac, fy ? chF : chC, fy ? shF : shC);
+                    const PointCore c = tripolar_core_lut(as, ac, fy ? chF : chC, fy ? shF : shC, s_atan);
                     const int loc = fy ? CF : CC;
                     store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
                     store_coord<FT>(a, loc, om, tripolar_finish(-c.lam_a, c.pole, false, ipm <= half, fpl), c.phi);
@@ -518,7 +538,15 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
     dim3 block(256), grid(ceil_div(a.w.wnx, 256), a.w.wny);
     const bool full_x = a.w.I0 == 1 - a.g.Hx && a.w.wnx == a.g.Nx + 2 * a.g.Hx;
     if (full_x && a.g.Hx <= a.g.Nx / 2) {       // (wnx >= Nx/2 + 1 + 2Hx threads per row are available)
-        coords_pair_kernel<FT><<<grid, block, 0, s>>>(a);
+        PairGrid pg;
+        pg.jw_lo = max(0, 1 - a.w.J0);
+        const int jw_hi = min(a.w.wny - 1, a.g.Ny - 1 - a.w.J0);
+        pg.n_pair_rows = max(0, jw_hi - pg.jw_lo + 1);
+        if (pg.n_pair_rows == 0) pg.jw_lo = 0;
+        pg.chunks_pair = ceil_div(a.g.Nx / 2 + 1 + 2 * a.g.Hx, 256);
+        pg.chunks_full = ceil_div(a.w.wnx, 256);
+        const long long nb = (long long)pg.n_pair_rows * pg.chunks_pair + (long long)(a.w.wny - pg.n_pair_rows) * pg.chunks_full;
+        coords_pair_kernel<FT><<<(unsigned)nb, block, 0, s>>>(a, pg);
         OSSG_LAUNCH_CHECK("coords_pair_kernel");
     } else {
         coords_kernel<FT><<<grid, block, 0, s>>>(a);

@@ -132,6 +132,23 @@ OSSG_HD PointCore tripolar_core(double as_i, double ac_i, double ch_j, double sh
     return c;
 }
 
+// the same point for the coordinate kernel's hot loop: table-driven atan, branch-free sqrt unless
+// x = y = 0 (the poles) or tiny
+OSSG_HD PointCore tripolar_core_lut(double as_i, double ac_i, double ch_j, double sh_j, const double* atan_table)
+{
+    const double x = as_i * ch_j;                                             // :67
+    const double y = ac_i * sh_j;                                             // :68
+    constexpr double m180_pi = -180.0 / m::PI_F64;
+    constexpr double p360_pi = 360.0 / m::PI_F64;
+    PointCore c;
+    c.pole = (x == 0.0) & (y == 0.0);                                         // :74
+    c.lam_a = m180_pi * m::atan_lut(y / x, atan_table);                       // :77
+    const double rho2 = y * y + x * x;
+    const double rho = (m::hi_abs(rho2) >= m::SQRT_NB_MIN_HI && rho2 < 0x1p1000) ? m::sqrt_nb(rho2) : sqrt(rho2);
+    c.phi = 90.0 - p360_pi * m::atan_lut(rho, atan_table);                    // :78
+    return c;
+}
+
 // tail of the point: pole value (:75-77), hemisphere shift (:82), pole-longitude shift (:86), wrap (:87)
 OSSG_HD double tripolar_finish(double lam_a, bool pole, bool ip_is_one, bool ip_le_half, double first_pole_longitude)
 {

@@ -167,3 +167,15 @@ def test_specialised_unit_vector_trig_is_bit_identical(mirror):
     for xs, (fs, fc) in ((lat, (16, 17)), (lon, (18, 19))):
         assert np.array_equal(hm.math(mirror, fs, xs).view(np.uint64), hm.math(mirror, 0, xs).view(np.uint64))
         assert np.array_equal(hm.math(mirror, fc, xs).view(np.uint64), hm.math(mirror, 1, xs).view(np.uint64))
+
+
+def test_table_driven_atan_is_bit_identical(mirror, oracle):
+    """atan_lut (coordinate kernel) against atan_f / the oracle over all reduction ranges, at the
+    range bounds, at the zero-numerator arguments 0.5, 1, 1.5 and at 0, inf, nan."""
+    b = np.array([0.4375, 0.6875, 1.1875, 2.4375, 0.5, 1.0, 1.5, 2.0 ** 66])
+    xs = np.concatenate([RNG.uniform(-6, 6, 300000), 10.0 ** RNG.uniform(-12, 25, 100000), -(10.0 ** RNG.uniform(-3, 3, 20000)),
+                         b, -b, np.nextafter(b, np.inf), np.nextafter(b, -np.inf), [0.0, -0.0, np.inf, -np.inf, np.nan, 1e300]])
+    a = hm.math(mirror, 20, xs)
+    assert np.array_equal(a.view(np.uint64), hm.math(mirror, orc.MATH_FN["atan"], xs).view(np.uint64))
+    fin = ~np.isnan(xs)
+    assert np.array_equal(a[fin].view(np.uint64), oracle.math("atan", xs[fin]).view(np.uint64))
