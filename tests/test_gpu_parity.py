@@ -178,6 +178,30 @@ def test_tiles_equal_slices_of_the_serial_grid(ossg, oracle, Rx, Ry, dtype):
                 assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)), (name, rx, ry)
 
 
+@pytest.mark.parametrize("Rx,Ry,dtype", [(1, 8, torch.float64), (2, 2, torch.float64), (3, 2, torch.float32), (1, 4, torch.float32)])
+def test_fine_grid_tiles_equal_slices_of_the_serial_grid(ossg, oracle, Rx, Ry, dtype):
+    """The same on a 1/4 degree grid, where every tile runs the tile kernel's straight-line path,
+    the mirror-pair coordinate kernel (Rx = 1) and the per-element one (Rx > 1): the layouts of
+    bench.py's multi-GPU runs (Y slabs) and of the (x, y) partitions."""
+    from ossg_b200.distributed import tile_of
+    from ossg_b200.grids import build_arrays, make_params
+    size, halo = (1440, 720, 1), (4, 4, 4)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    oracle.set_threads(oracle.max_threads())
+    ref = oracle.build(orc.make_params(size, halo), dtype=npdt)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for rx in range(Rx):
+        for ry in range(Ry):
+            i0, j0, nx, ny = tile_of(size[0], size[1], Rx, Ry, rx, ry)
+            params = make_params(size, halo, -80, 55, 70, orc.R_EARTH, tile=(i0, j0, nx, ny))
+            tiles = build_arrays(params, dtype, dev)
+            torch.cuda.synchronize()
+            for name, t in zip(orc.ALL_NAMES, tiles):
+                want = ref[name][j0 - 1:j0 - 1 + ny + 2 * halo[1], i0 - 1:i0 - 1 + nx + 2 * halo[0]]
+                got = t.cpu().numpy()
+                assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)), (name, rx, ry)
+
+
 # ------------------------------------------------------------------ zipper
 LOCS = {"cc": (0, 0), "fc": (1, 0), "cf": (0, 1), "ff": (1, 1)}
 
