@@ -280,6 +280,8 @@ def run_own(args):
         zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny)
     else:
         zipper = {"fold_exchange": bench_fold_exchange(world, rank, dev)}
+        torch.cuda.empty_cache()
+        zipper["distributed_fill_halo_regions"] = bench_distributed_fill(world, rank, dev)
 
     # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels)
     ms = C.c_float(); fl = C.c_double()
@@ -472,6 +474,64 @@ def bench_fold_exchange(world, rank, dev):
             res[key]["frac_of_measured_copy_735"] = res[key]["gbs_per_direction_per_gpu"] / 735.0
         out["peer_kernel_push" if push else "peer_kernel_pull"] = res
     return out
+
+
+def bench_distributed_fill(world, rank, dev):
+    """fill_halo_regions! of c,u,v,zeta (FP64, Nz=100, halo 4) on the 1/12 degree grid in an (x, y)
+    partition -- the distributed_bickley_jet-style halo-fill loop (BASELINE config 5): fold on the
+    top row + south/north rows + west/east columns.  NCCL form (pack/send/recv/unpack through
+    torch.distributed) against the NVLink peer-memory form (three kernels per fill, PeerHalo)."""
+    import torch
+    import torch.distributed as dist
+    import ossg_b200 as ossg
+    from ossg_b200 import _lib
+    from ossg_b200.distributed import PeerHalo, distributed_fill_halo_regions, tile_of
+    Nx, Ny, Nz, H = 4320, 2160, 100, 4
+    Rx, Ry = {2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
+    arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(Rx, Ry))
+    i0, j0, nx, ny = tile_of(Nx, Ny, Rx, Ry, arch.rx, arch.ry)
+
+    class G:
+        pass
+    g = G()
+    g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz = nx, ny, Nz, H, H, H
+    g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
+    g.size, g.halo = (nx, ny, Nz), (H, H, H)
+    C_, F_ = ossg.Center, ossg.Face
+    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)]
+    shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
+    fields = [ossg.Field(loc, g, data=torch.zeros(shape, dtype=torch.float64, device=dev)) for loc in locs]
+    L = _lib.lib()
+    for k, f in enumerate(fields):
+        d = f.descriptor()
+        _lib.check(L.ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
+    reps = 10
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_nccl = timed(lambda: distributed_fill_halo_regions(fields))
+    t_peer = timed(PeerHalo(fields))
+    # bytes a rank receives per fill: fold rows (top row only), 2 x Hy rows, 2 x Hx columns over the parent extent
+    levels, sx, sy = Nz + 2 * H, nx + 2 * H, ny + 2 * H
+    recv = len(fields) * 8 * ((2 if Ry > 1 else 0) * H * sx * levels * (0.5 if Ry == 2 else 1.0) + 2 * H * sy * levels)
+    if arch.is_top_row():
+        recv += sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fields)
+    return {"partition": f"({Rx},{Ry})", "fields": len(fields), "approx_recv_bytes_top_row_rank": recv,
+            "nccl": {"ms_per_fill": t_nccl}, "peer_memory": {"ms_per_fill": t_peer, "kernels_per_fill": 3 if arch.is_top_row() else 2},
+            "speedup": t_nccl / t_peer}
 
 
 def main():

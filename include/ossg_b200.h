@@ -206,6 +206,35 @@ typedef struct ossg_peer_field {
  * make the matching call (same fields, same epoch) or the kernels wait for each other forever   */
 int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields, const ossg_peer_fold* fold, void* stream);
 
+/* ---- ordinary halos of an (x, y)-partitioned field over NVLink peer memory ------------------ *
+ * Replaces Oceananigans' MPI halo passing (Isend/Irecv of FieldBoundaryBuffers between j- and
+ * i-adjacent ranks) for ranks of one NVSwitch node, with the same two ordered steps: phase 0
+ * stores this rank's top / bottom Hy interior rows (whole rows, all parent levels) into the south
+ * halo of the north neighbour and the north halo of the south neighbour; phase 1 stores its east /
+ * west Hx interior columns over the WHOLE local y extent (so corners carry exchanged and folded
+ * rows) into the west halo of the east neighbour and the east halo of the west neighbour, periodic
+ * in x.  One kernel per phase, posted NVLink writes, the flag barriers of ossg_zipper_fill_peer
+ * between neighbours only.  A neighbour id of -1 means "no neighbour" (domain edge in y); a
+ * neighbour equal to `me` (Rx == 1) makes the copy local.                                       */
+typedef struct ossg_peer_halo {
+    int32_t me, nranks;                     /* rank id and world size (<= OSSG_MAX_PEERS)        */
+    int32_t north, south, east, west;       /* neighbour rank ids                                */
+    int32_t phase;                          /* 0: south/north rows, 1: west/east columns         */
+    int32_t reserved;
+    void*   flags_local;                    /* flag block of THIS phase (2*OSSG_MAX_PEERS+1 uint64) */
+    void*   flags_peer[OSSG_MAX_PEERS];     /* the same block on rank r, peer-mapped              */
+    uint64_t epoch;
+} ossg_peer_halo;
+
+typedef struct ossg_peer_halo_field {
+    ossg_field_desc f;                      /* the LOCAL field                                   */
+    void*   north; void* south; void* east; void* west;   /* the field's data on the neighbours  */
+    int32_t ny_north, ny_south;             /* interior rows of the north / south neighbour      */
+    int32_t nx_east, nx_west;               /* interior columns of the east / west neighbour     */
+} ossg_peer_halo_field;
+
+int ossg_halo_exchange_peer(const ossg_peer_halo_field* fields, int nfields, const ossg_peer_halo* halo, void* stream);
+
 /* ---- measurement / test utilities (not part of the reference surface) ---------------------- */
 /* interior(c)[i,j,k] = hash(seed, global i, j, k) in [-1, 1); halos are filled with a NaN payload */
 int ossg_synth_field(const ossg_field_desc* f, uint64_t seed, int32_t gi0, int32_t gj0, void* stream);

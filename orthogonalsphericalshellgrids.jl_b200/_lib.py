@@ -60,6 +60,19 @@ class PeerField(C.Structure):
     _fields_ = [("f", FieldDesc), ("peer", C.c_void_p * OSSG_MAX_PEERS)]
 
 
+class PeerHaloDesc(C.Structure):
+    _fields_ = [("me", C.c_int32), ("nranks", C.c_int32),
+                ("north", C.c_int32), ("south", C.c_int32), ("east", C.c_int32), ("west", C.c_int32),
+                ("phase", C.c_int32), ("reserved", C.c_int32),
+                ("flags_local", C.c_void_p), ("flags_peer", C.c_void_p * OSSG_MAX_PEERS),
+                ("epoch", C.c_uint64)]
+
+
+class PeerHaloField(C.Structure):
+    _fields_ = [("f", FieldDesc), ("north", C.c_void_p), ("south", C.c_void_p), ("east", C.c_void_p), ("west", C.c_void_p),
+                ("ny_north", C.c_int32), ("ny_south", C.c_int32), ("nx_east", C.c_int32), ("nx_west", C.c_int32)]
+
+
 class OSSGError(RuntimeError):
     """Non-argument failure reported by libossg_b200.so (a CUDA error)."""
 
@@ -108,6 +121,7 @@ def lib() -> C.CDLL:
     L.ossg_ipc_export.argtypes = [C.c_void_p, C.POINTER(IpcHandle), C.POINTER(C.c_uint64)]
     L.ossg_ipc_open.argtypes = [C.POINTER(IpcHandle), C.c_uint64, C.POINTER(C.c_void_p)]
     L.ossg_zipper_fill_peer.argtypes = [C.POINTER(PeerField), C.c_int, C.POINTER(PeerFoldDesc), C.c_void_p]
+    L.ossg_halo_exchange_peer.argtypes = [C.POINTER(PeerHaloField), C.c_int, C.POINTER(PeerHaloDesc), C.c_void_p]
     L.ossg_selftest_sqrt_div.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
     _lib = L
     return L

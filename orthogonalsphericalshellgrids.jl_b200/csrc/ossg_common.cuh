@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 
 #include "../../include/ossg_b200.h"
 
@@ -29,6 +30,33 @@ inline int cuda_fail(cudaError_t e, const char* what)
         cudaError_t _e = cudaGetLastError();                             \
         if (_e != cudaSuccess) return ::ossg::cuda_fail(_e, name);       \
     } while (0)
+
+#if defined(__CUDACC__)
+// Copy of one halo-width piece (Hx elements of a row).  The common case -- 4 doubles, both ends
+// 32-byte aligned -- is ONE 256-bit load and ONE 256-bit store (LDG.256 / STG.256, sm_100): one
+// DRAM sector, and over NVLink one 32-byte packet instead of four 8-byte ones.
+template <typename T>
+__device__ __forceinline__ void copy_halo_piece(T* dst, const T* src, int Hx)
+{
+    const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+    if (sizeof(T) == 8 && Hx == 4 && (both & 31) == 0) {
+        double a, b, c, d;
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(src));
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+        return;
+    }
+    if (sizeof(T) == 4 && Hx == 4 && (both & 15) == 0) {
+        *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+        return;
+    }
+    int q = 0;
+    for (; q + 4 <= Hx; q += 4) {
+        const T v0 = src[q], v1 = src[q + 1], v2 = src[q + 2], v3 = src[q + 3];
+        dst[q] = v0; dst[q + 1] = v1; dst[q + 2] = v2; dst[q + 3] = v3;
+    }
+    for (; q < Hx; ++q) dst[q] = src[q];
+}
+#endif
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

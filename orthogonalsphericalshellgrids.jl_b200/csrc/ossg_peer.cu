@@ -219,6 +219,104 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
     }
 }
 
+// ------------------------------------------------------------------ ordinary halos (push)
+struct HaloBatch {
+    ossg_peer_halo_field hf[OSSG_MAX_PEER_BATCH];
+    ossg_peer_halo halo;
+    int n;
+    unsigned int partners;
+    long long items_per_field;           // phase 0: 2 directions x Hy rows x parent levels x column chunks
+    int chunks;                          // phase 0: ceil((Nx + 2Hx) / PB); phase 1: ceil(rows / PB)
+};
+
+template <typename T>
+__device__ __forceinline__ void halo_rows_push(const ossg_peer_halo_field& h, long long item, int chunks)
+{
+    // item -> (direction, halo row r, parent level, column chunk)
+    const ossg_field_desc& f = h.f;
+    const int sx = f.Nx + 2 * f.Hx, levels = f.Nz + 2 * f.Hz;
+    const int chunk = (int)(item % chunks);
+    long long rest = item / chunks;
+    const int lev = (int)(rest % levels);
+    rest /= levels;
+    const int r = (int)(rest % f.Hy), dir = (int)(rest / f.Hy);     // dir 0: to the north neighbour, 1: to the south neighbour
+    const int col = chunk * PB + threadIdx.x;
+    if (col >= sx) return;
+    T* peer = static_cast<T*>(dir ? h.south : h.north);
+    if (!peer) return;
+    const int ny_peer = dir ? h.ny_south : h.ny_north;
+    const size_t sxy = (size_t)sx * (size_t)(f.Ny + 2 * f.Hy), sxy_peer = (size_t)sx * (size_t)(ny_peer + 2 * f.Hy);
+    const int src_row = dir ? f.Hy + r : f.Ny + r;                    // bottom / top Hy interior rows (parent index)
+    const int dst_row = dir ? ny_peer + f.Hy + r : r;                 // the neighbour's north / south halo
+    peer[(size_t)lev * sxy_peer + (size_t)dst_row * sx + col] = static_cast<const T*>(f.data)[(size_t)lev * sxy + (size_t)src_row * sx + col];
+}
+
+template <typename T>
+__device__ __forceinline__ void halo_cols_push(const ossg_peer_halo_field& h, long long item, int chunks)
+{
+    // item -> (side, chunk of PB parent rows); a thread moves the Hx elements of one (row, side)
+    const ossg_field_desc& f = h.f;
+    const int chunk = (int)(item % chunks), side = (int)(item / chunks);   // side 0: to the east neighbour, 1: to the west neighbour
+    const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
+    const long long row = (long long)chunk * PB + threadIdx.x;
+    if (row >= rows) return;
+    T* peer = static_cast<T*>(side ? h.west : h.east);
+    if (!peer) return;
+    const int nx_peer = side ? h.nx_west : h.nx_east;
+    const T* src = static_cast<const T*>(f.data) + (size_t)row * (size_t)(f.Nx + 2 * f.Hx) + (side ? f.Hx : f.Nx);
+    T* dst = peer + (size_t)row * (size_t)(nx_peer + 2 * f.Hx) + (side ? nx_peer + f.Hx : 0);
+    copy_halo_piece(dst, src, f.Hx);
+}
+
+__global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) halo_peer_kernel(const __grid_constant__ HaloBatch b)
+{
+    const ossg_peer_halo& hd = b.halo;
+    unsigned long long* mine = static_cast<unsigned long long*>(hd.flags_local);
+    const int t = threadIdx.x;
+    const bool partner = t < hd.nranks && t != hd.me && ((b.partners >> t) & 1u);
+    unsigned int* error_word = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1;
+    if (partner) {                                                    // start barrier (see zipper_peer_kernel)
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(static_cast<unsigned long long*>(hd.flags_peer[t]) + hd.me, hd.epoch);
+        }
+        wait_epoch(mine + t, hd.epoch, error_word);
+    }
+    __syncthreads();
+
+    const long long nitems = b.items_per_field * b.n;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int fi = (int)(item / b.items_per_field);
+        const long long it = item - (long long)fi * b.items_per_field;
+        const ossg_peer_halo_field& h = b.hf[fi];
+        if (hd.phase == 0) {
+            if (h.f.elem_type == OSSG_F64) halo_rows_push<double>(h, it, b.chunks);
+            else halo_rows_push<float>(h, it, b.chunks);
+        } else {
+            if (h.f.elem_type == OSSG_F64) halo_cols_push<double>(h, it, b.chunks);
+            else halo_cols_push<float>(h, it, b.chunks);
+        }
+    }
+
+    __shared__ int is_last;                                           // end barrier
+    __syncthreads();
+    if (t == 0) {
+        unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);
+        __threadfence();
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (is_last) {
+            __threadfence();
+            atomicExch(counter, 0u);
+        }
+    }
+    __syncthreads();
+    if (is_last && partner) {
+        __threadfence_system();
+        st_release_sys(static_cast<unsigned long long*>(hd.flags_peer[t]) + OSSG_MAX_PEERS + hd.me, hd.epoch);
+        wait_epoch(mine + OSSG_MAX_PEERS + t, hd.epoch, error_word);
+    }
+}
+
 // ------------------------------------------------------------------ CUDA IPC plumbing
 struct OpenedHandle { unsigned char h[64]; void* base; };
 static std::mutex g_ipc_mu;
@@ -349,5 +447,71 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
     const int grid = (int)(b.nitems < resident ? b.nitems : resident);
     zipper_peer_kernel<<<grid, PB, 0, as_stream(stream)>>>(b);
     OSSG_LAUNCH_CHECK("zipper_peer_kernel");
+    return 0;
+}
+
+extern "C" int ossg_halo_exchange_peer(const ossg_peer_halo_field* fields, int nfields, const ossg_peer_halo* halo, void* stream)
+{
+    if (!fields || !halo || nfields < 1) return set_error(OSSG_EINVAL, "fields/halo is NULL or nfields < 1");
+    if (nfields > OSSG_MAX_PEER_BATCH) return set_error(OSSG_EINVAL, "at most %d fields per peer launch, got %d", OSSG_MAX_PEER_BATCH, nfields);
+    const ossg_peer_halo& hd = *halo;
+    if (hd.nranks < 1 || hd.nranks > OSSG_MAX_PEERS || hd.me < 0 || hd.me >= hd.nranks)
+        return set_error(OSSG_EINVAL, "bad rank layout: me = %d of %d (max %d)", hd.me, hd.nranks, OSSG_MAX_PEERS);
+    if (hd.phase != 0 && hd.phase != 1) return set_error(OSSG_EINVAL, "phase must be 0 (rows) or 1 (columns)");
+    if (!hd.flags_local || reinterpret_cast<uintptr_t>(hd.flags_local) % 8) return set_error(OSSG_EALIGN, "flags_local must be an 8-byte aligned device pointer");
+    if (hd.epoch == 0) return set_error(OSSG_EINVAL, "epoch must start at 1 and grow by one per call");
+    const int nb[4] = { hd.north, hd.south, hd.east, hd.west };
+    HaloBatch b;
+    b.halo = hd;
+    b.n = nfields;
+    b.partners = 0;
+    for (int k = (hd.phase ? 2 : 0); k < (hd.phase ? 4 : 2); ++k) {
+        if (nb[k] < -1 || nb[k] >= hd.nranks) return set_error(OSSG_EINVAL, "neighbour id %d out of range", nb[k]);
+        if (nb[k] >= 0 && nb[k] != hd.me) {
+            if (!hd.flags_peer[nb[k]]) return set_error(OSSG_EINVAL, "flags_peer[%d] is NULL", nb[k]);
+            b.partners |= 1u << nb[k];
+        }
+    }
+    long long items = 0;
+    int chunks = 0;
+    for (int k = 0; k < nfields; ++k) {
+        b.hf[k] = fields[k];
+        const ossg_field_desc& f = b.hf[k].f;
+        if (!f.data) return set_error(OSSG_EINVAL, "field %d: data is NULL", k);
+        if (f.elem_type != OSSG_F64 && f.elem_type != OSSG_F32) return set_error(OSSG_EINVAL, "field %d: bad elem_type", k);
+        if (f.Nx < 1 || f.Ny < 1 || f.Nz < 1 || f.Hx < 0 || f.Hy < 0 || f.Hz < 0) return set_error(OSSG_EINVAL, "field %d: bad sizes", k);
+        if (f.Hy > f.Ny || f.Hx > f.Nx) return set_error(OSSG_EHALO, "field %d: halo (%d, %d) larger than the tile (%d, %d)", k, f.Hx, f.Hy, f.Nx, f.Ny);
+        if (k && (f.Nx != b.hf[0].f.Nx || f.Ny != b.hf[0].f.Ny || f.Nz != b.hf[0].f.Nz || f.Hx != b.hf[0].f.Hx || f.Hy != b.hf[0].f.Hy || f.Hz != b.hf[0].f.Hz))
+            return set_error(OSSG_EINVAL, "field %d: all fields of a batch must share size and halo", k);
+        if (hd.phase == 0) {
+            if ((hd.north >= 0 && !b.hf[k].north) || (hd.south >= 0 && !b.hf[k].south)) return set_error(OSSG_EINVAL, "field %d: neighbour pointer is NULL", k);
+            if (hd.north < 0) b.hf[k].north = nullptr;
+            if (hd.south < 0) b.hf[k].south = nullptr;
+        } else {
+            if ((hd.east >= 0 && !b.hf[k].east) || (hd.west >= 0 && !b.hf[k].west)) return set_error(OSSG_EINVAL, "field %d: neighbour pointer is NULL", k);
+            if (hd.east < 0) b.hf[k].east = nullptr;
+            if (hd.west < 0) b.hf[k].west = nullptr;
+        }
+    }
+    {
+        const ossg_field_desc& f = b.hf[0].f;
+        if (hd.phase == 0) {
+            chunks = ceil_div(f.Nx + 2 * f.Hx, PB);
+            items = 2LL * f.Hy * (f.Nz + 2 * f.Hz) * chunks;
+        } else {
+            const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
+            chunks = (int)((rows + PB - 1) / PB);
+            items = 2LL * chunks;
+        }
+    }
+    if (items == 0) return 0;
+    b.items_per_field = items;
+    b.chunks = chunks;
+    int dev = 0, sms = 0;
+    OSSG_CUDA_TRY(cudaGetDevice(&dev));
+    OSSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long resident = (long long)sms * PEER_BLOCKS_PER_SM, total = items * nfields;
+    halo_peer_kernel<<<(int)(total < resident ? total : resident), PB, 0, as_stream(stream)>>>(b);
+    OSSG_LAUNCH_CHECK("halo_peer_kernel");
     return 0;
 }

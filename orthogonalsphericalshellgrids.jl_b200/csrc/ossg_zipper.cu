@@ -157,12 +157,7 @@ __device__ __forceinline__ void fused_periodic_row(const ossg_field_desc& f, siz
     T* c = static_cast<T*>(f.data) + row * (size_t)(Nx + 2 * Hx);
     const T* src = side ? c + Hx : c + Nx;                           // east halo <- west interior ; west halo <- east interior
     T* dst = side ? c + Nx + Hx : c;
-    int h = 0;
-    for (; h + 4 <= Hx; h += 4) {
-        const T v0 = src[h], v1 = src[h + 1], v2 = src[h + 2], v3 = src[h + 3];
-        dst[h] = v0; dst[h + 1] = v1; dst[h + 2] = v2; dst[h + 3] = v3;
-    }
-    for (; h < Hx; ++h) dst[h] = src[h];
+    copy_halo_piece(dst, src, Hx);
 }
 
 struct FusedBatch {

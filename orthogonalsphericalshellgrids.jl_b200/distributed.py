@@ -350,6 +350,99 @@ class PeerFold:
         return (word >> 32) != 0
 
 
+class PeerHalo:
+    """fill_halo_regions! of fields on an (x, y)-partitioned tripolar grid entirely over NVLink peer
+    memory: the fold (PeerFold, top row), then south/north rows, then west/east columns over the
+    whole y extent (ossg_halo_exchange_peer, one kernel per phase) -- the order of
+    distributed_fill_halo_regions(), without NCCL, staging buffers or host synchronisation.
+    Collective constructor over `group` (all ranks, same field list, world size <= 8)."""
+
+    def __init__(self, fields: Sequence, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        arch = fields[0].grid.architecture
+        world = dist.get_world_size(group)
+        if world > _lib.OSSG_MAX_PEERS:
+            raise ValueError(f"PeerHalo supports at most {_lib.OSSG_MAX_PEERS} ranks, got {world}")
+        self.arch, self.fields, self.epoch = arch, list(fields), 0
+        self.fold = PeerFold(fields, group=group)
+        L = _lib.lib()
+        dev = fields[0].data.device
+        self.flags = [torch.zeros(2 * _lib.OSSG_MAX_PEERS + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        torch.cuda.synchronize(dev)
+
+        def export(ptr):
+            h, off = _lib.IpcHandle(), C.c_uint64()
+            _lib.check(L.ossg_ipc_export(ptr, C.byref(h), C.byref(off)))
+            return bytes(h.bytes), int(off.value)
+
+        def open_(hb, off):
+            h, out = _lib.IpcHandle(), C.c_void_p()
+            C.memmove(h.bytes, hb, 64)
+            _lib.check(L.ossg_ipc_open(C.byref(h), off, C.byref(out)))
+            return out.value
+
+        mine = {"flags": [export(t.data_ptr()) for t in self.flags], "fields": [export(f.data.data_ptr()) for f in self.fields]}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        me = arch.local_rank
+        nb = {"north": arch.rank_of(arch.rx, arch.ry + 1) if arch.ry + 1 < arch.Ry else -1,
+              "south": arch.rank_of(arch.rx, arch.ry - 1) if arch.ry > 0 else -1,
+              "east": arch.rank_of((arch.rx + 1) % arch.Rx, arch.ry),
+              "west": arch.rank_of((arch.rx - 1) % arch.Rx, arch.ry)}
+        gN = self.fields[0].grid.global_size
+        self.descs = []
+        for phase in (0, 1):
+            hd = _lib.PeerHaloDesc()
+            hd.me, hd.nranks, hd.phase = me, world, phase
+            hd.north, hd.south, hd.east, hd.west = nb["north"], nb["south"], nb["east"], nb["west"]
+            hd.flags_local = self.flags[phase].data_ptr()
+            for r in set(v for v in nb.values() if v >= 0 and v != me):
+                hd.flags_peer[r] = open_(*gathered[r]["flags"][phase])
+            self.descs.append(hd)
+
+        def size_of(rank):
+            rx, ry = rank // arch.Ry, rank % arch.Ry
+            _, _, nx, ny = tile_of(gN[0], gN[1], arch.Rx, arch.Ry, rx, ry)
+            return nx, ny
+
+        B = _lib.OSSG_MAX_PEER_BATCH
+        self._launches = []
+        for b0 in range(0, len(self.fields), B):
+            chunk = list(range(b0, min(b0 + B, len(self.fields))))
+            arr = (_lib.PeerHaloField * len(chunk))()
+            for n, k in enumerate(chunk):
+                f = self.fields[k]
+                arr[n].f = f.descriptor()
+                for name in ("north", "south", "east", "west"):
+                    r = nb[name]
+                    ptr = None if r < 0 else (f.data.data_ptr() if r == me else open_(*gathered[r]["fields"][k]))
+                    setattr(arr[n], name, ptr)
+                arr[n].ny_north = size_of(nb["north"])[1] if nb["north"] >= 0 else 0
+                arr[n].ny_south = size_of(nb["south"])[1] if nb["south"] >= 0 else 0
+                arr[n].nx_east = size_of(nb["east"])[0]
+                arr[n].nx_west = size_of(nb["west"])[0]
+            self._launches.append((arr, len(chunk)))
+
+    def __call__(self, stream=None) -> None:
+        import ctypes as C
+        L = _lib.lib()
+        dev = self.fields[0].data.device
+        stream = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        self.fold(stream)
+        for phase in (0, 1):
+            for (arr, n) in self._launches:
+                self.epoch += 1
+                self.descs[phase].epoch = self.epoch
+                rc = L.ossg_halo_exchange_peer(arr, n, C.byref(self.descs[phase]), stream)
+                if rc:
+                    _lib.check(rc)
+
+    def timed_out(self) -> bool:
+        w = [int(t[2 * _lib.OSSG_MAX_PEERS].item()) >> 32 for t in self.flags]
+        return any(w) or (self.fold.active and self.fold.timed_out())
+
+
 def distributed_fill_halo_regions(fields: Sequence, stream=None, packer=None, group=None) -> None:
     """fill_halo_regions! for fields on a distributed tripolar grid: fold exchange on the top row
     (interior columns), then -- when x is not partitioned -- the local periodic west/east fill.

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import ossg_b200 as ossg                                    # noqa: E402
-from ossg_b200.distributed import (PeerFold, distributed_fill_halo_regions, fold_exchange,   # noqa: E402
+from ossg_b200.distributed import (PeerFold, PeerHalo, distributed_fill_halo_regions, fold_exchange,   # noqa: E402
                                    ordinary_halo_exchange, tile_of)
 from oracle import oracle as orc                            # noqa: E402
 
@@ -94,6 +94,27 @@ def check(world, rank, dev):
                 if peer.active and peer.timed_out():
                     failures.append(f"({Rx},{Ry}) rank {rank}: peer kernel timed out waiting for a partner")
                 dist.barrier()
+        # the whole fill (fold + south/north + west/east) over NVLink peer memory, two epochs
+        for f, p0 in zip(fields, pristine):
+            f.data.copy_(p0)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        phalo = PeerHalo(fields)
+        for rep in range(2):
+            if rep:
+                for f, p0 in zip(fields, pristine):
+                    f.data.copy_(p0)
+            phalo()
+            torch.cuda.synchronize(dev)
+            for f, want, (loc, code) in zip(fields, wants, specs):
+                a, b = f.data.cpu().numpy()[Hz:Hz + Nz], want[Hz:Hz + Nz]
+                same = (a == b) | (np.isnan(a) & np.isnan(b))
+                if not same.all():
+                    bad = np.argwhere(~same)[0]
+                    failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: PeerHalo fill (epoch {rep + 1}) differs at {bad.tolist()}")
+            if phalo.timed_out():
+                failures.append(f"({Rx},{Ry}) rank {rank}: PeerHalo kernel timed out waiting for a partner")
+            dist.barrier()
     return failures
 
 
