@@ -219,11 +219,20 @@ int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields, const ossg
 typedef struct ossg_peer_halo {
     int32_t me, nranks;                     /* rank id and world size (<= OSSG_MAX_PEERS)        */
     int32_t north, south, east, west;       /* neighbour rank ids                                */
-    int32_t phase;                          /* 0: south/north rows, 1: west/east columns         */
+    int32_t phase;                          /* 0: south/north rows, 1: west/east columns,
+                                               2: unpack of the staged west/east columns (local)  */
     int32_t reserved;
     void*   flags_local;                    /* flag block of THIS phase (2*OSSG_MAX_PEERS+1 uint64) */
     void*   flags_peer[OSSG_MAX_PEERS];     /* the same block on rank r, peer-mapped              */
     uint64_t epoch;
+    /* Optional staging of phase 1: a halo column is a 32-byte piece per row, the least efficient
+     * NVLink packet.  With staging, phase 1 stores the pieces CONTIGUOUSLY ([field][row][Hx]) into
+     * a buffer on the neighbour (full-size packets) and phase 2, a local kernel, scatters the
+     * received buffers into the halo columns.  NULL pointers select the direct form.            */
+    void*   stage_to_east;                  /* east neighbour's "from west" buffer, peer-mapped  */
+    void*   stage_to_west;                  /* west neighbour's "from east" buffer, peer-mapped  */
+    void*   stage_from_west;                /* this rank's buffers (phase 2 reads them)          */
+    void*   stage_from_east;
 } ossg_peer_halo;
 
 typedef struct ossg_peer_halo_field {

@@ -65,7 +65,9 @@ class PeerHaloDesc(C.Structure):
                 ("north", C.c_int32), ("south", C.c_int32), ("east", C.c_int32), ("west", C.c_int32),
                 ("phase", C.c_int32), ("reserved", C.c_int32),
                 ("flags_local", C.c_void_p), ("flags_peer", C.c_void_p * OSSG_MAX_PEERS),
-                ("epoch", C.c_uint64)]
+                ("epoch", C.c_uint64),
+                ("stage_to_east", C.c_void_p), ("stage_to_west", C.c_void_p),
+                ("stage_from_west", C.c_void_p), ("stage_from_east", C.c_void_p)]
 
 
 class PeerHaloField(C.Structure):

@@ -251,6 +251,30 @@ __device__ __forceinline__ void halo_rows_push(const ossg_peer_halo_field& h, lo
     peer[(size_t)lev * sxy_peer + (size_t)dst_row * sx + col] = static_cast<const T*>(f.data)[(size_t)lev * sxy + (size_t)src_row * sx + col];
 }
 
+// staged form of the column exchange: push = local strided read, contiguous remote write;
+// unpack (phase 2) = contiguous local read, strided local write
+template <typename T>
+__device__ __forceinline__ void halo_cols_stage(const ossg_peer_halo_field& h, const ossg_peer_halo& hd, int fi, long long item, int chunks, bool unpack)
+{
+    const ossg_field_desc& f = h.f;
+    const int chunk = (int)(item % chunks), side = (int)(item / chunks);   // push: side 0 -> east neighbour; unpack: side 0 = west halo
+    const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
+    const long long row = (long long)chunk * PB + threadIdx.x;
+    if (row >= rows) return;
+    const size_t piece = ((size_t)fi * rows + row) * f.Hx;
+    if (!unpack) {
+        T* stage = static_cast<T*>(side ? hd.stage_to_west : hd.stage_to_east);
+        if (!(side ? h.west : h.east)) return;
+        const T* src = static_cast<const T*>(f.data) + (size_t)row * (size_t)(f.Nx + 2 * f.Hx) + (side ? f.Hx : f.Nx);
+        copy_halo_piece(stage + piece, src, f.Hx);
+    } else {
+        const T* stage = static_cast<const T*>(side ? hd.stage_from_east : hd.stage_from_west);
+        if (!(side ? h.east : h.west)) return;
+        T* dst = static_cast<T*>(f.data) + (size_t)row * (size_t)(f.Nx + 2 * f.Hx) + (side ? f.Nx + f.Hx : 0);
+        copy_halo_piece(dst, stage + piece, f.Hx);
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void halo_cols_push(const ossg_peer_halo_field& h, long long item, int chunks)
 {
@@ -292,6 +316,9 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) halo_peer_kernel(const
         if (hd.phase == 0) {
             if (h.f.elem_type == OSSG_F64) halo_rows_push<double>(h, it, b.chunks);
             else halo_rows_push<float>(h, it, b.chunks);
+        } else if (hd.phase == 2 || hd.stage_to_east) {
+            if (h.f.elem_type == OSSG_F64) halo_cols_stage<double>(h, hd, fi, it, b.chunks, hd.phase == 2);
+            else halo_cols_stage<float>(h, hd, fi, it, b.chunks, hd.phase == 2);
         } else {
             if (h.f.elem_type == OSSG_F64) halo_cols_push<double>(h, it, b.chunks);
             else halo_cols_push<float>(h, it, b.chunks);
@@ -457,7 +484,11 @@ extern "C" int ossg_halo_exchange_peer(const ossg_peer_halo_field* fields, int n
     const ossg_peer_halo& hd = *halo;
     if (hd.nranks < 1 || hd.nranks > OSSG_MAX_PEERS || hd.me < 0 || hd.me >= hd.nranks)
         return set_error(OSSG_EINVAL, "bad rank layout: me = %d of %d (max %d)", hd.me, hd.nranks, OSSG_MAX_PEERS);
-    if (hd.phase != 0 && hd.phase != 1) return set_error(OSSG_EINVAL, "phase must be 0 (rows) or 1 (columns)");
+    if (hd.phase < 0 || hd.phase > 2) return set_error(OSSG_EINVAL, "phase must be 0 (rows), 1 (columns) or 2 (unpack staged columns)");
+    const bool staged = hd.stage_to_east || hd.stage_to_west || hd.stage_from_east || hd.stage_from_west;
+    if (staged && !(hd.stage_to_east && hd.stage_to_west && hd.stage_from_east && hd.stage_from_west))
+        return set_error(OSSG_EINVAL, "staging needs all four buffers");
+    if (hd.phase == 2 && !staged) return set_error(OSSG_EINVAL, "phase 2 needs the staging buffers");
     if (!hd.flags_local || reinterpret_cast<uintptr_t>(hd.flags_local) % 8) return set_error(OSSG_EALIGN, "flags_local must be an 8-byte aligned device pointer");
     if (hd.epoch == 0) return set_error(OSSG_EINVAL, "epoch must start at 1 and grow by one per call");
     const int nb[4] = { hd.north, hd.south, hd.east, hd.west };
@@ -465,7 +496,7 @@ extern "C" int ossg_halo_exchange_peer(const ossg_peer_halo_field* fields, int n
     b.halo = hd;
     b.n = nfields;
     b.partners = 0;
-    for (int k = (hd.phase ? 2 : 0); k < (hd.phase ? 4 : 2); ++k) {
+    for (int k = (hd.phase ? 2 : 0); k < (hd.phase ? 4 : 2) && hd.phase != 2; ++k) {
         if (nb[k] < -1 || nb[k] >= hd.nranks) return set_error(OSSG_EINVAL, "neighbour id %d out of range", nb[k]);
         if (nb[k] >= 0 && nb[k] != hd.me) {
             if (!hd.flags_peer[nb[k]]) return set_error(OSSG_EINVAL, "flags_peer[%d] is NULL", nb[k]);

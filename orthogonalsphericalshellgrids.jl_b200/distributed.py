@@ -382,7 +382,16 @@ class PeerHalo:
             _lib.check(L.ossg_ipc_open(C.byref(h), off, C.byref(out)))
             return out.value
 
-        mine = {"flags": [export(t.data_ptr()) for t in self.flags], "fields": [export(f.data.data_ptr()) for f in self.fields]}
+        # staging buffers of the column phase (x split only): [batch][from_west | from_east], 8 bytes per element
+        B = _lib.OSSG_MAX_PEER_BATCH
+        g0 = self.fields[0].grid
+        rows = (g0.Ny + 2 * g0.Hy) * (g0.Nz + 2 * g0.Hz)
+        nbatches = (len(self.fields) + B - 1) // B
+        self.staged = arch.Rx > 1
+        self.stage = [[torch.empty(min(B, len(self.fields) - b * B) * rows * g0.Hx, dtype=torch.float64, device=dev) for _ in range(2)]
+                      for b in range(nbatches)] if self.staged else []
+        mine = {"flags": [export(t.data_ptr()) for t in self.flags], "fields": [export(f.data.data_ptr()) for f in self.fields],
+                "stage": [[export(t.data_ptr()) for t in pair] for pair in self.stage]}
         gathered = [None] * world
         dist.all_gather_object(gathered, mine, group=group)
         me = arch.local_rank
@@ -392,21 +401,27 @@ class PeerHalo:
               "west": arch.rank_of((arch.rx - 1) % arch.Rx, arch.ry)}
         gN = self.fields[0].grid.global_size
         self.descs = []
-        for phase in (0, 1):
+        for phase in (0, 1, 2):
             hd = _lib.PeerHaloDesc()
             hd.me, hd.nranks, hd.phase = me, world, phase
             hd.north, hd.south, hd.east, hd.west = nb["north"], nb["south"], nb["east"], nb["west"]
-            hd.flags_local = self.flags[phase].data_ptr()
+            hd.flags_local = self.flags[min(phase, 1)].data_ptr()
             for r in set(v for v in nb.values() if v >= 0 and v != me):
-                hd.flags_peer[r] = open_(*gathered[r]["flags"][phase])
+                hd.flags_peer[r] = open_(*gathered[r]["flags"][min(phase, 1)])
             self.descs.append(hd)
+        # per batch: where this rank pushes (the neighbours' buffers) and what it unpacks (its own)
+        self.stage_ptrs = []
+        for b in range(nbatches if self.staged else 0):
+            self.stage_ptrs.append(dict(
+                to_east=open_(*gathered[nb["east"]]["stage"][b][0]),      # east neighbour's "from west" buffer
+                to_west=open_(*gathered[nb["west"]]["stage"][b][1]),      # west neighbour's "from east" buffer
+                from_west=self.stage[b][0].data_ptr(), from_east=self.stage[b][1].data_ptr()))
 
         def size_of(rank):
             rx, ry = rank // arch.Ry, rank % arch.Ry
             _, _, nx, ny = tile_of(gN[0], gN[1], arch.Rx, arch.Ry, rx, ry)
             return nx, ny
 
-        B = _lib.OSSG_MAX_PEER_BATCH
         self._launches = []
         for b0 in range(0, len(self.fields), B):
             chunk = list(range(b0, min(b0 + B, len(self.fields))))
@@ -430,11 +445,16 @@ class PeerHalo:
         dev = self.fields[0].data.device
         stream = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
         self.fold(stream)
-        for phase in (0, 1):
-            for (arr, n) in self._launches:
+        for phase in (0, 1, 2) if self.staged else (0, 1):
+            for b, (arr, n) in enumerate(self._launches):
+                hd = self.descs[phase]
                 self.epoch += 1
-                self.descs[phase].epoch = self.epoch
-                rc = L.ossg_halo_exchange_peer(arr, n, C.byref(self.descs[phase]), stream)
+                hd.epoch = self.epoch
+                if self.staged and phase > 0:
+                    sp = self.stage_ptrs[b]
+                    hd.stage_to_east, hd.stage_to_west = sp["to_east"], sp["to_west"]
+                    hd.stage_from_west, hd.stage_from_east = sp["from_west"], sp["from_east"]
+                rc = L.ossg_halo_exchange_peer(arr, n, C.byref(hd), stream)
                 if rc:
                     _lib.check(rc)
 
