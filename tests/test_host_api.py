@@ -33,12 +33,14 @@ def test_header_cites_the_reference_for_each_entry_point(ossg):
 def test_struct_layouts_match_the_header(ossg):
     # sizes the C compiler gives the structs in include/ossg_b200.h (checked by compiling a probe)
     import subprocess, tempfile, os
-    src = '#include "ossg_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(ossg_tripolar_params), sizeof(ossg_field_desc), sizeof(ossg_fold_window));return 0;}'
+    src = '#include "ossg_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ossg_tripolar_params), sizeof(ossg_field_desc), sizeof(ossg_fold_window), sizeof(ossg_ipc_handle), sizeof(ossg_peer_fold), sizeof(ossg_peer_field), sizeof(ossg_peer_halo), sizeof(ossg_peer_halo_field));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.dirname(ossg._lib.HEADER_PATH), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")], check=True)
         out = subprocess.run([os.path.join(d, "p")], capture_output=True, text=True).stdout.split()
-    assert [int(x) for x in out] == [C.sizeof(ossg._lib.TripolarParams), C.sizeof(ossg._lib.FieldDesc), C.sizeof(ossg._lib.FoldWindow)]
+    L_ = ossg._lib
+    assert [int(x) for x in out] == [C.sizeof(t) for t in (L_.TripolarParams, L_.FieldDesc, L_.FoldWindow, L_.IpcHandle, L_.PeerFoldDesc,
+                                                           L_.PeerField, L_.PeerHaloDesc, L_.PeerHaloField)]
 
 
 def test_argument_errors_do_not_need_a_device(ossg):
