@@ -279,9 +279,15 @@ def run_own(args):
     if world == 1:
         zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny)
     else:
-        zipper = {"fold_exchange": bench_fold_exchange(world, rank, dev)}
-        torch.cuda.empty_cache()
-        zipper["distributed_fill_halo_regions"] = bench_distributed_fill(world, rank, dev)
+        # (a failure of the peer-memory plumbing -- e.g. CUDA IPC unavailable in the container -- must not
+        # take the construction number down with it)
+        zipper = {}
+        for key, fn in (("fold_exchange", bench_fold_exchange), ("distributed_fill_halo_regions", bench_distributed_fill)):
+            try:
+                zipper[key] = fn(world, rank, dev)
+            except Exception as e:          # noqa: BLE001
+                zipper[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
 
     # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels)
     ms = C.c_float(); fl = C.c_double()
