@@ -183,7 +183,7 @@ def run_own(args):
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no "NCCL version" banner)
+    # (NCCL_DEBUG is left as the environment has it: unset, NCCL prints nothing and stdout is the one JSON line)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
