@@ -395,6 +395,21 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
         res[name] = {"ms": ms, "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9}
     res["fill_halo_regions_batch4"]["what"] = ("zipper north fill + periodic west/east fill of c,u,v,zeta in ONE launch "
                                                "(fill_fused_kernel); the periodic part moves 32-byte pieces, one DRAM sector each way")
+    # repeated fill_halo_regions! on the same fields, back to back, no flush (SURVEY 8d "repeated fill"):
+    # the 117 MB the zipper touches stay resident in the 126 MB L2, the loop is launch/latency bound
+    for name, fn, b in (("repeat200_zipper_batch4_no_flush", L.ossg_zipper_fill_batch, algo),
+                        ("repeat200_fill_halo_regions_batch4_no_flush", L.ossg_fill_halo_regions_batch, algo_full)):
+        for _ in range(5):
+            _lib.check(fn(descs, 4, stream.cuda_stream))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(200):
+            _lib.check(fn(descs, 4, stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 200
+        res[name] = {"ms": ms, "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9}
     res["config"] = f"{nx}x{ny}x{Nz} FP64 fields c,u,v,zeta, Hy=4, L2 flushed (256 MB write) before each timed fill"
     del fields
     return res
