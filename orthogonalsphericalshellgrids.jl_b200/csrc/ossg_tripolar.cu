@@ -135,6 +135,9 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
     }
 }
 
+#ifndef OSSG_COORD_ILP
+#define OSSG_COORD_ILP 1
+#endif
 // 1-D grid of coords_pair_kernel: the pair rows (J = 1..Ny-1) need Nx/2 + 1 + 2Hx threads, the other
 // rows one thread per padded element; a 2-D grid sized for the latter would launch an empty
 // second half for every pair row.
@@ -156,8 +159,8 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
             jw = r < pg.jw_lo ? r : r + pg.n_pair_rows;
         }
     }
-    __shared__ double s_atan[24];                            // atan reduction table (ossg_math.cuh)
-    if (threadIdx.x < 24) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
+    __shared__ double s_atan[30];                            // atan reduction table (ossg_math.cuh)
+    if (threadIdx.x < 30) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
     __syncthreads();
     const int t = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
@@ -175,32 +178,44 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
             const double chF = __ldg(tb.chF + J - 1), shF = __ldg(tb.shF + J - 1);
             const double chC = __ldg(tb.chC + J - 1), shC = __ldg(tb.shC + J - 1);
             const size_t o = row + (size_t)(i + Hx - 1);
-            {   // x-Face: ip <-> Nx+2-ip ; ip = 1 and ip = Nx/2+1 are their own mirrors
-                const double as = __ldg(tb.asF + i - 1), ac = __ldg(tb.acF + i - 1);
-                const int ipm = Nx + 2 - ip;
-                const bool has_mirror = (t != 0) && (t != half);
-                int im = ipm + shift; if (im > Nx) im -= Nx;
-                const size_t om = row + (size_t)(im + Hx - 1);
+            // x-Face: ip <-> Nx+2-ip (ip = 1 and ip = Nx/2+1 are their own mirrors); x-Center: ip <-> Nx+1-ip
+            const int ipmF = Nx + 2 - ip, ipmC = Nx + 1 - ip;
+            const bool mirrorF = (t != 0) && (t != half), pairC = t < half;
+            int imF = ipmF + shift; if (imF > Nx) imF -= Nx;
+            int imC = ipmC + shift; if (imC > Nx) imC -= Nx;
+            const size_t omF = row + (size_t)(imF + Hx - 1), omC = row + (size_t)(imC + Hx - 1);
+            const double asF = __ldg(tb.asF + i - 1), acF = __ldg(tb.acF + i - 1);
+            const double asC = __ldg(tb.asC + i - 1), acC = __ldg(tb.acC + i - 1);
+            const double fpl90 = fpl + 90.0;
+            // Speculative straight-line evaluation, OSSG_COORD_ILP staggerings per basic block (table-
+            // driven branch-free atan, div_nb, sqrt_nb): ptxas interleaves the independent chains.  A
+            // point that leaves the preconditions sets `bad`; the thread then redoes its four points
+            // through the general functions and overwrites the speculative stores.
+            bool bad = false;
 #pragma unroll 1
-                for (int fy = 0; fy < 2; ++fy) {                // fy = 0: FC (y-Center), 1: FF
-                    const PointCore c = tripolar_core_lut(as, ac, fy ? chF : chC, fy ? shF : shC, s_atan);
-                    const int loc = fy ? FF : FC;
-                    store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
-                    if (has_mirror)
-                        store_coord<FT>(a, loc, om, tripolar_finish(-c.lam_a, c.pole, false, ipm <= half, fpl), c.phi);
+            for (int k0 = 0; k0 < 4; k0 += OSSG_COORD_ILP) {
+#pragma unroll
+                for (int kk = 0; kk < OSSG_COORD_ILP; ++kk) {           // k = 0: FC, 1: FF, 2: CC, 3: CF
+                    const int k = k0 + kk;
+                    const bool fx = k < 2, fy = k & 1;
+                    const PointCore c = tripolar_core_sl(fx ? asF : asC, fx ? acF : acC, fy ? chF : chC, fy ? shF : shC, s_atan, bad);
+                    const int loc = fx ? (fy ? FF : FC) : (fy ? CF : CC);
+                    if (fx || pairC) store_coord<FT>(a, loc, o, tripolar_finish_sl(c.lam_a, ip <= half, fpl90, bad), c.phi);
+                    if (fx ? mirrorF : pairC)
+                        store_coord<FT>(a, loc, fx ? omF : omC, tripolar_finish_sl(-c.lam_a, (fx ? ipmF : ipmC) <= half, fpl90, bad), c.phi);
                 }
             }
-            if (t < half) {   // x-Center: ip <-> Nx+1-ip, never self-paired
-                const double as = __ldg(tb.asC + i - 1), ac = __ldg(tb.acC + i - 1);
-                const int ipm = Nx + 1 - ip;
-                int im = ipm + shift; if (im > Nx) im -= Nx;
-                const size_t om = row + (size_t)(im + Hx - 1);
+            if (bad) {
 #pragma unroll 1
-                for (int fy = 0; fy < 2; ++fy) {                // fy = 0: CC, 1: CF
-                    const PointCore c = tripolar_core_lut(as, ac, fy ? chF : chC, fy ? shF : shC, s_atan);
-                    const int loc = fy ? CF : CC;
+                for (int k = 0; k < 4; ++k) {
+                    const bool fx = k < 2, fy = k & 1;
+                    if (!fx && !pairC) break;
+                    const PointCore c = tripolar_core_lut(fx ? asF : asC, fx ? acF : acC, fy ? chF : chC, fy ? shF : shC, s_atan);
+                    const int loc = fx ? (fy ? FF : FC) : (fy ? CF : CC);
                     store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
-                    store_coord<FT>(a, loc, om, tripolar_finish(-c.lam_a, c.pole, false, ipm <= half, fpl), c.phi);
+                    if (fx ? mirrorF : pairC)
+                        store_coord<FT>(a, loc, fx ? omF : omC,
+                                        tripolar_finish(-c.lam_a, c.pole, false, (fx ? ipmF : ipmC) <= half, fpl), c.phi);
                 }
             }
         } else if (t <= half + 2 * Hx) {

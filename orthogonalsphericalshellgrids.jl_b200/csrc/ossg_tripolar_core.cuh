@@ -149,6 +149,33 @@ OSSG_HD PointCore tripolar_core_lut(double as_i, double ac_i, double ch_j, doubl
     return c;
 }
 
+// Speculative straight-line forms (no branch): the same bits as tripolar_core / tripolar_finish
+// whenever `bad` stays false; a bad point (x or y zero or tiny: pole row, pole meridians;
+// reduction-boundary arguments; |lambda| >= 360 before the wrap) is recomputed by the caller
+// through the general functions.
+OSSG_HD PointCore tripolar_core_sl(double as_i, double ac_i, double ch_j, double sh_j, const double* atan_table, bool& bad)
+{
+    const double x = as_i * ch_j;                                             // :67
+    const double y = ac_i * sh_j;                                             // :68
+    constexpr double m180_pi = -180.0 / m::PI_F64;
+    constexpr double p360_pi = 360.0 / m::PI_F64;
+    PointCore c;
+    c.pole = false;                                                           // x = y = 0 is a bad point
+    bad |= (m::hi_abs(y) < m::DIV_NB_MIN_HI) | (m::hi_abs(x) - 0x39B00000u >= 0x0C800000u);   // |y| >= 2^-969, 2^-100 <= |x| < 2^100
+    c.lam_a = m180_pi * m::atan_sl(m::div_nb(y, x), atan_table, bad);         // :77
+    const double rho2 = y * y + x * x;                                        // (>= 2^-200 here)
+    c.phi = 90.0 - p360_pi * m::atan_sl(m::sqrt_nb(rho2), atan_table, bad);   // :78
+    return c;
+}
+OSSG_HD double tripolar_finish_sl(double lam_a, bool ip_le_half, double fpl90, bool& bad)
+{
+    double l = lam_a + (ip_le_half ? -90.0 : 90.0);                           // :82 (not a pole: :77 took lam_a)
+    l += fpl90;                                                               // :86, fpl90 = first_pole_longitude + 90
+    bad |= !(fabs(l) < 360.0);                                                // then fmod(l, 360) == l and l + 360 < 720
+    const double r = l + 360.0;
+    return (r < 360.0) ? r : (r - 360.0);
+}
+
 // tail of the point: pole value (:75-77), hemisphere shift (:82), pole-longitude shift (:86), wrap (:87)
 OSSG_HD double tripolar_finish(double lam_a, bool pole, bool ip_is_one, bool ip_le_half, double first_pole_longitude)
 {

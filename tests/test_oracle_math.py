@@ -177,5 +177,6 @@ def test_table_driven_atan_is_bit_identical(mirror, oracle):
                          b, -b, np.nextafter(b, np.inf), np.nextafter(b, -np.inf), [0.0, -0.0, np.inf, -np.inf, np.nan, 1e300]])
     a = hm.math(mirror, 20, xs)
     assert np.array_equal(a.view(np.uint64), hm.math(mirror, orc.MATH_FN["atan"], xs).view(np.uint64))
+    assert np.array_equal(hm.math(mirror, 21, xs).view(np.uint64), a.view(np.uint64))      # straight-line form + its fallback
     fin = ~np.isnan(xs)
     assert np.array_equal(a[fin].view(np.uint64), oracle.math("atan", xs[fin]).view(np.uint64))
