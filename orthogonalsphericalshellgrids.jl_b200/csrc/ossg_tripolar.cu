@@ -10,6 +10,9 @@
 //   K2f metrics_frame_kernel  the halo frame (north fold image, x halos, fold row Ny, south
 //                           continuation rows): each element evaluated at its source
 // Compile with -fmad=false: see ossg_math.cuh for the determinism contract.
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "ossg_common.cuh"
@@ -251,11 +254,49 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
 // only -- deg2rad(phi), cos(deg2rad(phi)) for the haversines and, for CC and FF, the unit vector
 // of lat_lon_to_cartesian -- so that the four (resp. up to six) cells sharing a point do not
 // repeat its trigonometry.
+#ifndef OSSG_USE_TMA
+#define OSSG_USE_TMA 0
+#endif
 constexpr int TX = 32, TY = 8, NT = TX * TY;
-constexpr int QX = TX + 1, QY = TY + 1, QPTS = QX * QY;
+constexpr int QY = TY + 1;
+// Patch geometry.  cp.async staging: (TX+1) x QY points, dense.  TMA staging: the box is (TX+2) x QY
+// (the inner box extent must be a multiple of 16 bytes; the extra column is fetched and ignored) and
+// every patch starts on a 128-byte boundary (TMA destination alignment): stride 320 doubles.
+template <bool TMA> struct TileGeom {
+    static constexpr int QX = TMA ? TX + 2 : TX + 1;
+    static constexpr int QPTS = QX * QY;                 // logical points of a patch (TMA: incl. the pad column)
+    static constexpr int PS = TMA ? 320 : QPTS;          // patch stride in shared memory, doubles
+    static constexpr size_t SMEM_BYTES = (size_t)18 * PS * sizeof(double) + (TMA ? 128 : 0);
+};
 // shared arrays: lam, phr, cosphi per staggering (12) + unit vectors of CC and FF (6)
-constexpr int N_SMEM_ARRAYS = 18;
-constexpr size_t TILE_SMEM_BYTES = (size_t)N_SMEM_ARRAYS * QPTS * sizeof(double);
+struct TileMaps { CUtensorMap m[8]; };                  // lam cc,fc,cf,ff, phi cc,fc,cf,ff of the window (TMA staging)
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(phase) : "memory");
+        if (!done && clock64() - t0 > 2000000000ll) __trap();        // a lost TMA transaction must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(x), "r"(y) : "memory");
+}
 
 struct FastRect { int I0, J0, nx, ny; };   // global indices of the first fast cell, extents
 
@@ -279,21 +320,46 @@ __device__ __forceinline__ void store_metric(const BuildArgs& a, int id, size_t 
     static_cast<FT*>(a.metrics_out[id])[o] = (FT)v;
 }
 
-template <typename FT>
-__global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
+template <typename FT, bool TMA>
+__global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
+                                                             const __grid_constant__ TileMaps tm)
 {
-    extern __shared__ __align__(16) double smem[];
-    double* s_lam = smem;                     // [4][QPTS]  lambda (degrees)
-    double* s_phr = smem + 4 * QPTS;          // [4][QPTS]  phi (degrees) during staging, then deg2rad(phi)/2
-    double* s_cos = smem + 8 * QPTS;          // [4][QPTS]  cos(deg2rad(phi))
-    double* s_ux = smem + 12 * QPTS;          // [2][QPTS]  unit vectors: slot 0 = CC, slot 1 = FF
-    double* s_uy = smem + 14 * QPTS;
-    double* s_uz = smem + 16 * QPTS;
+    constexpr int QX = TileGeom<TMA>::QX, QPTS = TileGeom<TMA>::QPTS, PS = TileGeom<TMA>::PS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(TMA ? (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127
+                                                 : reinterpret_cast<uintptr_t>(smem_raw));
+    double* s_lam = smem;                     // [4][PS]  lambda (degrees)
+    double* s_phr = smem + 4 * PS;            // [4][PS]  phi (degrees) during staging, then deg2rad(phi)/2
+    double* s_cos = smem + 8 * PS;            // [4][PS]  cos(deg2rad(phi))
+    double* s_ux = smem + 12 * PS;            // [2][PS]  unit vectors: slot 0 = CC, slot 1 = FF
+    double* s_uy = smem + 14 * PS;
+    double* s_uz = smem + 16 * PS;
 
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
     const Window w = a.w;
 
+    if (TMA) {
+        // ---- stage the four coordinate patches with the Tensor Memory Accelerator: one thread issues
+        // eight 2-D box loads ((TX+2) x QY doubles each, zero-filled outside the window) that complete
+        // on an mbarrier; no address arithmetic, no load instructions in the other 255 threads.
+        __shared__ __align__(8) unsigned long long s_bar;
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, 8u * QPTS * (unsigned)sizeof(double));
+#pragma unroll
+            for (int loc = 0; loc < 4; ++loc) {
+                // the box must start on a 16-byte boundary of the row (measured: an odd FP64 column
+                // raises an illegal-instruction fault): start at the even column at or below the
+                // patch; the (TX+2)-wide box still covers the TX+1 columns the patch needs
+                const int x0 = (It0 + patch_di(loc) - w.I0) & ~1, y0 = Jt0 + patch_dj(loc) - w.J0;
+                tma_load_2d(&s_lam[loc * PS], &tm.m[loc], x0, y0, &s_bar);
+                tma_load_2d(&s_phr[loc * PS], &tm.m[4 + loc], x0, y0, &s_bar);
+            }
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
     // ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers.
     // Thread (tx, ty) copies patch point (tx, ty) of all four patches (one offset computation, the
     // staggering shifts are constants); the first QY + TX threads then copy column TX and row TY.
@@ -308,11 +374,11 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
                 const int i2 = iw + di, j2 = jw + dj;
                 if (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny) {
                     const long long o2 = o + (long long)dj * w.wnx + di;
-                    cp_async_8(&s_lam[loc * QPTS + p], a.coords64[loc] + o2);
-                    cp_async_8(&s_phr[loc * QPTS + p], a.coords64[4 + loc] + o2);
+                    cp_async_8(&s_lam[loc * PS + p], a.coords64[loc] + o2);
+                    cp_async_8(&s_phr[loc * PS + p], a.coords64[4 + loc] + o2);
                 } else {
-                    s_lam[loc * QPTS + p] = 0.0;
-                    s_phr[loc * QPTS + p] = 0.0;
+                    s_lam[loc * PS + p] = 0.0;
+                    s_phr[loc * PS + p] = 0.0;
                 }
             }
         };
@@ -322,6 +388,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     }
     cp_async_wait_all();
     __syncthreads();
+    }
 
     // ---- point stage: everything that depends on one point only, once per patch point, in ONE
     // pass (every task reads and writes its own point only):
@@ -338,14 +405,15 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
         for (int h = warp; h < HC; h += NW) {
             const int u = h * 32 + lane;                  // index into the unit-vector arrays
             if (u < 2 * QPTS) {
-                const int t = u < QPTS ? u : u + 2 * QPTS;    // CC patch, then FF patch
+                const int t = u < QPTS ? u : u - QPTS + 3 * PS;   // CC patch, then FF patch
                 const double lat = s_phr[t], lon = s_lam[t];
                 bool bad = false;
                 Vec3 v = lat_lon_to_cartesian_spec(lat, lon, bad);
                 if (bad) v = lat_lon_to_cartesian_ool(lat, lon);
-                s_ux[u] = v.x;
-                s_uy[u] = v.y;
-                s_uz[u] = v.z;
+                const int us = u < QPTS ? u : u - QPTS + PS;
+                s_ux[us] = v.x;
+                s_uy[us] = v.y;
+                s_uz[us] = v.z;
                 const double phr = lat * D2R;
                 s_phr[t] = 0.5 * phr;                     // the haversines want deg2rad(phi)/2
                 s_cos[t] = m::cos_rad_inl(phr);
@@ -354,8 +422,9 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
         if (W0 == 0 || warp >= W0) {
 #pragma unroll 1
             for (int l = (W0 == 0 ? warp : warp - W0); l < LC; l += NLW) {
-                const int t = QPTS + l * 32 + lane;       // FC patch, then CF patch
-                if (t < 3 * QPTS) {
+                const int v = l * 32 + lane;              // FC patch, then CF patch
+                const int t = v < QPTS ? PS + v : 2 * PS + (v - QPTS);
+                if (v < 2 * QPTS) {
                     const double phr = s_phr[t] * D2R;
                     s_phr[t] = 0.5 * phr;
                     s_cos[t] = m::cos_rad_inl(phr);
@@ -371,7 +440,10 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     const int tx = threadIdx.x, ty = threadIdx.y;
     const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
     // patch index of this cell's own point per staggering (index = loc)
-    const int own_cc = (ty + 1) * QX + tx + 1, own_fc = (ty + 1) * QX + tx, own_cf = ty * QX + tx + 1, own_ff = ty * QX + tx;
+    // (TMA staging: a patch whose first column is odd sits one column to the right in its box)
+    const int shC = TMA ? ((It0 - 1 - w.I0) & 1) : 0, shF = TMA ? ((It0 - w.I0) & 1) : 0;
+    const int own_cc = (ty + 1) * QX + tx + 1 + shC, own_fc = (ty + 1) * QX + tx + shF;
+    const int own_cf = ty * QX + tx + 1 + shC, own_ff = ty * QX + tx + shF;
 
     // ---- cell stage, speculative straight-line form: the 8 haversines and 2 quadrilaterals are
     // evaluated through their hot sequences in ONE basic block (branch-free sqrt / division, short
@@ -381,7 +453,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
     // overwritten by the same thread.
     const double R2 = 2 * R, RR = R * R;
     bool bad = false;
-#define PT(L, p) s_lam[(L) * QPTS + (p)], s_phr[(L) * QPTS + (p)], s_cos[(L) * QPTS + (p)]
+#define PT(L, p) s_lam[(L) * PS + (p)], s_phr[(L) * PS + (p)], s_cos[(L) * PS + (p)]
     {
         const double dx_fc = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - 1), R2, bad);        // utils.jl:14
         const double dy_fc = haversine_spec(PT(FF, own_ff + QX), PT(FF, own_ff), R2, bad);       // :19
@@ -398,7 +470,7 @@ __global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_consta
         store_metric<FT>(a, DX_FF, o, haversine_spec(PT(CF, own_cf), PT(CF, own_cf - 1), R2, bad));    // :16
         store_metric<FT>(a, DX_CC, o, haversine_spec(PT(FC, own_fc + 1), PT(FC, own_fc), R2, bad));    // :13
     }
-#define UV(q, p) Vec3{ s_ux[(q) * QPTS + (p)], s_uy[(q) * QPTS + (p)], s_uz[(q) * QPTS + (p)] }
+#define UV(q, p) Vec3{ s_ux[(q) * PS + (p)], s_uy[(q) * PS + (p)], s_uz[(q) * PS + (p)] }
     {   // az_ff from CC[i-1,j-1], CC[i,j-1], CC[i,j], CC[i-1,j] (:38-43); az_cc from FF[i,j], FF[i+1,j], FF[i+1,j+1], FF[i,j+1] (:23-28)
         const int b0 = own_cc - QX - 1, b1 = own_ff;
         store_metric<FT>(a, AZ_FF, o, spherical_area_quadrilateral_spec(UV(0, b0), UV(0, b0 + 1), UV(0, b0 + QX + 1), UV(0, b0 + QX), bad) * RR);
@@ -585,6 +657,46 @@ static int side_stream(cudaStream_t* out)
     return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_tiled_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(sym);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor maps of the eight FP64 coordinate arrays of the window, box (TX+2) x QY.  Returns false
+// when TMA cannot describe them (odd row pitch -> stride not a multiple of 16 bytes, unaligned
+// base, no driver entry point); the caller then uses the cp.async staging.
+static bool make_tile_maps(const BuildArgs& a, TileMaps& tm)
+{
+    PFN_encodeTiled enc = encode_tiled_fn();
+    if (!enc || (a.w.wnx & 1) || a.w.wnx < TileGeom<true>::QX || a.w.wny < QY) return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)a.w.wnx, (cuuint64_t)a.w.wny };
+    const cuuint64_t strides[1] = { (cuuint64_t)a.w.wnx * sizeof(double) };
+    const cuuint32_t box[2] = { (cuuint32_t)TileGeom<true>::QX, (cuuint32_t)QY };
+    const cuuint32_t estr[2] = { 1, 1 };
+    for (int k = 0; k < 8; ++k) {
+        if (reinterpret_cast<uintptr_t>(a.coords64[k]) & 15) return false;
+        if (enc(&tm.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, a.coords64[k], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 template <typename FT>
 static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, cudaEvent_t between = nullptr)
 {
@@ -619,11 +731,25 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         static bool attr_set[2] = { false, false };
         const int which = sizeof(FT) == 4;
         if (!attr_set[which]) {
-            OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
+            OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<false>::SMEM_BYTES));
+            OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<true>::SMEM_BYTES));
             attr_set[which] = true;
         }
         dim3 block(TX, TY), grid(ceil_div(fr.nx, TX), ceil_div(fr.ny, TY));
-        metrics_tile_kernel<FT><<<grid, block, TILE_SMEM_BYTES, s>>>(a, fr);
+        TileMaps tm;
+        // Staging of the coordinate patches: cp.async by default.  The TMA form (eight 2-D box loads
+        // issued by one thread) is complete and parity-tested but measured 3 % slower on the 1/12
+        // degree grid (0.650 vs 0.631 ms: 3 % more patch points because of the 16-byte box
+        // alignment, and the patch arrives later than 256 threads' own loads), so it is opt-in:
+        // OSSG_TILE_STAGING=tma.
+        const char* staging = getenv("OSSG_TILE_STAGING");
+        const bool want_tma = OSSG_USE_TMA || (staging && strcmp(staging, "tma") == 0);
+        if (want_tma && make_tile_maps(a, tm)) {
+            metrics_tile_kernel<FT, true><<<grid, block, TileGeom<true>::SMEM_BYTES, s>>>(a, fr, tm);
+        } else {
+            memset(&tm, 0, sizeof(tm));
+            metrics_tile_kernel<FT, false><<<grid, block, TileGeom<false>::SMEM_BYTES, s>>>(a, fr, tm);
+        }
         OSSG_LAUNCH_CHECK("metrics_tile_kernel");
     }
     if (between) OSSG_CUDA_TRY(cudaEventRecord(between, s));

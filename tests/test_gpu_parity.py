@@ -15,6 +15,9 @@ import torch
 
 from oracle import oracle as orc
 
+import os as _os
+ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-12          # north_star tolerance, Float64
@@ -424,6 +427,35 @@ def test_abi_argument_errors(ossg):
     assert L.ossg_tripolar_build(C.byref(p), 0, out, 16, 1 << 20, None) == ossg._lib.OSSG_EHALO
     with pytest.raises(ValueError, match="should be even"):
         ossg.TripolarGrid(size=(61, 30, 1))
+
+
+def test_tma_staging_of_the_tile_kernel_matches_oracle():
+    """The opt-in TMA staging of metrics_tile_kernel (OSSG_TILE_STAGING=tma, UTMALDG box loads on an
+    mbarrier) in a fresh process: FP64 and FP32 grids and a tile window, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+import ossg_b200 as ossg
+from oracle import oracle as orc
+from ossg_b200.grids import build_arrays, make_params
+o = orc.Oracle(); o.set_threads(o.max_threads())
+for size, dt, npdt in (((360, 180, 1), ossg.Float64, np.float64), ((1440, 720, 1), ossg.Float64, np.float64), ((360, 180, 1), ossg.Float32, np.float32)):
+    g = ossg.TripolarGrid(ossg.GPU(), dt, size=size)
+    ref = o.build(orc.make_params(size, (4, 4, 4)), dtype=npdt)
+    for n in orc.ALL_NAMES:
+        assert np.array_equal(g.arrays[n].parent.cpu().numpy().view(np.uint8), ref[n].view(np.uint8)), (size, n)
+ref = o.build(orc.make_params((1440, 720, 1), (4, 4, 4)))
+p = make_params((1440, 720, 1), (4, 4, 4), -80, 55, 70, orc.R_EARTH, tile=(1, 361, 1440, 360))
+for n, t in zip(orc.ALL_NAMES, build_arrays(p, torch.float64, torch.device('cuda', 0))):
+    assert np.array_equal(t.cpu().numpy().view(np.uint8), np.ascontiguousarray(ref[n][360:360 + 368, :]).view(np.uint8)), n
+print('tma ok')
+""" % (ROOT, ROOT)
+    env = dict(os.environ, OSSG_TILE_STAGING="tma")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "tma ok" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
 
 
 def test_branch_free_sqrt_div_match_ieee(ossg):
