@@ -115,6 +115,21 @@ def check(world, rank, dev):
             if phalo.timed_out():
                 failures.append(f"({Rx},{Ry}) rank {rank}: PeerHalo kernel timed out waiting for a partner")
             dist.barrier()
+        # Float32 fields through the same kernels (4-byte elements: the 16-byte vector pieces and their
+        # unaligned scalar fallback), against the FP64 reference rounded once (the fill is a copy with a sign)
+        f32 = [ossg.Field(f.loc, grid, data=p0.to(torch.float32)) for f, p0 in zip(fields, pristine)]
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        phalo32 = PeerHalo(f32)
+        phalo32()
+        torch.cuda.synchronize(dev)
+        for f, want, (loc, code) in zip(f32, wants, specs):
+            a, b = f.data.cpu().numpy()[Hz:Hz + Nz], want[Hz:Hz + Nz].astype(np.float32)
+            same = (a == b) | (np.isnan(a) & np.isnan(b))
+            if not same.all():
+                bad = np.argwhere(~same)[0]
+                failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: Float32 PeerHalo fill differs at {bad.tolist()}")
+        dist.barrier()
     return failures
 
 
