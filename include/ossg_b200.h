@@ -118,6 +118,16 @@ int ossg_tripolar_metrics(const ossg_tripolar_params* p, const void* const coord
                           int metrics_type, void* const metrics[12],
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Cartesian nodes --------------------------------------------------------------------- *
+ * (external) Oceananigans.Grids.lat_lon_to_cartesian(lat, lon, radius) over n nodes, the kernel of
+ * get_cartesian_nodes_and_vertices as used by test/test_tripolar_grid.jl:68 and
+ * examples/visualize_tripolar_grid.jl:39-42:
+ *     x = radius cosd(lon) cosd(lat),  y = radius sind(lon) cosd(lat),  z = radius sind(lat)
+ * lam/phi are FP64 coordinate arrays (any staggering, any layout: n contiguous elements);
+ * x, y, z are arrays of out_type.                                                               */
+int ossg_cartesian_nodes(const void* lam, const void* phi, size_t n, double radius, int out_type,
+                         void* x, void* y, void* z, void* stream);
+
 /* ---- Zipper boundary condition ------------------------------------------------------------- *
  * Replaces the per-thread bodies fold_north_{center_center,face_center,center_face,face_face}!
  * (src/zipper_boundary_condition.jl:70-138) as dispatched by _fill_north_halo! (:146-155), for

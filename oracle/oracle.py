@@ -154,6 +154,16 @@ class Oracle:
         self.zipper(c, Nx, Ny, Nz, Hx, Hy, Hz, locx, locy, sign)
         return self.periodic_x(c, Nx, Ny, Nz, Hx, Hy, Hz)
 
+    def cartesian_nodes(self, lam, phi, radius=1.0):
+        """(external) Oceananigans.Grids.lat_lon_to_cartesian over arrays of nodes."""
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        out = [np.empty_like(lam) for _ in range(3)]
+        self.lib.ossg_oracle_cartesian_nodes.restype = None
+        self.lib.ossg_oracle_cartesian_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.ossg_oracle_cartesian_nodes(lam.ctypes.data, phi.ctypes.data, lam.size, float(radius), *[o.ctypes.data for o in out])
+        return out
+
     def math(self, name: str, x) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)

@@ -514,6 +514,18 @@ void ossg_oracle_set_threads(int n)
     g_threads = n > 0 ? n : 1;
 }
 
+/* (external) Oceananigans.Grids.lat_lon_to_cartesian(lat, lon, radius) over n nodes
+ * (test/test_tripolar_grid.jl:68, examples/visualize_tripolar_grid.jl:39-42) */
+void ossg_oracle_cartesian_nodes(const double *lam, const double *phi, size_t n, double radius,
+                                 double *x, double *y, double *z)
+{
+    for (size_t e = 0; e < n; ++e) {
+        x[e] = radius * om_cosd(lam[e]) * om_cosd(phi[e]);
+        y[e] = radius * om_sind(lam[e]) * om_cosd(phi[e]);
+        z[e] = radius * om_sind(phi[e]);
+    }
+}
+
 /* evaluate one elementary function over an array (tests compare with mpmath / glibc) */
 int ossg_oracle_math_eval(int fn, const double *x, double *y, size_t n)
 {

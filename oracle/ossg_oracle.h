@@ -38,6 +38,8 @@ int  ossg_oracle_uses_libm(void);
 int  ossg_oracle_max_threads(void);
 void ossg_oracle_set_threads(int n);
 int  ossg_oracle_math_eval(int fn, const double *x, double *y, size_t n);
+void ossg_oracle_cartesian_nodes(const double *lam, const double *phi, size_t n, double radius,
+                                 double *x, double *y, double *z);
 
 #ifdef __cplusplus
 }

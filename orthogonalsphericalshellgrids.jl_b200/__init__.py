@@ -5,7 +5,7 @@ The reference exports two names, TripolarGrid and ZipperBoundaryCondition
 (src/OrthogonalSphericalShellGrids.jl:4); the rest of this namespace mirrors the Oceananigans
 generics the reference extends for the path."""
 from ._lib import OSSGError, build as build_library, lib as load_library
-from .grids import (CPU, GPU, Center, Face, Float32, Float64, OffsetArray, OrthogonalSphericalShellGrid,
+from .grids import (cartesian_nodes, CPU, GPU, Center, Face, Float32, Float64, OffsetArray, OrthogonalSphericalShellGrid,
                     R_Earth, Tripolar, TripolarGrid, with_halo, x_domain, y_domain)
 from .fields import (BoundaryCondition, CenterField, Field, FieldBoundaryConditions, PeriodicBoundaryCondition,
                      XFaceField, YFaceField, ZFaceField, Zipper, ZipperBoundaryCondition, bc_str,

@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
     L.ossg_tripolar_build_profiled.argtypes = [C.POINTER(TripolarParams), C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
     L.ossg_tripolar_coords.argtypes = [C.POINTER(TripolarParams), vpp, C.c_void_p, C.c_size_t, C.c_void_p]
     L.ossg_tripolar_metrics.argtypes = [C.POINTER(TripolarParams), vpp, C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.ossg_cartesian_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ossg_zipper_fill.argtypes = [C.POINTER(FieldDesc), C.c_void_p]
     L.ossg_zipper_fill_batch.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_void_p]
     L.ossg_fill_halo_regions_batch.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_void_p]

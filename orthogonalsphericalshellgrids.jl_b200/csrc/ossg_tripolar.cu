@@ -783,6 +783,40 @@ static int check_ptrs(void* const* v, int n, size_t align, const char* what)
 
 using namespace ossg;
 
+namespace ossg {
+template <typename FT>
+__global__ void __launch_bounds__(256) cartesian_nodes_kernel(const double* __restrict__ lam, const double* __restrict__ phi, size_t n,
+                                                              double radius, FT* __restrict__ x, FT* __restrict__ y, FT* __restrict__ z)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double sin_lat, cos_lat, sin_lon, cos_lon;
+    m::sincosd(__ldg(phi + t), sin_lat, cos_lat);
+    m::sincosd(__ldg(lam + t), sin_lon, cos_lon);
+    x[t] = (FT)(radius * cos_lon * cos_lat);
+    y[t] = (FT)(radius * sin_lon * cos_lat);
+    z[t] = (FT)(radius * sin_lat);
+}
+}  // namespace ossg
+
+extern "C" int ossg_cartesian_nodes(const void* lam, const void* phi, size_t n, double radius, int out_type,
+                                    void* x, void* y, void* z, void* stream)
+{
+    if (!lam || !phi || !x || !y || !z) return set_error(OSSG_EINVAL, "NULL array");
+    if (out_type != OSSG_F64 && out_type != OSSG_F32) return set_error(OSSG_EINVAL, "out_type must be OSSG_F64 or OSSG_F32");
+    if (n == 0) return 0;
+    if (n > (size_t)0x7fffffff * 256) return set_error(OSSG_EINVAL, "too many nodes for one launch");
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (out_type == OSSG_F64)
+        cartesian_nodes_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const double*>(lam), static_cast<const double*>(phi), n, radius,
+                                                                              static_cast<double*>(x), static_cast<double*>(y), static_cast<double*>(z));
+    else
+        cartesian_nodes_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const double*>(lam), static_cast<const double*>(phi), n, radius,
+                                                                             static_cast<float*>(x), static_cast<float*>(y), static_cast<float*>(z));
+    OSSG_LAUNCH_CHECK("cartesian_nodes_kernel");
+    return 0;
+}
+
 extern "C" size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, int out_type)
 {
     ossg_tripolar_params q;

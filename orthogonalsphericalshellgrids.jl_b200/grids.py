@@ -311,3 +311,23 @@ def with_halo(new_halo, old_grid: OrthogonalSphericalShellGrid):
         # src/with_halo.jl:25-44: global size from the local sizes; `radius` is not forwarded there
         return TripolarGrid(old_grid.architecture, old_grid.dtype, size=old_grid.global_size, **kw)
     return TripolarGrid(old_grid.architecture, old_grid.dtype, size=old_grid.size, radius=old_grid.radius, **kw)
+
+
+def cartesian_nodes(grid: OrthogonalSphericalShellGrid, loc=(Face, Face), radius=None, dtype=None):
+    """Cartesian coordinates (x, y, z) of the grid's nodes at horizontal location `loc`, over the
+    whole parent arrays -- Oceananigans' get_cartesian_nodes_and_vertices / lat_lon_to_cartesian
+    as used by test/test_tripolar_grid.jl:68 and examples/visualize_tripolar_grid.jl:39-42, computed
+    on the GPU (ossg_cartesian_nodes).  Needs the FP64 coordinates, i.e. a Float64 grid."""
+    import ctypes as C
+    suffix = ("f" if loc[0] is Face else "c") + ("f" if loc[1] is Face else "c")
+    lam, phi = grid.arrays["lam_" + suffix].parent, grid.arrays["phi_" + suffix].parent
+    if lam.dtype != torch.float64:
+        raise ValueError("cartesian_nodes needs a Float64 grid (the coordinates are read as FP64)")
+    dtype = dtype or torch.float64
+    out = [torch.empty_like(lam, dtype=dtype) for _ in range(3)]
+    L = _lib.lib()
+    stream = torch.cuda.current_stream(lam.device).cuda_stream
+    _lib.check(L.ossg_cartesian_nodes(lam.data_ptr(), phi.data_ptr(), lam.numel(), float(grid.radius if radius is None else radius),
+                                      _lib.OSSG_F64 if dtype == torch.float64 else _lib.OSSG_F32,
+                                      out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stream))
+    return tuple(OffsetArray(t, grid.Hx, grid.Hy) for t in out)

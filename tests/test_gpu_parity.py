@@ -429,6 +429,37 @@ def test_abi_argument_errors(ossg):
         ossg.TripolarGrid(size=(61, 30, 1))
 
 
+def test_cartesian_nodes_and_orthogonality_on_gpu(ossg, oracle):
+    """ossg_cartesian_nodes (Oceananigans lat_lon_to_cartesian / get_cartesian_nodes_and_vertices)
+    bit for bit against the oracle, and the reference's orthogonality test
+    (test/test_tripolar_grid.jl:36-76) evaluated on the GPU-produced FF nodes of the 1 degree grid
+    with poles at (75, 35 N): centred-difference angle within 0.01 degree of 90 outside the masked
+    pole windows and phi < -78 (bounds as in tests/test_oracle_golden.py)."""
+    size = (360, 180, 1)
+    grid = ossg.TripolarGrid(ossg.GPU(), size=size, first_pole_longitude=75, north_poles_latitude=35)
+    for loc, suffix in (((ossg.Face, ossg.Face), "ff"), ((ossg.Center, ossg.Center), "cc")):
+        x, y, z = ossg.cartesian_nodes(grid, loc, radius=1.0)
+        lam, phi = grid.arrays["lam_" + suffix].parent.cpu().numpy(), grid.arrays["phi_" + suffix].parent.cpu().numpy()
+        for got, want in zip((x, y, z), oracle.cartesian_nodes(lam, phi, 1.0)):
+            assert np.array_equal(got.parent.cpu().numpy().view(np.uint64), want.view(np.uint64)), suffix
+    xr = ossg.cartesian_nodes(grid, (ossg.Face, ossg.Face))[0]           # default radius = grid.radius
+    want = oracle.cartesian_nodes(grid.arrays["lam_ff"].parent.cpu().numpy(), grid.arrays["phi_ff"].parent.cpu().numpy(), grid.radius)[0]
+    assert np.array_equal(xr.parent.cpu().numpy().view(np.uint64), want.view(np.uint64))
+    x32 = ossg.cartesian_nodes(grid, (ossg.Face, ossg.Face), dtype=torch.float32)[0]
+    assert np.array_equal(x32.parent.cpu().numpy(), want.astype(np.float32))
+    # orthogonality on the device
+    Nx, Ny, H = 360, 180, 4
+    x, y, z = (t.parent[H:H + Ny, H:H + Nx] for t in ossg.cartesian_nodes(grid, (ossg.Face, ossg.Face), radius=1.0))
+    P = torch.stack([x, y, z], dim=-1)
+    lamd = grid.arrays["lam_ff"].parent[H:H + Ny, H:H + Nx]
+    phid = grid.arrays["phi_ff"].parent[H:H + Ny, H:H + Nx]
+    masked = (((lamd - 75).abs() < 5) & ((35 - phid).abs() < 5)) | (((lamd - 255).abs() < 5) & ((35 - phid).abs() < 5)) | (phid < -78)
+    v1, v2 = P[1:-1, 2:] - P[1:-1, :-2], P[2:, 1:-1] - P[:-2, 1:-1]
+    cos = (v1 * v2).sum(-1) / (v1.norm(dim=-1) * v2.norm(dim=-1))
+    ang = torch.rad2deg(torch.arccos(cos.clamp(-1, 1))) - 90
+    assert float(ang[~masked[1:-1, 1:-1]].abs().max()) < 0.01
+
+
 def test_tma_staging_of_the_tile_kernel_matches_oracle():
     """The opt-in TMA staging of metrics_tile_kernel (OSSG_TILE_STAGING=tma, UTMALDG box loads on an
     mbarrier) in a fresh process: FP64 and FP32 grids and a tile window, bit for bit."""
