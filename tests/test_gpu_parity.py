@@ -429,6 +429,19 @@ def test_abi_argument_errors(ossg):
         ossg.TripolarGrid(size=(61, 30, 1))
 
 
+def test_headline_grid_matches_oracle_bit_for_bit(ossg, oracle):
+    """The benchmark configuration itself (1/12 degree, 4320 x 2160, halo 4, FP64): all 20 padded
+    arrays against the multi-threaded oracle, array by array to bound host memory."""
+    size, halo = (4320, 2160, 100), (4, 4, 4)
+    oracle.set_threads(oracle.max_threads())
+    ref = oracle.build(orc.make_params(size, halo))
+    grid = ossg.TripolarGrid(ossg.GPU(), ossg.Float64, size=size, halo=halo)
+    for name in orc.ALL_NAMES:
+        got = grid.arrays[name].parent.cpu().numpy()
+        assert np.array_equal(got.view(np.uint64), ref[name].view(np.uint64)), name
+        ref[name] = None
+
+
 def test_cartesian_nodes_and_orthogonality_on_gpu(ossg, oracle):
     """ossg_cartesian_nodes (Oceananigans lat_lon_to_cartesian / get_cartesian_nodes_and_vertices)
     bit for bit against the oracle, and the reference's orthogonality test
