@@ -185,7 +185,19 @@ def run_own(args):
     dev = torch.device("cuda", local_rank)
     # (NCCL_DEBUG is left as the environment has it: unset, NCCL prints nothing and stdout is the one JSON line)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout must
+        # carry the one JSON line only, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     L = _lib.lib()
     if L.ossg_device_ok() != 0:
         raise SystemExit("no usable CUDA device: " + _lib.last_error())
