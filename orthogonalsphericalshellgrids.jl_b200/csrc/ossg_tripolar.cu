@@ -546,28 +546,51 @@ __host__ __device__ inline Frame make_frame(const Window& w, const FastRect& fr)
     return f;
 }
 
+// One thread per (frame element, staggering class), class-major: a warp serves 32 consecutive
+// elements of ONE class, evaluates that class's three metrics at its own M2 source and stores them
+// coalesced.  (The former one-thread-per-element form evaluated up to four sources in sequence: a
+// 40 us latency chain holding 128 registers next to the tile kernel.)
 template <typename FT>
 __global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f)
 {
+    const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * n) return;
+    const int loc = (int)(t / n);
+    t -= (long long)loc * n;
     const Window w = a.w;
     int iw, jw;
     if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
     else if ((t -= f.n_south) < f.n_north) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); jw += f.jhi; }
     else if ((t -= f.n_north) < f.n_west) { jw = (int)(t / f.ilo); iw = (int)(t - (long long)jw * f.ilo); jw += f.jlo; }
-    else if ((t -= f.n_west) < f.n_east) {
+    else {
+        t -= f.n_west;
         const int ne = w.wnx - f.ihi;
         jw = (int)(t / ne); iw = (int)(t - (long long)jw * ne) + f.ihi; jw += f.jlo;
-    } else return;
-
+    }
     const GridDims g = a.g;
     const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
+    const int I = w.I0 + iw, J = w.J0 + jw;
+    // metric ids of the class: dx, dy, az
+    const int idx = loc == CC ? DX_CC : loc == FC ? DX_FC : loc == CF ? DX_CF : DX_FF;
+    const int idy = loc == CC ? DY_CC : loc == FC ? DY_FC : loc == CF ? DY_CF : DY_FF;
+    const int idz = loc == CC ? AZ_CC : loc == FC ? AZ_FC : loc == CF ? AZ_CF : AZ_FF;
     double out[N_METRIC];
-    const FrameAcc acc{ a.coords64, w, tb, g, a.first_pole_longitude };
-    metrics_at_padded(acc, tb, g, a.radius, w.I0 + iw, w.J0 + jw, out);
+    if (J <= 1) {                                            // M3: lat-lon continuation rows
+        const double* row = tb.ll + (size_t)(J + g.Hy - 1) * LL_NCOL;
+        out[idx] = row[loc == CC ? LL_DX_CC : loc == FC ? LL_DX_FC : loc == CF ? LL_DX_CF : LL_DX_FF];
+        out[idy] = row[LL_DY];
+        out[idz] = row[loc == CC ? LL_AZ_CC : loc == FC ? LL_AZ_FC : loc == CF ? LL_AZ_CF : LL_AZ_FF];
+    } else {                                                 // M1 at the class's M2 source
+        int si, sj; bool wrapped;
+        halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, si, sj, wrapped);
+        const FrameAcc acc{ a.coords64, w, tb, g, a.first_pole_longitude };
+        metrics_cell(acc, si, sj, a.radius, 1u << loc, out);
+    }
     const size_t o = (size_t)jw * w.wnx + iw;
-#pragma unroll
-    for (int k = 0; k < N_METRIC; ++k) static_cast<FT*>(a.metrics_out[k])[o] = (FT)out[k];
+    static_cast<FT*>(a.metrics_out[idx])[o] = (FT)out[idx];
+    static_cast<FT*>(a.metrics_out[idy])[o] = (FT)out[idy];
+    static_cast<FT*>(a.metrics_out[idz])[o] = (FT)out[idz];
 }
 
 // ------------------------------------------------------------------ host side
@@ -723,7 +746,7 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         OSSG_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         OSSG_CUDA_TRY(cudaEventRecord(ev_fork, s));
         OSSG_CUDA_TRY(cudaStreamWaitEvent(fs, ev_fork, 0));
-        metrics_frame_kernel<FT><<<ceil_div(nframe, 128), 128, 0, fs>>>(a, f);
+        metrics_frame_kernel<FT><<<ceil_div(4 * nframe, 128), 128, 0, fs>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
         OSSG_CUDA_TRY(cudaEventRecord(ev_join, fs));
     }
@@ -758,7 +781,7 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         cudaEventDestroy(ev_fork);          // (released when the recorded work completes)
         cudaEventDestroy(ev_join);
     } else if (nframe > 0) {
-        metrics_frame_kernel<FT><<<ceil_div(nframe, 128), 128, 0, s>>>(a, f);
+        metrics_frame_kernel<FT><<<ceil_div(4 * nframe, 128), 128, 0, s>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
     }
     return 0;
