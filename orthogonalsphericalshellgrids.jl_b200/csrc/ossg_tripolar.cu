@@ -546,18 +546,18 @@ __host__ __device__ inline Frame make_frame(const Window& w, const FastRect& fr)
     return f;
 }
 
-// One thread per (frame element, staggering class), class-major: a warp serves 32 consecutive
-// elements of ONE class, evaluates that class's three metrics at its own M2 source and stores them
-// coalesced.  (The former one-thread-per-element form evaluated up to four sources in sequence: a
-// 40 us latency chain holding 128 registers next to the tile kernel.)
+// One thread per (frame element, metric), metric-major: a warp serves 32 consecutive elements of
+// ONE metric, evaluates it at its class's M2 source and stores it coalesced.  (The former
+// one-thread-per-element form evaluated up to four sources and twelve metrics in sequence: a 40 us
+// latency chain holding 128 registers next to the tile kernel.)
 template <typename FT>
 __global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f)
 {
     const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 4 * n) return;
-    const int loc = (int)(t / n);
-    t -= (long long)loc * n;
+    if (t >= N_METRIC * n) return;
+    const int mtr = (int)(t / n);
+    t -= (long long)mtr * n;
     const Window w = a.w;
     int iw, jw;
     if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
@@ -571,26 +571,20 @@ __global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f
     const GridDims g = a.g;
     const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
     const int I = w.I0 + iw, J = w.J0 + jw;
-    // metric ids of the class: dx, dy, az
-    const int idx = loc == CC ? DX_CC : loc == FC ? DX_FC : loc == CF ? DX_CF : DX_FF;
-    const int idy = loc == CC ? DY_CC : loc == FC ? DY_FC : loc == CF ? DY_CF : DY_FF;
-    const int idz = loc == CC ? AZ_CC : loc == FC ? AZ_FC : loc == CF ? AZ_CF : AZ_FF;
-    double out[N_METRIC];
+    const int loc = metric_loc(mtr);
+    double v;
     if (J <= 1) {                                            // M3: lat-lon continuation rows
         const double* row = tb.ll + (size_t)(J + g.Hy - 1) * LL_NCOL;
-        out[idx] = row[loc == CC ? LL_DX_CC : loc == FC ? LL_DX_FC : loc == CF ? LL_DX_CF : LL_DX_FF];
-        out[idy] = row[LL_DY];
-        out[idz] = row[loc == CC ? LL_AZ_CC : loc == FC ? LL_AZ_FC : loc == CF ? LL_AZ_CF : LL_AZ_FF];
+        const int col = mtr == DX_CC ? LL_DX_CC : mtr == DX_FC ? LL_DX_FC : mtr == DX_CF ? LL_DX_CF : mtr == DX_FF ? LL_DX_FF
+                      : mtr == AZ_CC ? LL_AZ_CC : mtr == AZ_FC ? LL_AZ_FC : mtr == AZ_CF ? LL_AZ_CF : mtr == AZ_FF ? LL_AZ_FF : LL_DY;
+        v = row[col];
     } else {                                                 // M1 at the class's M2 source
         int si, sj; bool wrapped;
         halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, si, sj, wrapped);
         const FrameAcc acc{ a.coords64, w, tb, g, a.first_pole_longitude };
-        metrics_cell(acc, si, sj, a.radius, 1u << loc, out);
+        v = metric_one(acc, mtr, si, sj, a.radius);
     }
-    const size_t o = (size_t)jw * w.wnx + iw;
-    static_cast<FT*>(a.metrics_out[idx])[o] = (FT)out[idx];
-    static_cast<FT*>(a.metrics_out[idy])[o] = (FT)out[idy];
-    static_cast<FT*>(a.metrics_out[idz])[o] = (FT)out[idz];
+    static_cast<FT*>(a.metrics_out[mtr])[(size_t)jw * w.wnx + iw] = (FT)v;
 }
 
 // ------------------------------------------------------------------ host side
@@ -746,7 +740,7 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         OSSG_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         OSSG_CUDA_TRY(cudaEventRecord(ev_fork, s));
         OSSG_CUDA_TRY(cudaStreamWaitEvent(fs, ev_fork, 0));
-        metrics_frame_kernel<FT><<<ceil_div(4 * nframe, 128), 128, 0, fs>>>(a, f);
+        metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, fs>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
         OSSG_CUDA_TRY(cudaEventRecord(ev_join, fs));
     }
@@ -781,7 +775,7 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         cudaEventDestroy(ev_fork);          // (released when the recorded work completes)
         cudaEventDestroy(ev_join);
     } else if (nframe > 0) {
-        metrics_frame_kernel<FT><<<ceil_div(4 * nframe, 128), 128, 0, s>>>(a, f);
+        metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, s>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
     }
     return 0;

@@ -496,6 +496,43 @@ OSSG_HD void metrics_cell(const Acc& acc, int i, int j, double R, unsigned mask,
     if (want_cf) out[AZ_CF] = out[DY_CF] * out[DX_CF];                                     // :35
 }
 
+// ONE metric of M1 at interior cell (i, j) (same expressions as metrics_cell; the frame kernel runs
+// one thread per element and metric).  The product areas az_fc, az_cf evaluate their two spacings.
+template <class Acc>
+OSSG_HD double metric_one(const Acc& acc, int mtr, int i, int j, double R)
+{
+    // haversine(first point X, second point Y) between two points of one staggering
+    auto hav = [&](int loc, int ix, int jx, int iy, int jy) {
+        double lx, px, ly, py;
+        acc(loc, ix, jx, lx, px);
+        acc(loc, iy, jy, ly, py);
+        const double rx = px * D2R, ry = py * D2R;
+        return haversine_pre_ool(lx, 0.5 * rx, cos_rad_ool(rx), ly, 0.5 * ry, cos_rad_ool(ry), R);
+    };
+    auto quad = [&](int loc, int ia, int ja, int ib, int jb, int ic, int jc, int id, int jd) {
+        double l, p;
+        acc(loc, ia, ja, l, p); const Vec3 a = lat_lon_to_cartesian_ool(p, l);
+        acc(loc, ib, jb, l, p); const Vec3 b = lat_lon_to_cartesian_ool(p, l);
+        acc(loc, ic, jc, l, p); const Vec3 c = lat_lon_to_cartesian_ool(p, l);
+        acc(loc, id, jd, l, p); const Vec3 d = lat_lon_to_cartesian_ool(p, l);
+        return spherical_area_quadrilateral_ool(a, b, c, d) * (R * R);
+    };
+    switch (mtr) {
+    case DX_CC: return hav(FC, i + 1, j, i, j);                              // utils.jl:13
+    case DX_FC: return hav(CC, i, j, i - 1, j);                              // :14
+    case DX_CF: return hav(FF, i + 1, j, i, j);                              // :15
+    case DX_FF: return hav(CF, i, j, i - 1, j);                              // :16
+    case DY_CC: return hav(CF, i, j + 1, i, j);                              // :18
+    case DY_FC: return hav(FF, i, j + 1, i, j);                              // :19
+    case DY_CF: return hav(CC, i, j, i, j - 1);                              // :20
+    case DY_FF: return hav(FC, i, j, i, j - 1);                              // :21
+    case AZ_CC: return quad(FF, i, j, i + 1, j, i + 1, j + 1, i, j + 1);     // :23-28
+    case AZ_FC: return hav(FF, i, j + 1, i, j) * hav(CC, i, j, i - 1, j);    // :34  dy_fc * dx_fc
+    case AZ_CF: return hav(CC, i, j, i, j - 1) * hav(FF, i + 1, j, i, j);    // :35  dy_cf * dx_cf
+    default:    return quad(CC, i - 1, j - 1, i, j - 1, i, j, i - 1, j);     // :38-43  az_ff
+    }
+}
+
 // Full value of the 12 metrics at padded global element (I, J): M1 evaluated at each class's M2
 // source, or the lat-lon row for J <= 1 (M3).  Generic (slow) path used for halo elements and by
 // tests; the tile kernel handles the bulk.
