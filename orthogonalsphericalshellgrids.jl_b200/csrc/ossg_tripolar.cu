@@ -1,14 +1,20 @@
 // csrc/ossg_tripolar.cu -- TripolarGrid coordinate + metric generation on sm_100a.
 //
 // Kernels (all FP64 arithmetic, outputs FP64 or rounded once to FP32):
-//   K0 tables_kernel        1-D tables: a*sind/cosd(lam1D), cosh/sinh(psi(phi1D)), lat-lon rows
-//   K1 coords_kernel        8 padded coordinate arrays; circshift + zipper/periodic halos are
-//                           index maps (every element evaluated at its source)
-//   K2 metrics_tile_kernel  12 metric arrays over the interior: coordinate tile + 1-cell apron
-//                           staged in shared memory, per-point cos(phi) and unit vectors computed
-//                           once per tile point, coalesced stores
+//   K0  tables_kernel         1-D tables: a*sind/cosd(lam1D), cosh/sinh(psi(phi1D)), lat-lon rows
+//   K1  coords_pair_kernel    8 padded coordinate arrays for windows that span x: one thread per
+//                             mirror pair of columns (the map is exactly mirror symmetric), branch-free
+//                             straight-line point with a table-driven atan; circshift + zipper/periodic
+//                             halos are index maps (every element evaluated at its source)
+//   K1' coords_kernel         the same per padded element (windows that split x)
+//   K2  metrics_tile_kernel   12 metric arrays over the interior: four coordinate patches staged in
+//                             shared memory (cp.async; TMA box loads opt-in), per-point cos(phi) and
+//                             unit vectors once per patch point, then 8 haversines + 2 spherical
+//                             quadrilaterals per cell as one speculative straight-line block
 //   K2f metrics_frame_kernel  the halo frame (north fold image, x halos, fold row Ny, south
-//                           continuation rows): each element evaluated at its source
+//                             continuation rows): one thread per (element, metric) at its source,
+//                             on a side stream next to K2
+//   cartesian_nodes_kernel    lat_lon_to_cartesian over a coordinate pair
 // Compile with -fmad=false: see ossg_math.cuh for the determinism contract.
 #include <cuda.h>
 #include <cstdlib>
