@@ -11,6 +11,7 @@ from .fields import (BoundaryCondition, CenterField, Field, FieldBoundaryConditi
                      XFaceField, YFaceField, ZFaceField, Zipper, ZipperBoundaryCondition, bc_str,
                      fill_halo_regions, regularize_field_boundary_conditions, set_, sign,
                      validate_boundary_condition_location)
+from .immersed import GridFittedBottom, ImmersedBoundaryGrid, immersed_cell
 from .distributed import (Distributed, DistributedTripolarGrid, Partition, reconstruct_global_grid)
 
 __all__ = ["TripolarGrid", "ZipperBoundaryCondition"]

@@ -111,7 +111,9 @@ def default_boundary_conditions() -> FieldBoundaryConditions:
 class Field:
     """A 3-D field on a tripolar grid: parent tensor of shape (Nz+2Hz, Ny+2Hy, Nx+2Hx) on the
     grid's device.  If the supplied north boundary condition is not a Zipper it is replaced by
-    ZipperBoundaryCondition(sign(LX, LY)) (src/tripolar_grid_extensions.jl:57-80)."""
+    ZipperBoundaryCondition(sign(LX, LY)) (src/tripolar_grid_extensions.jl:57-80).
+    LZ = None is Julia's `Nothing` location: a horizontal field with one level and no z halo
+    (parent shape (1, Ny+2Hy, Nx+2Hx)), e.g. the bottom height of an immersed boundary."""
 
     def __init__(self, loc, grid: OrthogonalSphericalShellGrid, data: Optional[torch.Tensor] = None,
                  boundary_conditions: Optional[FieldBoundaryConditions] = "default", dtype=None):
@@ -120,7 +122,8 @@ class Field:
         self.loc = (LX, LY, LZ)
         self.grid = grid
         dtype = dtype or grid.dtype
-        shape = (grid.Nz + 2 * grid.Hz, grid.Ny + 2 * grid.Hy, grid.Nx + 2 * grid.Hx)
+        self.Nz, self.Hz = (1, 0) if LZ is None else (grid.Nz, grid.Hz)
+        shape = (self.Nz + 2 * self.Hz, grid.Ny + 2 * grid.Hy, grid.Nx + 2 * grid.Hx)
         if data is None:
             device = grid.arrays["lam_cc"].parent.device
             data = torch.zeros(shape, dtype=dtype, device=device)
@@ -146,7 +149,7 @@ class Field:
     # -- reference-style helpers
     def interior(self) -> torch.Tensor:
         g = self.grid
-        return self.data[g.Hz:g.Hz + g.Nz, g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]
+        return self.data[self.Hz:self.Hz + self.Nz, g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]
 
     def __getitem__(self, ijk):
         """Julia indexing c[i, j, k] (1-based interior, halos outside)."""
@@ -159,14 +162,14 @@ class Field:
                 hi = None if v.stop is None else v.stop + H
                 return slice(lo, hi)
             return v + H - 1
-        return self.data[ix(k, g.Hz), ix(j, g.Hy), ix(i, g.Hx)]
+        return self.data[ix(k, self.Hz), ix(j, g.Hy), ix(i, g.Hx)]
 
     def descriptor(self) -> FieldDesc:
         g = self.grid
         bc = self.boundary_conditions.north if self.boundary_conditions is not None else None
         s = float(bc.condition) if is_zipper(bc) else 1.0
         et = _lib.OSSG_F64 if self.data.dtype == torch.float64 else _lib.OSSG_F32
-        return FieldDesc(self.data.data_ptr(), et, g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz,
+        return FieldDesc(self.data.data_ptr(), et, g.Nx, g.Ny, self.Nz, g.Hx, g.Hy, self.Hz,
                          _loc_code(self.loc[0]), _loc_code(self.loc[1]), 0, 0, s)
 
 
@@ -191,14 +194,20 @@ _NODE = {(0, 0): "cc", (1, 0): "fc", (0, 1): "cf", (1, 1): "ff"}
 
 def set_(f: Field, value) -> Field:
     """set!(field, value): a number, an array of the interior shape (Nz, Ny, Nx), or a function
-    (λ, φ, z) evaluated at the field's nodes."""
+    evaluated at the field's nodes: (λ, φ, z) for a 3-D field, (λ, φ) for a horizontal one."""
     g = f.grid
     if callable(value):
         key = _NODE[(_loc_code(f.loc[0]), _loc_code(f.loc[1]))]
         lam = g.arrays["lam_" + key].interior(g.Nx, g.Ny).to(f.data.dtype)
         phi = g.arrays["phi_" + key].interior(g.Nx, g.Ny).to(f.data.dtype)
-        zc = torch.as_tensor(g.z.zc, dtype=f.data.dtype, device=f.data.device)
-        f.interior().copy_(value(lam[None, :, :], phi[None, :, :], zc[:, None, None]).expand(g.Nz, g.Ny, g.Nx))
+        if f.loc[2] is None:
+            v = value(lam[None, :, :], phi[None, :, :])
+        else:
+            z = g.z.zf if _loc_code(f.loc[2]) == _lib.OSSG_FACE else g.z.zc
+            zt = torch.as_tensor(np.asarray(z)[:f.Nz], dtype=f.data.dtype, device=f.data.device)
+            v = value(lam[None, :, :], phi[None, :, :], zt[:, None, None])
+        v = torch.as_tensor(v, dtype=f.data.dtype, device=f.data.device)
+        f.interior().copy_(v.expand(f.Nz, g.Ny, g.Nx))
     elif isinstance(value, (int, float)):
         f.interior().fill_(value)
     else:

@@ -318,6 +318,47 @@ def test_reference_zipper_testset_fold_row(ossg):
     assert np.array_equal(urow[1:5], -urow[6:10][::-1])                                  # :68-72
 
 
+def test_immersed_bottom_height_is_symmetric_across_the_fold(ossg, oracle):
+    """test/test_zipper_boundary_conditions.jl:46-54: a random bottom under
+    ImmersedBoundaryGrid(grid, GridFittedBottom(bottom)) is mirror-symmetric in row Ny; the whole
+    (Center, Center, Nothing) field equals the oracle's zipper + periodic fill of the same input.
+    Then the pole mask of examples/bickley_jet.jl:25-29 and fields on the wrapped grid."""
+    under = ossg.TripolarGrid(size=(10, 10, 1))
+    Nx, Ny, Hx, Hy = under.Nx, under.Ny, under.Hx, under.Hy
+    rng = np.random.default_rng(54)
+    bottom = rng.random((Ny, Nx))
+    grid = ossg.ImmersedBoundaryGrid(under, ossg.GridFittedBottom(bottom))
+    h = grid.immersed_boundary.bottom_height
+    assert tuple(h.data.shape) == (1, Ny + 2 * Hy, Nx + 2 * Hx) and h.loc[2] is None
+    got = h.data.cpu().numpy()
+    row = got[0, Hy + Ny - 1, Hx:Hx + Nx]
+    assert np.array_equal(row, row[::-1])                                                # :54
+    assert np.array_equal(row[:Nx // 2], bottom[Ny - 1, :Nx // 2])                       # left half kept
+    want = np.zeros_like(got)
+    want[0, Hy:Hy + Ny, Hx:Hx + Nx] = bottom
+    want = oracle.fill_halo_regions(want, Nx, Ny, 1, Hx, Hy, 0, 0, 0, 1.0)
+    assert _same_bits(got, want)
+    # fields on the wrapped grid take the zipper like on the bare one (TRG union, src/tripolar_grid.jl:371)
+    c, u = ossg.CenterField(grid), ossg.XFaceField(grid)
+    assert c.boundary_conditions.north.condition == 1 and u.boundary_conditions.north.condition == -1
+    ossg.set_(c, lambda lam, phi, z: lam + 0 * phi + 0 * z)
+    ossg.fill_halo_regions(c)
+    crow = c.interior()[0, Ny - 1, :].cpu().numpy()
+    assert np.array_equal(crow, crow[::-1])                                              # :65
+    # bickley-jet mask: both poles and the southern cap are immersed, and the mask is fold-symmetric
+    lp, pp = 45.0, 25.0
+    under = ossg.TripolarGrid(size=(120, 60, 1), halo=(5, 5, 5), first_pole_longitude=lp, north_poles_latitude=pp)
+    def mask(lam, phi):
+        near = lambda l0: ((lam - l0).abs() < 5) & ((pp - phi).abs() < 5)
+        return (near(lp) | near(lp + 180) | (phi < -78)).to(lam.dtype)
+    grid = ossg.ImmersedBoundaryGrid(under, ossg.GridFittedBottom(mask))
+    hb = grid.immersed_boundary.bottom_height.interior()[0].cpu().numpy()
+    assert np.array_equal(hb[-1], hb[-1][::-1])
+    assert hb[-1, 0] == 1 and hb[-1, 60] == 1 and hb[0].all() and 0 < hb.mean() < 0.2
+    wet = ~ossg.immersed_cell(grid)
+    assert tuple(wet.shape) == (1, 60 + 10, 120 + 10) and bool(wet[0, 5 + 30, 5 + 30])
+
+
 def test_fold_quirk_sign_flip_is_reproduced(ossg, oracle):
     """for (Face, Center), sign -1, c[Nx/2+1, Ny] flips on EVERY fill
     (src/zipper_boundary_condition.jl:102 with i' == i); a drop-in must do the same."""

@@ -131,6 +131,30 @@ def test_default_zipper_signs(ossg):
     assert ossg.ZipperBoundaryCondition().condition == 1 and ossg.bc_str(ossg.ZipperBoundaryCondition()) == "Zipper"
 
 
+def test_horizontal_field_and_immersed_wrapper_host_logic(ossg):
+    """(Center, Center, Nothing) fields (the immersed-boundary bottom height) have one
+    level and no z halo in their descriptor; an ImmersedBoundaryGrid forwards every grid attribute
+    (the TRG union, src/tripolar_grid.jl:371) and cannot be built without a device."""
+    g = _StubGrid(ossg, size=(10, 8, 5), halo=(3, 2, 4))
+    f = ossg.Field((ossg.Center, ossg.Center, None), g, data=torch.zeros((1, 8 + 4, 10 + 6), dtype=torch.float64))
+    d = f.descriptor()
+    assert (d.Nx, d.Ny, d.Nz, d.Hx, d.Hy, d.Hz, d.locx, d.locy, d.sign) == (10, 8, 1, 3, 2, 0, 0, 0, 1.0)
+    assert tuple(f.interior().shape) == (1, 8, 10)
+    ossg.set_(f, np.arange(80.0).reshape(8, 10))
+    assert float(f[10, 8, 1]) == 79.0 and float(f[1, 1, 1]) == 0.0
+    with pytest.raises(ValueError):
+        ossg.Field((ossg.Center, ossg.Center, None), g, data=torch.zeros((5 + 8, 12, 16), dtype=torch.float64))
+    from ossg_b200.immersed import ImmersedBoundaryGrid
+    w = ImmersedBoundaryGrid.__new__(ImmersedBoundaryGrid)
+    w.underlying_grid = g
+    assert (w.Nx, w.Ny, w.Nz, w.Hy) == (10, 8, 5, 2) and w.architecture is g.architecture
+    assert _field(ossg, w, (ossg.Face, ossg.Center, ossg.Center)).boundary_conditions.north.condition == -1
+    if NO_GPU:
+        g.arrays = {"lam_cc": None}
+        with pytest.raises(Exception):
+            ossg.ImmersedBoundaryGrid(g, ossg.GridFittedBottom(0.0))
+
+
 def test_zipper_is_north_only(ossg):
     """src/zipper_boundary_condition.jl:58-62"""
     g = _StubGrid(ossg)
