@@ -26,7 +26,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(Nx=4320, Ny=2160, Nz=100, halo=4, south=-80.0, north_poles_latitude=55.0,
                 first_pole_longitude=70.0, radius=6371.0e3)
-CPU_SAMPLE = dict(Nx=1440, Ny=720)          # 1/9 of the workload's cells per CPU step
+CPU_SAMPLE = dict(Nx=1440, Ny=720)          # fallback CPU sample: 1/9 of the workload's cells per step
+CPU_BUDGET_S = 150.0                        # the CPU arm runs the FULL workload unless that would exceed this
 METRIC = "grid cells/s for coords+metrics (FP64)"
 UNIT = "cells/s"
 
@@ -105,20 +106,36 @@ class ClockSampler:
 # ------------------------------------------------------------------ CPU arm (oracle = port of the reference)
 def cpu_construct_rate(threads, steps, warmup):
     """cells/s of the CPU restatement (glibc libm, literal per-point evaluation like the
-    reference's kernels, row-parallel over `threads`) on the bounded sample."""
+    reference's kernels, row-parallel over `threads`).  The sample is the FULL workload (the 1/12
+    degree grid, ~1-5 s per step on 8-24 host threads) as long as warmup + steps of it fit
+    CPU_BUDGET_S -- projected from the first full-size step -- otherwise the 1440x720 grid (1/9 of
+    the cells).  Returns (cells/s, seconds per step, description of the sample)."""
     from oracle import oracle as orc
     o = orc.Oracle(libm=True)
     o.set_threads(threads)
-    p = orc.make_params((CPU_SAMPLE["Nx"], CPU_SAMPLE["Ny"], 1), (WORKLOAD["halo"],) * 3,
-                        WORKLOAD["south"], WORKLOAD["north_poles_latitude"], WORKLOAD["first_pole_longitude"],
-                        WORKLOAD["radius"])
-    for _ in range(warmup):
+
+    def params(Nx, Ny):
+        return orc.make_params((Nx, Ny, 1), (WORKLOAD["halo"],) * 3, WORKLOAD["south"], WORKLOAD["north_poles_latitude"],
+                               WORKLOAD["first_pole_longitude"], WORKLOAD["radius"])
+
+    Nx, Ny = WORKLOAD["Nx"], WORKLOAD["Ny"]
+    p = params(Nx, Ny)
+    t0 = time.perf_counter()
+    o.build(p)                                   # first full-size step: warm-up and the projection
+    first = time.perf_counter() - t0
+    what = f"the full workload ({Nx}x{Ny} grid) per step"
+    if first * (steps + max(warmup, 1)) > CPU_BUDGET_S:
+        Nx, Ny = CPU_SAMPLE["Nx"], CPU_SAMPLE["Ny"]
+        p = params(Nx, Ny)
+        what = f"{Nx}x{Ny} grid (1/9 of the workload's cells) per step"
+        o.build(p)
+    for _ in range(max(warmup, 1) - 1):
         o.build(p)
     t0 = time.perf_counter()
     for _ in range(steps):
         o.build(p)
     dt = (time.perf_counter() - t0) / steps
-    return CPU_SAMPLE["Nx"] * CPU_SAMPLE["Ny"] / dt, dt
+    return Nx * Ny / dt, dt, what
 
 
 def cpu_zipper_rate(threads):
@@ -144,15 +161,14 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     t_all = time.perf_counter()
-    rate, dt = cpu_construct_rate(threads, max(1, args.steps), max(0, args.warmup))
+    rate, dt, what = cpu_construct_rate(threads, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{CPU_SAMPLE['Nx']}x{CPU_SAMPLE['Ny']} grid (1/9 of the workload's cells) per step, "
-                                   "CPU restatement of reference v0.2.1 with glibc libm; Julia is not installed"},
+                         "sample": what + ", CPU restatement of reference v0.2.1 with glibc libm; Julia is not installed"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }
@@ -343,18 +359,28 @@ def run_own(args):
             "whole_step_frac": (inst_tile + inst_coords) / (ms_step * 1e-3) / peak_inst,
             "fp64_inst_source": f"ncu SASS opcode counts, profiles/{PROFILE_TAG}_*_opcodes.md"})
 
+    roofline_zipper = None
+    if world == 1 and isinstance(zipper, dict):
+        best = zipper.get("repeat100_zipper_batch8_larger_than_l2")
+        if not best or "gbs" not in best:
+            best = zipper.get("batch4")
+        if best and "gbs" in best:
+            roofline_zipper = {"bound": "hbm", "kernel": "zipper_kernel", "achieved": best["gbs"], "peak": hbm_peak,
+                               "unit": "GB/s", "frac": best["gbs"] / hbm_peak, "peak_source": peak_src,
+                               "algorithmic_bytes_per_launch": best["algorithmic_bytes"],
+                               "measured_on": "repeat100_zipper_batch8_larger_than_l2" if "what" in best and "8 fields" in best["what"] else "batch4"}
     cpu_threads = os.cpu_count() or 1
-    cpu_rate, cpu_dt = cpu_construct_rate(cpu_threads, 2, 1)
+    cpu_rate, cpu_dt, cpu_what = cpu_construct_rate(cpu_threads, 3, 1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
         "kernel_ms": kernel_ms,
-        "roofline": roofline, "roofline_fp64": roofline_fp64,
+        "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_zipper": roofline_zipper,
         "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                         "sample": f"{CPU_SAMPLE['Nx']}x{CPU_SAMPLE['Ny']} grid (1/9 of the workload's cells), 2 steps, "
-                                   "CPU restatement of reference v0.2.1 (glibc libm); Julia is not installed"},
+                         "sample": cpu_what + ", 3 steps, CPU restatement of reference v0.2.1 (glibc libm); "
+                                   "Julia is not installed"},
         "e2e": {"value": cells_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": len(pin_params),
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
                 "what": "ossg_tripolar_build + copy of the 20 arrays to pinned host buffers (TripolarGrid(CPU()) equivalent)"},
@@ -423,6 +449,55 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
         ms = e0.elapsed_time(e1) / 200
         res[name] = {"ms": ms, "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9}
     res["config"] = f"{nx}x{ny}x{Nz} FP64 fields c,u,v,zeta, Hy=4, L2 flushed (256 MB write) before each timed fill"
+    # ---- the same batched fill with a CLEAN flush: the 256 MB write above leaves the L2 full of dirty
+    # lines whose write-back shares the DRAM with the timed kernel; reading a second 256 MB buffer
+    # afterwards replaces them by clean lines (the inputs are still not in the L2)
+    flush2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush2.zero_()
+    times = []
+    for it in range(8):
+        flush.fill_(it)
+        sink = flush2.view(torch.int64).sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        _lib.check(L.ossg_zipper_fill_batch(descs, 4, stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if it >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    res["batch4_clean_flush"] = {"ms": ms, "algorithmic_bytes": algo, "gbs": algo / (ms * 1e-3) / 1e9,
+                                 "what": "L2 flushed by a 256 MB write followed by a 256 MB read (no dirty lines left to write back "
+                                         "during the timed fill)"}
+    del flush2, sink
+    # ---- 8 fields per launch (c,u,v,zeta twice: e.g. two time levels), repeated back to back WITHOUT a
+    # flush: one fill touches 235 MB, more than the 126 MB L2, so every fill streams from and to HBM
+    # ("inputs larger than L2"); this is the sustained rate a model's halo-fill loop sees
+    try:
+        more = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in specs]
+    except RuntimeError as e:                                   # not enough memory for 8 x 8 GB
+        more = None
+        res["repeat100_zipper_batch8_larger_than_l2"] = {"error": str(e)[:100]}
+    if more is not None:
+        descs8 = (_lib.FieldDesc * 8)(*[
+            _lib.FieldDesc(t.data_ptr(), _lib.OSSG_F64, nx, ny, Nz, H, H, H, loc[0], loc[1], 0, 0, s)
+            for t, (loc, s) in zip(fields + more, specs + specs)])
+        for k in range(4, 8):
+            _lib.check(L.ossg_synth_field(C.byref(descs8[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
+        for _ in range(5):
+            _lib.check(L.ossg_zipper_fill_batch(descs8, 8, stream.cuda_stream))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(100):
+            _lib.check(L.ossg_zipper_fill_batch(descs8, 8, stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 100
+        res["repeat100_zipper_batch8_larger_than_l2"] = {
+            "ms": ms, "algorithmic_bytes": 2 * algo, "gbs": 2 * algo / (ms * 1e-3) / 1e9,
+            "what": "8 fields per launch, 100 fills back to back, no flush: 235 MB per fill exceed the 126 MB L2"}
+        del more
     del fields
     return res
 
@@ -446,7 +521,7 @@ def bench_fold_exchange(world, rank, dev):
     g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
     g.size, g.halo = (nx, ny, Nz), (H, H, H)
     C_, F_ = ossg.Center, ossg.Face
-    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)] * 2      # c, u, v, zeta twice: batches of up to 8
+    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)] * 4      # c, u, v, zeta four times: batches of up to 16
     shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
     all_fields = [ossg.Field(loc, g, data=torch.empty(shape, dtype=torch.float64, device=dev)) for loc in locs]
     fields = all_fields[:4]
@@ -490,22 +565,22 @@ def bench_fold_exchange(world, rank, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for push in (False, True):
+    for push in (False, True, "bulk"):
         res = {}
-        for nf in (1, 2, 4, 8):
+        for nf in (1, 2, 4, 8, 16):
             t = timed(PeerFold(all_fields[:nf], push=push))
             rb = sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in all_fields[:nf])
             res[f"fields{nf}"] = {"ms_per_exchange": t, "recv_bytes_per_rank": rb, "gbs_per_direction_per_gpu": rb / (t * 1e-3) / 1e9}
-        t1, t8 = res["fields1"], res["fields8"]
+        t1, t8 = res["fields1"], res["fields16"]
         slope = (t8["ms_per_exchange"] - t1["ms_per_exchange"]) / (t8["recv_bytes_per_rank"] - t1["recv_bytes_per_rank"])
         res["marginal_gbs"] = 1e-6 / slope
         res["fixed_us"] = 1e3 * (t1["ms_per_exchange"] - slope * t1["recv_bytes_per_rank"])
         # NVLink 5 nominal 900 GB/s per direction; 735 GB/s is what a bidirectional cudaMemcpyPeer
         # reaches on this pool (tools/p2p_probe.py, profiles/r01_p2p_probe.txt)
-        for key in ("fields4", "fields8"):
+        for key in ("fields4", "fields8", "fields16"):
             res[key]["frac_of_nvlink_900"] = res[key]["gbs_per_direction_per_gpu"] / 900.0
             res[key]["frac_of_measured_copy_735"] = res[key]["gbs_per_direction_per_gpu"] / 735.0
-        out["peer_kernel_push" if push else "peer_kernel_pull"] = res
+        out["peer_kernel_push_bulk" if push == "bulk" else "peer_kernel_push" if push else "peer_kernel_pull"] = res
     return out
 
 

@@ -181,7 +181,7 @@ int ossg_fold_unpack(const ossg_field_desc* f, const ossg_fold_window* w, const 
  * synchronises and no NCCL call is on this path.  Same result as ossg_zipper_fill on the global
  * field (src/zipper_boundary_condition.jl:70-155), bit for bit.                                 */
 #define OSSG_MAX_PEERS 8
-#define OSSG_MAX_PEER_BATCH 8
+#define OSSG_MAX_PEER_BATCH 16
 #define OSSG_IPC_HANDLE_BYTES 64
 typedef struct ossg_ipc_handle { unsigned char bytes[OSSG_IPC_HANDLE_BYTES]; } ossg_ipc_handle;
 /* handle of the device allocation that contains device_ptr, and device_ptr's offset inside it   */
@@ -202,7 +202,10 @@ typedef struct ossg_peer_fold {
     uint64_t epoch;                         /* 1, 2, 3, ... one per call, the same on all ranks  */
     int32_t push;                           /* 0: each rank loads its sources from the owners;
                                                1: each rank stores its rows into the destinations'
-                                               halos (posted NVLink writes); same on all ranks    */
+                                               halos (posted NVLink writes);
+                                               2: as 1, rows staged in shared memory in destination
+                                               order and sent as bulk copies (cp.async.bulk, one
+                                               transfer per row segment); same on all ranks        */
     int32_t reserved;
 } ossg_peer_fold;
 

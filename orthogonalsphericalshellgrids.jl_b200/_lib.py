@@ -42,7 +42,7 @@ class FoldWindow(C.Structure):
                 ("src_i0", C.c_int32), ("src_n", C.c_int32)]
 
 
-OSSG_MAX_PEERS, OSSG_MAX_PEER_BATCH = 8, 8
+OSSG_MAX_PEERS, OSSG_MAX_PEER_BATCH = 8, 16
 
 
 class IpcHandle(C.Structure):

@@ -163,10 +163,123 @@ __device__ __forceinline__ void peer_column_push(const ossg_peer_field& p, const
     if (fix_row) dstb[(size_t)(Ny + Hy - 1) * sxr] = peer_sign(vrow, s);
 }
 
+// ---- push form with bulk stores (fold.push == 2).  The block stages the folded rows of one
+// (field, level, 256 source columns) item in shared memory in DESTINATION order (the reversal and the
+// sign happen on the way in), then a few elected threads hand every destination row segment to the
+// bulk-copy engine (cp.async.bulk shared -> global, the 1-D TMA store): the segment crosses NVLink as
+// one 2 KB transfer per row instead of 64 SM-issued 32-byte-per-lane stores.  A bulk copy needs 16-byte
+// aligned addresses and sizes, so the staging position of an element has the parity of its destination
+// address, and the (at most A-1) leading / trailing elements of a segment that fall outside the aligned
+// run -- as well as the wrapped x-Face column 1 -- are stored directly by their threads.  A chunk's
+// destinations may touch up to BULK_NREG ranks (the x-Face map is shifted by one column against the
+// partition); elements beyond that are stored directly too.
+constexpr int BULK_ROWS = 5;            // rows staged per pass (Hy = 4 plus the row-Ny overwrite: one pass)
+constexpr int BULK_NREG = 3;            // destination ranks per chunk served by bulk copies
+constexpr int BULK_RS = PB + 4;         // staging row stride in elements (alignment slack: up to 3 elements)
+
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void peer_chunk_push_bulk(const ossg_peer_field& p, const ossg_peer_fold& fd, int chunk, int kk, unsigned char* sraw)
+{
+    constexpr long long A = 16 / sizeof(T);                           // elements per 16 bytes
+    T* sb = reinterpret_cast<T*>(sraw);
+    const ossg_field_desc& f = p.f;
+    const int tx = threadIdx.x;
+    const int gNx = fd.gNx, Ny = f.Ny, Hy = f.Hy, Hx = f.Hx;
+    const int c0 = chunk * PB;
+    const int n = min(PB, f.Nx - c0);                                 // source columns c0+1 .. c0+n of this rank
+    const int sg_lo = fd.i0[fd.me] + c0, sg_hi = sg_lo + n - 1;       // their global indices
+    const int cst = f.locx ? gNx + 2 : gNx + 1;                       // destination column = cst - source column
+    const int dlo = cst - sg_hi;                                      // destination range, ascending, without the
+    const int dhi = min(cst - sg_lo, gNx);                            // wrapped x-Face column (source 1 -> Nx+1 -> 1)
+    int r_lo = 0;
+#pragma unroll 1
+    for (; r_lo < fd.nranks - 1; ++r_lo)
+        if (dlo < fd.i0[r_lo] + fd.nx[r_lo]) break;                   // owner of the lowest destination column
+    const int half = gNx / 2;
+    const bool center = f.locy == OSSG_CENTER;
+    const int nrows = Hy + (center ? 1 : 0);                          // row q < Hy: halo row q; q == Hy: row Ny (:102, :135)
+    const size_t sx = (size_t)(f.Nx + 2 * Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
+
+    // this thread's source column and destination
+    const bool active = tx < n;
+    const int isg = sg_lo + tx;
+    double s = f.sign;
+    int idg = cst - isg;
+    bool wrapped = false;
+    if (idg > gNx) { s = fabs(s); idg -= gNx; wrapped = true; }
+    int r = 0;
+#pragma unroll 1
+    for (; r < fd.nranks - 1; ++r)
+        if (idg < fd.i0[r] + fd.nx[r]) break;
+    const size_t sxr = (size_t)(fd.nx[r] + 2 * Hx), sxyr = sxr * (size_t)(Ny + 2 * Hy);
+    T* dstb = static_cast<T*>(const_cast<void*>(p.peer[r])) + (size_t)(f.k0 + kk) * sxyr + (idg - fd.i0[r] + Hx);
+    const T* c = static_cast<const T*>(f.data) + (size_t)(f.k0 + kk) * sxy + (c0 + tx + Hx);
+    const int reg = r - r_lo;
+    const int chi = min(dhi, fd.i0[r] + fd.nx[r] - 1);                // this thread's segment: [clo, chi] on rank r
+    const int clo_halo = max(dlo, fd.i0[r]);
+
+#pragma unroll 1
+    for (int q0 = 0; q0 < nrows; q0 += BULK_ROWS) {
+        const int nq = min(BULK_ROWS, nrows - q0);
+        if (tx < BULK_NREG * BULK_ROWS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int qq = 0; qq < nq; ++qq) {
+                const int q = q0 + qq;
+                const bool fix = q == Hy;
+                if (fix && idg <= half) continue;                     // row Ny is overwritten for the right half only
+                const T v = peer_sign(fix ? c[(size_t)(Ny + Hy - 1) * sx] : c[(size_t)((f.locy ? Ny : Ny - 1) + Hy - 1 - q) * sx], s);
+                T* d = dstb + (fix ? (size_t)(Ny + Hy - 1) : (size_t)(Ny + Hy + q)) * sxr;
+                const int clo = fix ? max(clo_halo, half + 1) : clo_halo;
+                bool direct = wrapped || reg >= BULK_NREG;
+                if (!direct) {
+                    const long long E = (long long)(reinterpret_cast<uintptr_t>(d) / sizeof(T));   // destination element index
+                    const long long E_lo = E - (idg - clo), E_end = E + (chi - idg) + 1;
+                    const long long Ea = (E_lo + A - 1) & ~(A - 1), Eb = E_end & ~(A - 1);       // 16-byte aligned run
+                    if (E >= Ea && E < Eb) sb[(size_t)(reg * BULK_ROWS + qq) * BULK_RS + (size_t)(E - (E_lo & ~(A - 1)))] = v;
+                    else direct = true;
+                }
+                if (direct) *d = v;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged values visible to the bulk-copy engine
+        __syncthreads();
+        if (tx < BULK_NREG * nq) {
+            const int g = tx / nq, qq = tx - g * nq, q = q0 + qq, rr = r_lo + g;
+            if (rr < fd.nranks) {
+                const bool fix = q == Hy;
+                int clo = max(dlo, fd.i0[rr]);
+                if (fix) clo = max(clo, half + 1);
+                const int ch = min(dhi, fd.i0[rr] + fd.nx[rr] - 1);
+                if (ch >= clo) {
+                    const size_t sxq = (size_t)(fd.nx[rr] + 2 * Hx), sxyq = sxq * (size_t)(Ny + 2 * Hy);
+                    T* d = static_cast<T*>(const_cast<void*>(p.peer[rr])) + (size_t)(f.k0 + kk) * sxyq + (clo - fd.i0[rr] + Hx)
+                           + (fix ? (size_t)(Ny + Hy - 1) : (size_t)(Ny + Hy + q)) * sxq;
+                    const long long E_lo = (long long)(reinterpret_cast<uintptr_t>(d) / sizeof(T)), E_end = E_lo + (ch - clo) + 1;
+                    const long long Ea = (E_lo + A - 1) & ~(A - 1), Eb = E_end & ~(A - 1);
+                    if (Eb > Ea)
+                        bulk_store_s2g(reinterpret_cast<void*>(static_cast<uintptr_t>(Ea) * sizeof(T)),
+                                       &sb[(size_t)(g * BULK_ROWS + qq) * BULK_RS + (size_t)(Ea - (E_lo & ~(A - 1)))],
+                                       (unsigned)((Eb - Ea) * sizeof(T)));
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+
 __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(const __grid_constant__ PeerBatch b)
 {
     const ossg_peer_fold& fd = b.fold;
     unsigned long long* mine = static_cast<unsigned long long*>(fd.flags_local);
+    __shared__ __align__(128) unsigned char s_bulk[BULK_NREG * BULK_ROWS * BULK_RS * sizeof(double)];   // staging rows of the bulk push form
     // ---- start barrier with the partner ranks (owners of the mirror columns): lane r talks to rank r
     const int t = threadIdx.x;
     const bool partner = t < fd.nranks && t != fd.me && ((b.partners >> t) & 1u);
@@ -188,6 +301,13 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
         const int kk = (int)(rest % b.levels), fi = (int)(rest / b.levels);
         const ossg_peer_field& p = b.pf[fi];
         const int i = chunk * PB + threadIdx.x + 1;
+        if (fd.push == 2) {                                           // (block-uniform)
+            if (chunk * PB < p.f.Nx && kk < p.f.nk) {
+                if (p.f.elem_type == OSSG_F64) peer_chunk_push_bulk<double>(p, fd, chunk, kk, s_bulk);
+                else peer_chunk_push_bulk<float>(p, fd, chunk, kk, s_bulk);
+            }
+            continue;
+        }
         if (i <= p.f.Nx && kk < p.f.nk) {
             if (fd.push) {
                 if (p.f.elem_type == OSSG_F64) peer_column_push<double>(p, fd, i, kk);
@@ -201,6 +321,10 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
 
     // ---- end barrier (last block only, lane r talks to rank r)
     __shared__ int is_last;
+    if (fd.push == 2) {                                               // bulk stores of this block complete and ordered
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // before the generic-proxy release below
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
     __syncthreads();
     if (t == 0) {
         unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);

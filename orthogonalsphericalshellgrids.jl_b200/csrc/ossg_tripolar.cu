@@ -263,7 +263,14 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
 #ifndef OSSG_USE_TMA
 #define OSSG_USE_TMA 0
 #endif
-constexpr int TX = 32, TY = 8, NT = TX * TY;
+#ifndef OSSG_TX
+#define OSSG_TX 32
+#endif
+#ifndef OSSG_TY
+#define OSSG_TY 8
+#endif
+constexpr int TX = OSSG_TX, TY = OSSG_TY, NT = TX * TY;
+constexpr int TILE_CTAS = 1024 / NT;                       // 32 warps of tile CTAs per SM
 constexpr int QY = TY + 1;
 // Patch geometry.  cp.async staging: (TX+1) x QY points, dense.  TMA staging: the box is (TX+2) x QY
 // (the inner box extent must be a multiple of 16 bytes; the extra column is fetched and ignored) and
@@ -327,7 +334,7 @@ __device__ __forceinline__ void store_metric(const BuildArgs& a, int id, size_t 
 }
 
 template <typename FT, bool TMA>
-__global__ void __launch_bounds__(NT, 4) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
+__global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
                                                              const __grid_constant__ TileMaps tm)
 {
     constexpr int QX = TileGeom<TMA>::QX, QPTS = TileGeom<TMA>::QPTS, PS = TileGeom<TMA>::PS;

@@ -262,11 +262,13 @@ class PeerFold:
     Collective constructor: every rank of `group` must build it for the same list of fields (ranks
     below the top row take part in the handle exchange only)."""
 
-    def __init__(self, fields: Sequence, group=None, push: bool = True):
+    def __init__(self, fields: Sequence, group=None, push=True):
         import ctypes as C
         import torch.distributed as dist
         from .fields import is_zipper
-        self.push = bool(push)
+        # push: False / 0 = pull (peer loads), True / 1 = push (peer stores), 2 or "bulk" = push through
+        # bulk copies (rows staged in shared memory, one cp.async.bulk transfer per row segment)
+        self.push = 2 if push in (2, "bulk") else int(bool(push))
         self.fields = [f for f in fields if f.boundary_conditions is not None and is_zipper(f.boundary_conditions.north)]
         arch = fields[0].grid.architecture
         if arch.Rx > _lib.OSSG_MAX_PEERS:

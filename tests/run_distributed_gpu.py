@@ -69,9 +69,9 @@ def check(world, rank, dev):
                 bad = np.argwhere(~same)[0]
                 failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: fill differs at {bad.tolist()}")
         dist.barrier()
-        # the same fill with the fold served by the one-kernel NVLink peer path (pull and push
-        # forms), three epochs each
-        for push in (False, True):
+        # the same fill with the fold served by the one-kernel NVLink peer path (pull, push and
+        # bulk-push forms), three epochs each
+        for push in (False, True, "bulk"):
             for f, p0 in zip(fields, pristine):
                 f.data.copy_(p0)
             torch.cuda.synchronize(dev)

@@ -415,13 +415,19 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
     GPU: every rank's tile is its own array, peer pointers are plain device pointers and each
     rank's kernel runs on its own stream (they wait for each other through the epoch flags).
     Two epochs, all four staggerings in one batch, Rx = 1..4, both signs, FP64 and FP32, pull
-    (peer loads) and push (peer stores) forms."""
+    (peer loads), push (peer stores) and bulk push (rows staged in shared memory, cp.async.bulk row
+    segments) forms.  The bulk form also runs on wider grids whose chunks of 256 columns are full,
+    straddle ranks, have odd row pitches (the 16-byte alignment of a segment then changes from row to
+    row) and need two staging passes (Hy = 6)."""
     from ossg_b200.distributed import local_sizes
     lib_ = ossg._lib
     L = lib_.lib()
-    gNx, Ny, Nz, Hx, Hy, Hz = 24, 10, 2, 3, 3, 1
-    for npdt, push in ((np.float64, 0), (np.float32, 0), (np.float64, 1), (np.float32, 1)):
-        for Rx in (1, 2, 3, 4):
+    Ny, Nz, Hx, Hz = 10, 2, 3, 1
+    cases = [(np.float64, 0, 24, 3), (np.float32, 0, 24, 3), (np.float64, 1, 24, 3), (np.float32, 1, 24, 3),
+             (np.float64, 2, 24, 3), (np.float32, 2, 24, 3), (np.float64, 2, 1100, 3), (np.float32, 2, 1100, 6),
+             (np.float64, 2, 1030, 6), (np.float32, 2, 778, 3)]
+    for npdt, push, gNx, Hy in cases:
+        for Rx in (1, 2, 3, 4) + ((7, 8) if gNx > 24 else ()):
             sx = local_sizes(gNx, Rx)
             starts = [1 + sum(sx[:r]) for r in range(Rx)]
             specs = [(loc, sign) for loc in LOCS.values() for sign in (1, -1)]
