@@ -268,6 +268,12 @@ int ossg_fp64_peak_probe(int iters, float* ms, double* flops, void* stream);
  * operands drawn from the ranges the kernel admits; mismatches[0] = sqrt, [1] = division
  * (host pointers; the call synchronises the stream)                                            */
 int ossg_selftest_sqrt_div(uint64_t n, uint64_t seed, uint64_t mismatches[2], void* stream);
+/* NVLink store-path probe: kernel-issued copy of `rows` contiguous source segments of seg_bytes to
+ * dst + (r / group) * group_stride + (r % group) * pitch (dst usually peer-mapped); mode 0: 8-byte
+ * stores, 1: 16-byte stores, 2: shared-memory staging + one bulk store per chunk, 3: bulk load +
+ * bulk store; chunk_bytes <= 16384; blocks <= 0 selects 4 blocks per SM                          */
+int ossg_peer_copy_probe(void* dst, const void* src, uint64_t rows, uint32_t seg_bytes, uint64_t group,
+                         uint64_t group_stride, uint64_t pitch, uint32_t chunk_bytes, int mode, int blocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -126,6 +126,8 @@ def lib() -> C.CDLL:
     L.ossg_zipper_fill_peer.argtypes = [C.POINTER(PeerField), C.c_int, C.POINTER(PeerFoldDesc), C.c_void_p]
     L.ossg_halo_exchange_peer.argtypes = [C.POINTER(PeerHaloField), C.c_int, C.POINTER(PeerHaloDesc), C.c_void_p]
     L.ossg_selftest_sqrt_div.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
+    L.ossg_peer_copy_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
+                                       C.c_uint32, C.c_int, C.c_int, C.c_void_p]
     _lib = L
     return L
 

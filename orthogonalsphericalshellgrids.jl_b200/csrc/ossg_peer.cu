@@ -80,7 +80,8 @@ struct PeerBatch {
     ossg_peer_fold fold;
     int n;
     unsigned int partners;       // bit r: rank r owns fold sources / destinations of this rank's columns
-    int chunks, levels;          // work items: n fields x levels x chunks of PB columns
+    int chunks, levels;          // work items: n fields x levels x chunks of PB columns (bulk push: of bulk_cw columns)
+    int bulk_cw;
     long long nitems;
 };
 
@@ -174,8 +175,10 @@ __device__ __forceinline__ void peer_column_push(const ossg_peer_field& p, const
 // destinations may touch up to BULK_NREG ranks (the x-Face map is shifted by one column against the
 // partition); elements beyond that are stored directly too.
 constexpr int BULK_ROWS = 5;            // rows staged per pass (Hy = 4 plus the row-Ny overwrite: one pass)
-constexpr int BULK_NREG = 3;            // destination ranks per chunk served by bulk copies
-constexpr int BULK_RS = PB + 4;         // staging row stride in elements (alignment slack: up to 3 elements)
+constexpr int BULK_NREG = 2;            // destination ranks per chunk served by bulk copies
+constexpr int BULK_CW = 544;            // widest chunk, columns: a 540-column tile (1/12 degree on 8 GPUs) is ONE chunk,
+                                        // i.e. one 4.3 KB transfer per row; wider tiles are cut into equal chunks
+constexpr int BULK_RS = BULK_CW + 4;    // staging row stride in elements (alignment slack: up to 3 elements)
 
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes)
 {
@@ -184,15 +187,15 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uns
 }
 
 template <typename T>
-__device__ __forceinline__ void peer_chunk_push_bulk(const ossg_peer_field& p, const ossg_peer_fold& fd, int chunk, int kk, unsigned char* sraw)
+__device__ __forceinline__ void peer_chunk_push_bulk(const ossg_peer_field& p, const ossg_peer_fold& fd, int chunk, int cw, int kk, unsigned char* sraw)
 {
     constexpr long long A = 16 / sizeof(T);                           // elements per 16 bytes
     T* sb = reinterpret_cast<T*>(sraw);
     const ossg_field_desc& f = p.f;
     const int tx = threadIdx.x;
     const int gNx = fd.gNx, Ny = f.Ny, Hy = f.Hy, Hx = f.Hx;
-    const int c0 = chunk * PB;
-    const int n = min(PB, f.Nx - c0);                                 // source columns c0+1 .. c0+n of this rank
+    const int c0 = chunk * cw;
+    const int n = min(cw, f.Nx - c0);                                 // source columns c0+1 .. c0+n of this rank
     const int sg_lo = fd.i0[fd.me] + c0, sg_hi = sg_lo + n - 1;       // their global indices
     const int cst = f.locx ? gNx + 2 : gNx + 1;                       // destination column = cst - source column
     const int dlo = cst - sg_hi;                                      // destination range, ascending, without the
@@ -206,30 +209,28 @@ __device__ __forceinline__ void peer_chunk_push_bulk(const ossg_peer_field& p, c
     const int nrows = Hy + (center ? 1 : 0);                          // row q < Hy: halo row q; q == Hy: row Ny (:102, :135)
     const size_t sx = (size_t)(f.Nx + 2 * Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
 
-    // this thread's source column and destination
-    const bool active = tx < n;
-    const int isg = sg_lo + tx;
-    double s = f.sign;
-    int idg = cst - isg;
-    bool wrapped = false;
-    if (idg > gNx) { s = fabs(s); idg -= gNx; wrapped = true; }
-    int r = 0;
-#pragma unroll 1
-    for (; r < fd.nranks - 1; ++r)
-        if (idg < fd.i0[r] + fd.nx[r]) break;
-    const size_t sxr = (size_t)(fd.nx[r] + 2 * Hx), sxyr = sxr * (size_t)(Ny + 2 * Hy);
-    T* dstb = static_cast<T*>(const_cast<void*>(p.peer[r])) + (size_t)(f.k0 + kk) * sxyr + (idg - fd.i0[r] + Hx);
-    const T* c = static_cast<const T*>(f.data) + (size_t)(f.k0 + kk) * sxy + (c0 + tx + Hx);
-    const int reg = r - r_lo;
-    const int chi = min(dhi, fd.i0[r] + fd.nx[r] - 1);                // this thread's segment: [clo, chi] on rank r
-    const int clo_halo = max(dlo, fd.i0[r]);
-
 #pragma unroll 1
     for (int q0 = 0; q0 < nrows; q0 += BULK_ROWS) {
         const int nq = min(BULK_ROWS, nrows - q0);
         if (tx < BULK_NREG * BULK_ROWS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
         __syncthreads();
-        if (active) {
+#pragma unroll 1
+        for (int col = tx; col < n; col += PB) {                      // this thread's source columns and their destinations
+            const int isg = sg_lo + col;
+            double s = f.sign;
+            int idg = cst - isg;
+            bool wrapped = false;
+            if (idg > gNx) { s = fabs(s); idg -= gNx; wrapped = true; }
+            int r = 0;
+#pragma unroll 1
+            for (; r < fd.nranks - 1; ++r)
+                if (idg < fd.i0[r] + fd.nx[r]) break;
+            const size_t sxr = (size_t)(fd.nx[r] + 2 * Hx), sxyr = sxr * (size_t)(Ny + 2 * Hy);
+            T* dstb = static_cast<T*>(const_cast<void*>(p.peer[r])) + (size_t)(f.k0 + kk) * sxyr + (idg - fd.i0[r] + Hx);
+            const T* c = static_cast<const T*>(f.data) + (size_t)(f.k0 + kk) * sxy + (c0 + col + Hx);
+            const int reg = r - r_lo;
+            const int chi = min(dhi, fd.i0[r] + fd.nx[r] - 1);        // this column's segment: [clo, chi] on rank r
+            const int clo_halo = max(dlo, fd.i0[r]);
 #pragma unroll 1
             for (int qq = 0; qq < nq; ++qq) {
                 const int q = q0 + qq;
@@ -302,9 +303,9 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
         const ossg_peer_field& p = b.pf[fi];
         const int i = chunk * PB + threadIdx.x + 1;
         if (fd.push == 2) {                                           // (block-uniform)
-            if (chunk * PB < p.f.Nx && kk < p.f.nk) {
-                if (p.f.elem_type == OSSG_F64) peer_chunk_push_bulk<double>(p, fd, chunk, kk, s_bulk);
-                else peer_chunk_push_bulk<float>(p, fd, chunk, kk, s_bulk);
+            if (chunk * b.bulk_cw < p.f.Nx && kk < p.f.nk) {
+                if (p.f.elem_type == OSSG_F64) peer_chunk_push_bulk<double>(p, fd, chunk, b.bulk_cw, kk, s_bulk);
+                else peer_chunk_push_bulk<float>(p, fd, chunk, b.bulk_cw, kk, s_bulk);
             }
             continue;
         }
@@ -552,6 +553,7 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
     if (next != fd.gNx + 1) return set_error(OSSG_EWINDOW, "top-row tiles cover %d columns, global Nx = %d", next - 1, fd.gNx);
     if (!fd.flags_local || reinterpret_cast<uintptr_t>(fd.flags_local) % 8) return set_error(OSSG_EALIGN, "flags_local must be an 8-byte aligned device pointer");
     if (fd.epoch == 0) return set_error(OSSG_EINVAL, "epoch must start at 1 and grow by one per call");
+    if (fd.push < 0 || fd.push > 2) return set_error(OSSG_EINVAL, "push must be 0 (pull), 1 (push) or 2 (bulk push), got %d", fd.push);
     PeerBatch b;
     b.fold = fd;
     b.n = nfields;
@@ -571,6 +573,13 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
             if (!b.pf[k].peer[r]) return set_error(OSSG_EINVAL, "field %d: peer[%d] is NULL", k, r);
         gx = max(gx, ceil_div(f.Nx, PB));
         gy = max(gy, f.nk);
+    }
+    b.bulk_cw = PB;
+    if (fd.push == 2) {                          // equal chunks of at most BULK_CW columns (all fields share this rank's Nx)
+        const int nx = fd.nx[fd.me];
+        const int nch = ceil_div(nx, BULK_CW);
+        b.bulk_cw = ceil_div(nx, nch);
+        gx = nch;
     }
     // partner ranks: owners of the images of this rank's columns under the fold map (an involution,
     // so the relation is symmetric: r is my partner exactly when I am r's)

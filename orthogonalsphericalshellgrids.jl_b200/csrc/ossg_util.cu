@@ -161,3 +161,100 @@ extern "C" int ossg_selftest_sqrt_div(uint64_t n, uint64_t seed, uint64_t mismat
     mismatches[1] = h[1];
     return 0;
 }
+
+// ------------------------------------------------------------------ NVLink store-path probe
+// Kernel-issued copy of `rows` row segments (seg_bytes each, contiguous source) to a destination
+// that is contiguous or laid out like fold rows: row r lands at (r / group) * group_stride +
+// (r % group) * pitch.  Persistent blocks stride over (row, chunk) items.  Modes:
+//   0  one 8-byte load + store per thread (what the push form of the fold does)
+//   1  one 16-byte load + store per thread
+//   2  chunk loaded by the threads into shared memory, ONE bulk store (cp.async.bulk S2G) per chunk
+//   3  bulk load (G2S on an mbarrier) + bulk store: no SM load/store instruction touches the data
+namespace ossg {
+struct ProbeArgs {
+    char* dst; const char* src;
+    unsigned long long rows, group, group_stride, pitch;
+    unsigned seg_bytes, chunk_bytes, chunks_per_row;
+    int mode;
+};
+constexpr int PROBE_MAX_CHUNK = 16384;
+
+__global__ void __launch_bounds__(256, 4) peer_copy_probe_kernel(const ProbeArgs a)
+{
+    __shared__ __align__(128) unsigned char sbuf[PROBE_MAX_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
+    const int t = threadIdx.x;
+    const unsigned long long nitems = a.rows * a.chunks_per_row;
+    unsigned phase = 0;
+    if (a.mode == 3) {
+        if (t == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(&bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const unsigned long long r = item / a.chunks_per_row;
+        const unsigned c = (unsigned)(item - r * a.chunks_per_row);
+        const unsigned off = c * a.chunk_bytes;
+        const unsigned n = min(a.chunk_bytes, a.seg_bytes - off);
+        const char* src = a.src + r * a.seg_bytes + off;
+        char* dst = a.dst + (r / a.group) * a.group_stride + (r % a.group) * a.pitch + off;
+        if (a.mode == 0) {
+            for (unsigned b = t * 8; b < n; b += 256 * 8) *reinterpret_cast<double*>(dst + b) = *reinterpret_cast<const double*>(src + b);
+        } else if (a.mode == 1) {
+            for (unsigned b = t * 16; b < n; b += 256 * 16) *reinterpret_cast<double2*>(dst + b) = *reinterpret_cast<const double2*>(src + b);
+        } else if (a.mode == 2) {
+            if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            for (unsigned b = t * 16; b < n; b += 256 * 16) *reinterpret_cast<double2*>(sbuf + b) = *reinterpret_cast<const double2*>(src + b);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (t == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(sbuf)), "r"(n) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            if (t == 0) {
+                const unsigned ba = (unsigned)__cvta_generic_to_shared(&bar);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ba), "r"(n) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"((unsigned)__cvta_generic_to_shared(sbuf)), "l"(src), "r"(n), "r"(ba) : "memory");
+                unsigned done = 0;
+                const long long t0 = clock64();
+                while (!done) {
+                    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                                 : "=r"(done) : "r"(ba), "r"(phase) : "memory");
+                    if (!done && clock64() - t0 > 2000000000ll) __trap();
+                }
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(sbuf)), "r"(n) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            phase ^= 1;
+        }
+    }
+    if (a.mode >= 2 && t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+}  // namespace ossg
+
+extern "C" int ossg_peer_copy_probe(void* dst, const void* src, uint64_t rows, uint32_t seg_bytes, uint64_t group,
+                                    uint64_t group_stride, uint64_t pitch, uint32_t chunk_bytes, int mode, int blocks, void* stream)
+{
+    if (!dst || !src || rows == 0 || group == 0) return set_error(OSSG_EINVAL, "bad arguments");
+    if (mode < 0 || mode > 3) return set_error(OSSG_EINVAL, "mode must be 0..3");
+    if (seg_bytes == 0 || seg_bytes % 16 || pitch % 16 || group_stride % 16 || chunk_bytes == 0 || chunk_bytes % 16 || chunk_bytes > PROBE_MAX_CHUNK)
+        return set_error(OSSG_EALIGN, "segment, pitch and chunk sizes must be multiples of 16 bytes (chunk <= %d)", PROBE_MAX_CHUNK);
+    if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) return set_error(OSSG_EALIGN, "pointers must be 16-byte aligned");
+    ProbeArgs a;
+    a.dst = static_cast<char*>(dst); a.src = static_cast<const char*>(src);
+    a.rows = rows; a.group = group; a.group_stride = group_stride; a.pitch = pitch;
+    a.seg_bytes = seg_bytes; a.chunk_bytes = chunk_bytes; a.chunks_per_row = (seg_bytes + chunk_bytes - 1) / chunk_bytes;
+    a.mode = mode;
+    if (blocks < 1) blocks = 148 * 4;
+    peer_copy_probe_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a);
+    OSSG_LAUNCH_CHECK("peer_copy_probe_kernel");
+    return 0;
+}
