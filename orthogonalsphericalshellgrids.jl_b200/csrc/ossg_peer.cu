@@ -22,6 +22,7 @@
 #include <mutex>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 #include "ossg_common.cuh"
 
@@ -574,12 +575,24 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
         gx = max(gx, ceil_div(f.Nx, PB));
         gy = max(gy, f.nk);
     }
+    int dev = 0, sms = 0;
+    OSSG_CUDA_TRY(cudaGetDevice(&dev));
+    OSSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long resident = (long long)sms * PEER_BLOCKS_PER_SM;
     b.bulk_cw = PB;
-    if (fd.push == 2) {                          // equal chunks of at most BULK_CW columns (all fields share this rank's Nx)
+    if (fd.push == 2) {
+        // equal chunks (all fields share this rank's Nx): as wide as the staging rows allow -- few, large
+        // transfers -- but at least ~3 work items per resident block so that the persistent blocks finish
+        // together, as long as that keeps a chunk at 256 columns or more
         const int nx = fd.nx[fd.me];
-        const int nch = ceil_div(nx, BULK_CW);
+        const int nch_min = ceil_div(nx, BULK_CW);
+        const int nch_cap = max(nch_min, nx / PB);
+        int waves = 3;                                                // (OSSG_PEER_BULK_WAVES=0: always the widest chunks)
+        if (const char* e = getenv("OSSG_PEER_BULK_WAVES")) waves = atoi(e) < 0 ? 0 : atoi(e);
+        const int nch_bal = ceil_div((long long)waves * resident, (long long)nfields * gy);
+        const int nch = min(max(nch_bal, nch_min), nch_cap);
         b.bulk_cw = ceil_div(nx, nch);
-        gx = nch;
+        gx = ceil_div(nx, b.bulk_cw);
     }
     // partner ranks: owners of the images of this rank's columns under the fold map (an involution,
     // so the relation is symmetric: r is my partner exactly when I am r's)
@@ -600,10 +613,6 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
     b.chunks = gx;
     b.levels = gy;
     b.nitems = (long long)gx * gy * nfields;
-    int dev = 0, sms = 0;
-    OSSG_CUDA_TRY(cudaGetDevice(&dev));
-    OSSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long resident = (long long)sms * PEER_BLOCKS_PER_SM;
     const int grid = (int)(b.nitems < resident ? b.nitems : resident);
     zipper_peer_kernel<<<grid, PB, 0, as_stream(stream)>>>(b);
     OSSG_LAUNCH_CHECK("zipper_peer_kernel");

@@ -422,11 +422,20 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
     from ossg_b200.distributed import local_sizes
     lib_ = ossg._lib
     L = lib_.lib()
-    Ny, Nz, Hx, Hz = 10, 2, 3, 1
-    cases = [(np.float64, 0, 24, 3), (np.float32, 0, 24, 3), (np.float64, 1, 24, 3), (np.float32, 1, 24, 3),
-             (np.float64, 2, 24, 3), (np.float32, 2, 24, 3), (np.float64, 2, 1100, 3), (np.float32, 2, 1100, 6),
-             (np.float64, 2, 1030, 6), (np.float32, 2, 778, 3)]
-    for npdt, push, gNx, Hy in cases:
+    Ny, Hx, Hz = 10, 3, 1
+    # (dtype, form, global Nx, Hy, widest); widest: OSSG_PEER_BULK_WAVES=0, i.e. chunks of up to 544
+    # columns (one chunk per row of a 540-column tile: three columns per thread) instead of the
+    # load-balanced narrower ones
+    Nz = 2
+    cases = [(np.float64, 0, 24, 3, 0), (np.float32, 0, 24, 3, 0), (np.float64, 1, 24, 3, 0), (np.float32, 1, 24, 3, 0),
+             (np.float64, 2, 24, 3, 0), (np.float32, 2, 24, 3, 0), (np.float64, 2, 1100, 3, 0), (np.float32, 2, 1100, 6, 0),
+             (np.float64, 2, 1030, 6, 0), (np.float32, 2, 778, 3, 0), (np.float64, 2, 1080, 4, 1), (np.float32, 2, 1086, 3, 1),
+             (np.float64, 2, 1100, 6, 1)]
+    for npdt, push, gNx, Hy, widest in cases:
+        if widest:
+            _os.environ["OSSG_PEER_BULK_WAVES"] = "0"
+        else:
+            _os.environ.pop("OSSG_PEER_BULK_WAVES", None)
         for Rx in (1, 2, 3, 4) + ((7, 8) if gNx > 24 else ()):
             sx = local_sizes(gNx, Rx)
             starts = [1 + sum(sx[:r]) for r in range(Rx)]
@@ -459,7 +468,8 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
                     for r in range(Rx):
                         got = tiles[k][r].cpu().numpy()[:, :, Hx:Hx + sx[r]]
                         exp = wants[k][:, :, starts[r] - 1 + Hx:starts[r] - 1 + Hx + sx[r]]
-                        assert _same_bits(np.ascontiguousarray(got), np.ascontiguousarray(exp)), (npdt, push, Rx, loc, sign, r, epoch)
+                        assert _same_bits(np.ascontiguousarray(got), np.ascontiguousarray(exp)), (npdt, push, gNx, Rx, loc, sign, r, epoch)
+    _os.environ.pop("OSSG_PEER_BULK_WAVES", None)
 
 
 # ------------------------------------------------------------------ argument errors through the ABI
