@@ -138,21 +138,33 @@ def cpu_construct_rate(threads, steps, warmup):
     return Nx * Ny / dt, dt, what
 
 
-def cpu_zipper_rate(threads):
-    """GB/s of the oracle's zipper fill (1 thread: it is a scalar port) on a 1/4-degree field."""
+def cpu_fill_rates():
+    """The reference's fill_halo_regions! on the host (north_star: "next to it goes the reference's CPU
+    construction and fill_halo_regions!"): the oracle's zipper and zipper + periodic-x fill of c,u,v,zeta
+    on the 1/4 degree fields (1440x720x75, halo 4, FP64; a bounded sample of the 1/12 degree fields, which
+    are 8.1 GB each), one thread -- the oracle is a scalar port of one KA work-item loop."""
     import numpy as np
     from oracle import oracle as orc
     o = orc.Oracle()
     Nx, Ny, Nz, H = 1440, 720, 75, 4
-    c = np.zeros((Nz + 2 * H, Ny + 2 * H, Nx + 2 * H))
-    o.zipper(c, Nx, Ny, Nz, H, H, H, 0, 0, 1)
-    t0 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        o.zipper(c, Nx, Ny, Nz, H, H, H, 0, 0, 1)
-    dt = (time.perf_counter() - t0) / reps
-    nbytes = 2 * H * Nx * Nz * 8 + Nx * Nz * 8
-    return nbytes / dt / 1e9
+    specs = [((0, 0), 1.0), ((1, 0), -1.0), ((0, 1), -1.0), ((1, 1), 1.0)]
+    fields = [np.full((Nz + 2 * H, Ny + 2 * H, Nx + 2 * H), 0.5 + k) for k in range(len(specs))]   # (a fill is a copy: values do not matter)
+    algo = sum(2 * H * Nx * Nz * 8 + (Nx * Nz * 8 if loc[1] == 0 else 0) for loc, _ in specs)
+    rows = (Ny + 2 * H) * (Nz + 2 * H)
+    algo_full = algo + len(specs) * rows * 2 * (2 * H) * 8
+    out = {}
+    for name, fn, b in (("zipper_batch4", o.zipper, algo), ("fill_halo_regions_batch4", o.fill_halo_regions, algo_full)):
+        reps = 3
+        for it in range(reps + 1):
+            if it == 1:
+                t0 = time.perf_counter()
+            for c, (loc, s) in zip(fields, specs):
+                fn(c, Nx, Ny, Nz, H, H, H, loc[0], loc[1], s)
+        dt = (time.perf_counter() - t0) / reps
+        out[name] = {"ms": dt * 1e3, "algorithmic_bytes": b, "gbs": b / dt / 1e9}
+    out.update({"cores": 1, "kind": "port",
+                "sample": f"{Nx}x{Ny}x{Nz} FP64 fields c,u,v,zeta (1/4 degree), CPU restatement of reference v0.2.1"})
+    return out
 
 
 def run_reference(args):
@@ -372,6 +384,8 @@ def run_own(args):
                                "measured_on": "repeat100_zipper_batch8_larger_than_l2" if "what" in best and "8 fields" in best["what"] else "batch4"}
     cpu_threads = os.cpu_count() or 1
     cpu_rate, cpu_dt, cpu_what = cpu_construct_rate(cpu_threads, 3, 1)
+    if world == 1 and isinstance(zipper, dict):
+        zipper["cpu_baseline"] = cpu_fill_rates()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
