@@ -17,6 +17,7 @@
 //   cartesian_nodes_kernel    lat_lon_to_cartesian over a coordinate pair
 // Compile with -fmad=false: see ossg_math.cuh for the determinism contract.
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -333,137 +334,117 @@ __device__ __forceinline__ void store_metric(const BuildArgs& a, int id, size_t 
     static_cast<FT*>(a.metrics_out[id])[o] = (FT)v;
 }
 
-template <typename FT, bool TMA>
-__global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
-                                                             const __grid_constant__ TileMaps tm)
+// The three phases of the tile kernel as inline device functions (shared by metrics_tile_kernel and
+// the mirror-pair variant metrics_tile_pair_kernel below).
+template <bool TMA>
+struct TileSmem {
+    static constexpr int PS = TileGeom<TMA>::PS;
+    double* lam;      // [4][PS]  lambda (degrees)
+    double* phr;      // [4][PS]  phi (degrees) during staging, then deg2rad(phi)/2
+    double* cosp;     // [4][PS]  cos(deg2rad(phi))
+    double* ux;       // [2][PS]  unit vectors: slot 0 = CC, slot 1 = FF
+    double* uy;
+    double* uz;
+    __device__ __forceinline__ explicit TileSmem(double* smem)
+        : lam(smem), phr(smem + 4 * PS), cosp(smem + 8 * PS), ux(smem + 12 * PS), uy(smem + 14 * PS), uz(smem + 16 * PS) {}
+};
+
+// ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers.
+// Thread (tx, ty) copies patch point (tx, ty) of all four patches (one offset computation, the
+// staggering shifts are constants); the first QY + TX threads then copy column TX and row TY.
+// Ends with the wait for the thread's own copies; the caller synchronises the block.
+__device__ __forceinline__ void tile_stage_cp_async(const BuildArgs& a, const Window& w, int It0, int Jt0, int tid, const TileSmem<false>& S)
 {
-    constexpr int QX = TileGeom<TMA>::QX, QPTS = TileGeom<TMA>::QPTS, PS = TileGeom<TMA>::PS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* smem = reinterpret_cast<double*>(TMA ? (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127
-                                                 : reinterpret_cast<uintptr_t>(smem_raw));
-    double* s_lam = smem;                     // [4][PS]  lambda (degrees)
-    double* s_phr = smem + 4 * PS;            // [4][PS]  phi (degrees) during staging, then deg2rad(phi)/2
-    double* s_cos = smem + 8 * PS;            // [4][PS]  cos(deg2rad(phi))
-    double* s_ux = smem + 12 * PS;            // [2][PS]  unit vectors: slot 0 = CC, slot 1 = FF
-    double* s_uy = smem + 14 * PS;
-    double* s_uz = smem + 16 * PS;
-
-    const int tid = threadIdx.y * TX + threadIdx.x;
-    const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
-    const Window w = a.w;
-
-    if (TMA) {
-        // ---- stage the four coordinate patches with the Tensor Memory Accelerator: one thread issues
-        // eight 2-D box loads ((TX+2) x QY doubles each, zero-filled outside the window) that complete
-        // on an mbarrier; no address arithmetic, no load instructions in the other 255 threads.
-        __shared__ __align__(8) unsigned long long s_bar;
-        if (tid == 0) mbar_init(&s_bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(&s_bar, 8u * QPTS * (unsigned)sizeof(double));
+    constexpr int QX = TileGeom<false>::QX, PS = TileGeom<false>::PS;
+    auto stage_point = [&](int pi, int pj) {
+        const int iw = It0 + pi - w.I0, jw = Jt0 + pj - w.J0;
+        const long long o = (long long)jw * w.wnx + iw;
+        const int p = pj * QX + pi;
 #pragma unroll
-            for (int loc = 0; loc < 4; ++loc) {
-                // the box must start on a 16-byte boundary of the row (measured: an odd FP64 column
-                // raises an illegal-instruction fault): start at the even column at or below the
-                // patch; the (TX+2)-wide box still covers the TX+1 columns the patch needs
-                const int x0 = (It0 + patch_di(loc) - w.I0) & ~1, y0 = Jt0 + patch_dj(loc) - w.J0;
-                tma_load_2d(&s_lam[loc * PS], &tm.m[loc], x0, y0, &s_bar);
-                tma_load_2d(&s_phr[loc * PS], &tm.m[4 + loc], x0, y0, &s_bar);
+        for (int loc = 0; loc < 4; ++loc) {
+            const int di = patch_di(loc), dj = patch_dj(loc);
+            const int i2 = iw + di, j2 = jw + dj;
+            if (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny) {
+                const long long o2 = o + (long long)dj * w.wnx + di;
+                cp_async_8(&S.lam[loc * PS + p], a.coords64[loc] + o2);
+                cp_async_8(&S.phr[loc * PS + p], a.coords64[4 + loc] + o2);
+            } else {
+                S.lam[loc * PS + p] = 0.0;
+                S.phr[loc * PS + p] = 0.0;
             }
         }
-        mbar_wait(&s_bar, 0);
-    } else {
-    // ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers.
-    // Thread (tx, ty) copies patch point (tx, ty) of all four patches (one offset computation, the
-    // staggering shifts are constants); the first QY + TX threads then copy column TX and row TY.
-    {
-        auto stage_point = [&](int pi, int pj) {
-            const int iw = It0 + pi - w.I0, jw = Jt0 + pj - w.J0;
-            const long long o = (long long)jw * w.wnx + iw;
-            const int p = pj * QX + pi;
-#pragma unroll
-            for (int loc = 0; loc < 4; ++loc) {
-                const int di = patch_di(loc), dj = patch_dj(loc);
-                const int i2 = iw + di, j2 = jw + dj;
-                if (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny) {
-                    const long long o2 = o + (long long)dj * w.wnx + di;
-                    cp_async_8(&s_lam[loc * PS + p], a.coords64[loc] + o2);
-                    cp_async_8(&s_phr[loc * PS + p], a.coords64[4 + loc] + o2);
-                } else {
-                    s_lam[loc * PS + p] = 0.0;
-                    s_phr[loc * PS + p] = 0.0;
-                }
-            }
-        };
-        stage_point(threadIdx.x, threadIdx.y);
-        if (tid < QY) stage_point(TX, tid);
-        else if (tid < QY + TX) stage_point(tid - QY, TY);
-    }
+    };
+    stage_point(threadIdx.x, threadIdx.y);
+    if (tid < QY) stage_point(TX, tid);
+    else if (tid < QY + TX) stage_point(tid - QY, TY);
     cp_async_wait_all();
-    __syncthreads();
-    }
+}
 
-    // ---- point stage: everything that depends on one point only, once per patch point, in ONE
-    // pass (every task reads and writes its own point only):
-    //   heavy task (CC and FF points, 2 QPTS of them): unit vector + deg2rad(phi)/2 + cos(deg2rad(phi))
-    //   light task (FC and CF points, 2 QPTS of them): deg2rad(phi)/2 + cos(deg2rad(phi))
-    // 32-task chunks are dealt statically so that the warps finish together: heavy chunks round-robin;
-    // the warps that got one heavy chunk fewer share the light chunks (a heavy task costs ~4 light ones).
-    {
-        constexpr int NW = NT / 32, HC = (2 * QPTS + 31) / 32, LC = HC;
-        constexpr int W0 = HC % NW;                        // warps below W0 carry an extra heavy chunk
-        constexpr int NLW = (W0 == 0) ? NW : NW - W0;      // warps sharing the light chunks
-        const int warp = tid >> 5, lane = tid & 31;
+// ---- point stage: everything that depends on one point only, once per patch point, in ONE
+// pass (every task reads and writes its own point only):
+//   heavy task (CC and FF points, 2 QPTS of them): unit vector + deg2rad(phi)/2 + cos(deg2rad(phi))
+//   light task (FC and CF points, 2 QPTS of them): deg2rad(phi)/2 + cos(deg2rad(phi))
+// 32-task chunks are dealt statically so that the warps finish together: heavy chunks round-robin;
+// the warps that got one heavy chunk fewer share the light chunks (a heavy task costs ~4 light ones).
+template <bool TMA>
+__device__ __forceinline__ void tile_point_stage(const TileSmem<TMA>& S, int tid)
+{
+    constexpr int QPTS = TileGeom<TMA>::QPTS, PS = TileGeom<TMA>::PS;
+    constexpr int NW = NT / 32, HC = (2 * QPTS + 31) / 32, LC = HC;
+    constexpr int W0 = HC % NW;                        // warps below W0 carry an extra heavy chunk
+    constexpr int NLW = (W0 == 0) ? NW : NW - W0;      // warps sharing the light chunks
+    const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
-        for (int h = warp; h < HC; h += NW) {
-            const int u = h * 32 + lane;                  // index into the unit-vector arrays
-            if (u < 2 * QPTS) {
-                const int t = u < QPTS ? u : u - QPTS + 3 * PS;   // CC patch, then FF patch
-                const double lat = s_phr[t], lon = s_lam[t];
-                bool bad = false;
-                Vec3 v = lat_lon_to_cartesian_spec(lat, lon, bad);
-                if (bad) v = lat_lon_to_cartesian_ool(lat, lon);
-                const int us = u < QPTS ? u : u - QPTS + PS;
-                s_ux[us] = v.x;
-                s_uy[us] = v.y;
-                s_uz[us] = v.z;
-                const double phr = lat * D2R;
-                s_phr[t] = 0.5 * phr;                     // the haversines want deg2rad(phi)/2
-                s_cos[t] = m::cos_rad_inl(phr);
-            }
-        }
-        if (W0 == 0 || warp >= W0) {
-#pragma unroll 1
-            for (int l = (W0 == 0 ? warp : warp - W0); l < LC; l += NLW) {
-                const int v = l * 32 + lane;              // FC patch, then CF patch
-                const int t = v < QPTS ? PS + v : 2 * PS + (v - QPTS);
-                if (v < 2 * QPTS) {
-                    const double phr = s_phr[t] * D2R;
-                    s_phr[t] = 0.5 * phr;
-                    s_cos[t] = m::cos_rad_inl(phr);
-                }
-            }
+    for (int h = warp; h < HC; h += NW) {
+        const int u = h * 32 + lane;                  // index into the unit-vector arrays
+        if (u < 2 * QPTS) {
+            const int t = u < QPTS ? u : u - QPTS + 3 * PS;   // CC patch, then FF patch
+            const double lat = S.phr[t], lon = S.lam[t];
+            bool bad = false;
+            Vec3 v = lat_lon_to_cartesian_spec(lat, lon, bad);
+            if (bad) v = lat_lon_to_cartesian_ool(lat, lon);
+            const int us = u < QPTS ? u : u - QPTS + PS;
+            S.ux[us] = v.x;
+            S.uy[us] = v.y;
+            S.uz[us] = v.z;
+            const double phr = lat * D2R;
+            S.phr[t] = 0.5 * phr;                     // the haversines want deg2rad(phi)/2
+            S.cosp[t] = m::cos_rad_inl(phr);
         }
     }
-    __syncthreads();
+    if (W0 == 0 || warp >= W0) {
+#pragma unroll 1
+        for (int l = (W0 == 0 ? warp : warp - W0); l < LC; l += NLW) {
+            const int v = l * 32 + lane;              // FC patch, then CF patch
+            const int t = v < QPTS ? PS + v : 2 * PS + (v - QPTS);
+            if (v < 2 * QPTS) {
+                const double phr = S.phr[t] * D2R;
+                S.phr[t] = 0.5 * phr;
+                S.cosp[t] = m::cos_rad_inl(phr);
+            }
+        }
+    }
+}
 
-    const int ci = blockIdx.x * TX + threadIdx.x, cj = blockIdx.y * TY + threadIdx.y;
-    if (ci >= fr.nx || cj >= fr.ny) return;
+// ---- cell stage, speculative straight-line form: the 8 haversines and 2 quadrilaterals are
+// evaluated through their hot sequences in ONE basic block (branch-free sqrt / division, short
+// atan), so ptxas interleaves the independent chains; `bad` collects every violated
+// precondition (spacing above ~1.8 degrees, pole neighbourhoods, degenerate cells, NaN).  A bad
+// cell is recomputed through the general functions below; its speculative stores are
+// overwritten by the same thread.
+//   o        element offset of the cell in the window arrays
+//   shC/shF  TMA staging only: a patch whose first column is odd sits one column to the right in its box
+template <typename FT, bool TMA>
+__device__ __forceinline__ void tile_cell_stage(const BuildArgs& a, const TileSmem<TMA>& S, int tx, int ty, size_t o, int shC, int shF)
+{
+    constexpr int QX = TileGeom<TMA>::QX, PS = TileGeom<TMA>::PS;
+    double* const s_lam = S.lam; double* const s_phr = S.phr; double* const s_cos = S.cosp;
+    double* const s_ux = S.ux; double* const s_uy = S.uy; double* const s_uz = S.uz;
     const double R = a.radius;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
     // patch index of this cell's own point per staggering (index = loc)
-    // (TMA staging: a patch whose first column is odd sits one column to the right in its box)
-    const int shC = TMA ? ((It0 - 1 - w.I0) & 1) : 0, shF = TMA ? ((It0 - w.I0) & 1) : 0;
     const int own_cc = (ty + 1) * QX + tx + 1 + shC, own_fc = (ty + 1) * QX + tx + shF;
     const int own_cf = ty * QX + tx + 1 + shC, own_ff = ty * QX + tx + shF;
 
-    // ---- cell stage, speculative straight-line form: the 8 haversines and 2 quadrilaterals are
-    // evaluated through their hot sequences in ONE basic block (branch-free sqrt / division, short
-    // atan), so ptxas interleaves the independent chains; `bad` collects every violated
-    // precondition (spacing above ~1.8 degrees, pole neighbourhoods, degenerate cells, NaN).  A bad
-    // cell is recomputed through the general functions below; its speculative stores are
-    // overwritten by the same thread.
     const double R2 = 2 * R, RR = R * R;
     bool bad = false;
 #define PT(L, p) s_lam[(L) * PS + (p)], s_phr[(L) * PS + (p)], s_cos[(L) * PS + (p)]
@@ -520,6 +501,201 @@ __global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __gri
     }
 #undef PT
 #undef UV
+}
+
+template <typename FT, bool TMA>
+__global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
+                                                             const __grid_constant__ TileMaps tm)
+{
+    constexpr int QPTS = TileGeom<TMA>::QPTS, PS = TileGeom<TMA>::PS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(TMA ? (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127
+                                                 : reinterpret_cast<uintptr_t>(smem_raw));
+    const TileSmem<TMA> S(smem);
+
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
+    const Window w = a.w;
+
+    if constexpr (TMA) {
+        // ---- stage the four coordinate patches with the Tensor Memory Accelerator: one thread issues
+        // eight 2-D box loads ((TX+2) x QY doubles each, zero-filled outside the window) that complete
+        // on an mbarrier; no address arithmetic, no load instructions in the other 255 threads.
+        __shared__ __align__(8) unsigned long long s_bar;
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, 8u * QPTS * (unsigned)sizeof(double));
+#pragma unroll
+            for (int loc = 0; loc < 4; ++loc) {
+                // the box must start on a 16-byte boundary of the row (measured: an odd FP64 column
+                // raises an illegal-instruction fault): start at the even column at or below the
+                // patch; the (TX+2)-wide box still covers the TX+1 columns the patch needs
+                const int x0 = (It0 + patch_di(loc) - w.I0) & ~1, y0 = Jt0 + patch_dj(loc) - w.J0;
+                tma_load_2d(&S.lam[loc * PS], &tm.m[loc], x0, y0, &s_bar);
+                tma_load_2d(&S.phr[loc * PS], &tm.m[4 + loc], x0, y0, &s_bar);
+            }
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        tile_stage_cp_async(a, w, It0, Jt0, tid, S);
+        __syncthreads();
+    }
+
+    tile_point_stage<TMA>(S, tid);
+    __syncthreads();
+
+    const int ci = blockIdx.x * TX + threadIdx.x, cj = blockIdx.y * TY + threadIdx.y;
+    if (ci >= fr.nx || cj >= fr.ny) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
+    const int shC = TMA ? ((It0 - 1 - w.I0) & 1) : 0, shF = TMA ? ((It0 - w.I0) & 1) : 0;
+    tile_cell_stage<FT, TMA>(a, S, tx, ty, o, shC, shF);
+}
+
+// ------------------------------------------------------------------ K2 (mirror pairs; opt-in, OSSG_TILE_PAIRS=1)
+// The map is mirror symmetric about the pole meridians: with c = Nx/2 + 1 the x-Center points of
+// post-shift columns i and c - i (mod Nx) and the x-Face points of i and c + 1 - i carry the same
+// latitude bit for bit (generate_tripolar_coordinates.jl:67-78: x changes sign, y does not), in every
+// row including the fold row Ny.  About 70 % of the point stage depends on the latitude only
+// (sind/cosd(phi) of the unit vectors, cos(deg2rad(phi)) of the haversines), so a tile A and its
+// mirror tile B need those values only once.  The two tiles form a thread-block cluster of two CTAs:
+// each computes the latitude part for its own lower half of the shared patch columns and stores the
+// results into BOTH shared memories (distributed shared memory), after checking that the partner
+// really holds the same latitude bits (ossg_tripolar_metrics accepts any coordinates); a mismatch --
+// or a point outside the straight-line preconditions -- raises a flag and the CTA falls back to the
+// ordinary point stage.  The longitude part, the products and the cell stage are unchanged.
+//   x-Center patches (CC, CF: columns It0-1 .. It0+nt-1 -> px = 0 .. nt):  px <-> nt + 1 - px  (px = 0 has no partner)
+//   x-Face   patches (FF, FC: columns It0   .. It0+nt   -> px = 0 .. nt):  px <-> nt - px
+// Requires a window that spans x and Nx % 4 == 0 (each quarter of the columns is a run of A tiles
+// whose mirrors fill the next quarter).
+__device__ __forceinline__ long long f64_bits(double x) { return __double_as_longlong(x); }
+
+template <typename FT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, TILE_CTAS)
+metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
+{
+    constexpr int QX = TileGeom<false>::QX, QPTS = TileGeom<false>::QPTS, PS = TileGeom<false>::PS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TileSmem<false> S(reinterpret_cast<double*>(smem_raw));
+    __shared__ int s_flag;
+
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int member = (int)cluster.block_rank();             // 0: tile A, 1: its mirror tile B
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int Nx = a.g.Nx, q4 = Nx / 4;
+    const int nts = (q4 + TX - 1) / TX;                       // A tiles per quarter
+    const int pair = blockIdx.x >> 1;
+    const int seg = pair / nts, k = pair - seg * nts;
+    const int acol = seg * (Nx / 2) + 1 + k * TX;             // first column of tile A
+    const int nt = min(TX, q4 - k * TX);                      // columns of this pair's tiles
+    const int bcol = seg * Nx + Nx / 2 + 1 - (acol + nt - 1); // first column of tile B: column acol+t <-> bcol+nt-1-t
+    const int It0 = member ? bcol : acol, Jt0 = fr.J0 + blockIdx.y * TY;
+    const Window w = a.w;
+
+    if (tid == 0) s_flag = 0;
+    tile_stage_cp_async(a, w, It0, Jt0, tid, S);
+    cluster.sync();                                           // both patches staged, both flags cleared
+
+    // ---- latitude part.  This CTA computes columns 0 .. hC of its x-Center patches and 0 .. gF of its
+    // x-Face patches (in its own indexing); the partner computes the rest and stores it here.
+    {
+        const int hC = member ? nt / 2 : (nt + 1) / 2;
+        const int gF = member ? (nt - 1) / 2 : nt / 2;
+        const int nC = hC + 1, nF = gF + 1;
+        const int ntask = (nC + nF) * QY;                     // heavy tasks (CC, FF); as many light ones (CF, FC)
+        const unsigned other = (unsigned)(member ^ 1);
+        double* const r_phr = cluster.map_shared_rank(S.phr, other);
+        double* const r_cos = cluster.map_shared_rank(S.cosp, other);
+        double* const r_ux = cluster.map_shared_rank(S.ux, other);
+        double* const r_uz = cluster.map_shared_rank(S.uz, other);
+        int* const r_flag = cluster.map_shared_rank(&s_flag, other);
+        // task u -> patch point: x-Center patch first (nC columns per row), then the x-Face patch
+        auto locate = [&](int u, bool& face, int& idx, int& idxr, bool& shared) {
+            face = u >= nC * QY;
+            const int v = face ? u - nC * QY : u, ncol = face ? nF : nC;
+            const int py = v / ncol, px = v - py * ncol;
+            idx = py * QX + px;
+            shared = face || px >= 1;
+            idxr = py * QX + (face ? nt - px : nt + 1 - px);
+        };
+        const int NW = NT / 32, nchunk = (ntask + 31) / 32, W0 = nchunk % NW;
+        const int NLW = (W0 == 0) ? NW : NW - W0;
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+        for (int h = warp; h < nchunk; h += NW) {             // heavy: sind/cosd(phi) and cos(deg2rad(phi)) of a CC / FF point
+            const int u = h * 32 + lane;
+            if (u < ntask) {
+                bool face, shared; int idx, idxr;
+                locate(u, face, idx, idxr, shared);
+                const int t = (face ? FF : CC) * PS + idx, us = (face ? PS : 0) + idx;
+                const double lat = S.phr[t];
+                bool bad = false;
+                double sn, cs;
+                m::sincosd_lat_spec(lat, sn, cs, bad);
+                const double cphi = m::cos_rad_inl(lat * D2R);
+                S.uz[us] = sn;
+                S.ux[us] = cs;                                // (cosd(phi) until the longitude part multiplies it)
+                S.cosp[t] = cphi;
+                if (bad) s_flag = 1;
+                if (shared) {
+                    const int tr = (face ? FF : CC) * PS + idxr, ur = (face ? PS : 0) + idxr;
+                    if (!bad && f64_bits(r_phr[tr]) == f64_bits(lat)) { r_uz[ur] = sn; r_ux[ur] = cs; r_cos[tr] = cphi; }
+                    else *r_flag = 1;
+                }
+            }
+        }
+        if (W0 == 0 || warp >= W0) {
+#pragma unroll 1
+            for (int l = (W0 == 0 ? warp : warp - W0); l < nchunk; l += NLW) {   // light: cos(deg2rad(phi)) of a CF / FC point
+                const int u = l * 32 + lane;
+                if (u < ntask) {
+                    bool face, shared; int idx, idxr;
+                    locate(u, face, idx, idxr, shared);
+                    const int t = (face ? FC : CF) * PS + idx;
+                    const double lat = S.phr[t];
+                    const double cphi = m::cos_rad_inl(lat * D2R);
+                    S.cosp[t] = cphi;
+                    if (shared) {
+                        const int tr = (face ? FC : CF) * PS + idxr;
+                        if (f64_bits(r_phr[tr]) == f64_bits(lat)) r_cos[tr] = cphi;
+                        else *r_flag = 1;
+                    }
+                }
+            }
+        }
+    }
+    cluster.sync();                                           // the partner's half has arrived; no remote access after this point
+
+    // ---- longitude part and products, every patch point of this CTA
+#pragma unroll 1
+    for (int u = tid; u < 2 * QPTS; u += NT) {
+        const int t = u < QPTS ? u : u - QPTS + 3 * PS;       // CC patch, then FF patch
+        const int us = u < QPTS ? u : u - QPTS + PS;
+        const int t2 = u < QPTS ? PS + u : 2 * PS + (u - QPTS);   // the FC / CF point with the same index
+        bool bad = false;
+        double sl, cl;
+        m::sincosd_lon_spec(S.lam[t], sl, cl, bad);
+        const double cs = S.ux[us];
+        S.ux[us] = cl * cs;
+        S.uy[us] = sl * cs;
+        S.phr[t] = 0.5 * (S.phr[t] * D2R);                    // the haversines want deg2rad(phi)/2
+        S.phr[t2] = 0.5 * (S.phr[t2] * D2R);
+        if (bad) s_flag = 1;
+    }
+    __syncthreads();
+    if (s_flag) {                                             // (block-uniform) the ordinary point stage on a fresh patch
+        tile_stage_cp_async(a, w, It0, Jt0, tid, S);
+        __syncthreads();
+        tile_point_stage<false>(S, tid);
+        __syncthreads();
+    }
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (tx >= nt || blockIdx.y * TY + ty >= fr.ny) return;
+    const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
+    tile_cell_stage<FT, false>(a, S, tx, ty, o, 0, 0);
 }
 
 // ------------------------------------------------------------------ K2f (frame)
@@ -774,7 +950,20 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         // OSSG_TILE_STAGING=tma.
         const char* staging = getenv("OSSG_TILE_STAGING");
         const bool want_tma = OSSG_USE_TMA || (staging && strcmp(staging, "tma") == 0);
-        if (want_tma && make_tile_maps(a, tm)) {
+        // Mirror-pair variant (clusters of two CTAs sharing the latitude part of the point stage):
+        // written at the end of round 1 and not yet measured, hence opt-in: OSSG_TILE_PAIRS=1.
+        const char* pairs = getenv("OSSG_TILE_PAIRS");
+        const bool want_pairs = pairs && strcmp(pairs, "1") == 0 && !want_tma && fr.I0 == 1 && fr.nx == a.g.Nx && a.g.Nx % 4 == 0;
+        if (want_pairs) {
+            static bool pair_attr_set[2] = { false, false };
+            if (!pair_attr_set[which]) {
+                OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_pair_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<false>::SMEM_BYTES));
+                pair_attr_set[which] = true;
+            }
+            const int nts = ceil_div(a.g.Nx / 4, TX);
+            dim3 pgrid(4 * nts, ceil_div(fr.ny, TY));            // 2 quarters of A tiles x nts pairs x 2 members
+            metrics_tile_pair_kernel<FT><<<pgrid, block, TileGeom<false>::SMEM_BYTES, s>>>(a, fr);
+        } else if (want_tma && make_tile_maps(a, tm)) {
             metrics_tile_kernel<FT, true><<<grid, block, TileGeom<true>::SMEM_BYTES, s>>>(a, fr, tm);
         } else {
             memset(&tm, 0, sizeof(tm));

@@ -530,6 +530,57 @@ def test_cartesian_nodes_and_orthogonality_on_gpu(ossg, oracle):
     assert float(ang[~masked[1:-1, 1:-1]].abs().max()) < 0.01
 
 
+def test_mirror_pair_tile_kernel_matches_oracle():
+    """The opt-in mirror-pair form of the tile kernel (OSSG_TILE_PAIRS=1: clusters of two CTAs that
+    share the latitude part of the point stage through distributed shared memory) in a fresh process:
+    FP64 and FP32 grids incl. one whose tiles are all partial (Nx/4 < 32), a Y-slab window, and the
+    staged metrics entry point fed with glibc-libm coordinates, whose latitudes are NOT mirror
+    symmetric bit for bit -- every CTA must then notice and fall back to the ordinary point stage."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+import ossg_b200 as ossg
+from oracle import oracle as orc
+from ossg_b200.grids import build_arrays, make_params
+o = orc.Oracle(); o.set_threads(o.max_threads())
+for size, dt, npdt in (((360, 180, 1), ossg.Float64, np.float64), ((1440, 720, 1), ossg.Float64, np.float64),
+                       ((60, 30, 1), ossg.Float64, np.float64), ((1000, 300, 1), ossg.Float64, np.float64),
+                       ((360, 180, 1), ossg.Float32, np.float32)):
+    g = ossg.TripolarGrid(ossg.GPU(), dt, size=size)
+    ref = o.build(orc.make_params(size, (4, 4, 4)), dtype=npdt)
+    for n in orc.ALL_NAMES:
+        assert np.array_equal(g.arrays[n].parent.cpu().numpy().view(np.uint8), ref[n].view(np.uint8)), (size, n)
+ref = o.build(orc.make_params((1440, 720, 1), (4, 4, 4)))
+p = make_params((1440, 720, 1), (4, 4, 4), -80, 55, 70, orc.R_EARTH, tile=(1, 361, 1440, 360))
+for n, t in zip(orc.ALL_NAMES, build_arrays(p, torch.float64, torch.device('cuda', 0))):
+    assert np.array_equal(t.cpu().numpy().view(np.uint8), np.ascontiguousarray(ref[n][360:360 + 368, :]).view(np.uint8)), n
+# staged metrics from libm coordinates (a different last-ulp rounding of every coordinate)
+ol = orc.Oracle(libm=True)
+size = (360, 180, 1)
+po = orc.make_params(size, (4, 4, 4))
+coords = ol.coords(po)
+want = o.metrics(po, coords)
+L = ossg._lib.lib(); dev = torch.device('cuda', 0)
+params = make_params(size, (4, 4, 4), -80, 55, 70, orc.R_EARTH)
+cin = [torch.as_tensor(coords[n], device=dev).contiguous() for n in orc.COORD_NAMES]
+out = [torch.empty_like(cin[0]) for _ in range(12)]
+ws = torch.empty(L.ossg_tripolar_workspace_bytes(C.byref(params), 0), dtype=torch.uint8, device=dev)
+ossg._lib.check(L.ossg_tripolar_metrics(C.byref(params), ossg._lib.ptr_array([t.data_ptr() for t in cin]), 0,
+                                        ossg._lib.ptr_array([t.data_ptr() for t in out]), ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+for n, t in zip(orc.METRIC_NAMES, out):
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), want[n].view(np.uint64)), n
+print('pairs ok')
+""" % (ROOT, ROOT)
+    env = dict(os.environ, OSSG_TILE_PAIRS="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "pairs ok" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
 def test_tma_staging_of_the_tile_kernel_matches_oracle():
     """The opt-in TMA staging of metrics_tile_kernel (OSSG_TILE_STAGING=tma, UTMALDG box loads on an
     mbarrier) in a fresh process: FP64 and FP32 grids and a tile window, bit for bit."""
