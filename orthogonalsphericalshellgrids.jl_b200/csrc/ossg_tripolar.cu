@@ -151,7 +151,19 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
 // 1-D grid of coords_pair_kernel: the pair rows (J = 1..Ny-1) need Nx/2 + 1 + 2Hx threads, the other
 // rows one thread per padded element; a 2-D grid sized for the latter would launch an empty
 // second half for every pair row.
-struct PairGrid { int jw_lo, n_pair_rows, chunks_pair, chunks_full; };
+struct PairGrid {
+    int jw_lo, n_pair_rows, chunks_pair, chunks_full;
+#ifdef OSSG_COORD_MAGIC_DIV
+    // experiment (not measured yet): ceil(2^40 / chunks) -- b / chunks == (b * magic) >> 40 for b * chunks < 2^40,
+    // three instructions instead of the ~25 of an integer division in every block's prologue
+    unsigned long long magic_pair, magic_full;
+#endif
+};
+#ifdef OSSG_COORD_MAGIC_DIV
+__device__ __forceinline__ int magic_div(int b, int d, unsigned long long magic) { (void)d; return (int)(((unsigned long long)(unsigned)b * magic) >> 40); }
+#else
+__device__ __forceinline__ int magic_div(int b, int d, unsigned long long) { return b / d; }
+#endif
 
 template <typename FT>
 __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
@@ -159,18 +171,29 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
     int jw, chunk;
     {
         const int b = blockIdx.x, nb_pair = pg.n_pair_rows * pg.chunks_pair;
+#ifdef OSSG_COORD_MAGIC_DIV
+        const unsigned long long mp = pg.magic_pair, mf = pg.magic_full;
+#else
+        const unsigned long long mp = 0, mf = 0;
+#endif
         if (b < nb_pair) {
-            const int r = b / pg.chunks_pair;
+            const int r = magic_div(b, pg.chunks_pair, mp);
             jw = pg.jw_lo + r;
             chunk = b - r * pg.chunks_pair;
         } else {
-            const int r = (b - nb_pair) / pg.chunks_full;
+            const int r = magic_div(b - nb_pair, pg.chunks_full, mf);
             chunk = (b - nb_pair) - r * pg.chunks_full;
             jw = r < pg.jw_lo ? r : r + pg.n_pair_rows;
         }
     }
+#ifdef OSSG_ATAN_RANGE_TABLE
+    __shared__ double s_atan[30 + 11];                       // atan reduction table + 88 bytes of range table (ossg_math.cuh)
+    if (threadIdx.x < 30) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
+    else if (threadIdx.x < 30 + 88) reinterpret_cast<unsigned char*>(s_atan + 30)[threadIdx.x - 30] = m::kATAN_RANGE[threadIdx.x - 30];
+#else
     __shared__ double s_atan[30];                            // atan reduction table (ossg_math.cuh)
     if (threadIdx.x < 30) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
+#endif
     __syncthreads();
     const int t = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
@@ -839,6 +862,10 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
         pg.chunks_pair = ceil_div(a.g.Nx / 2 + 1 + 2 * a.g.Hx, 256);
         pg.chunks_full = ceil_div(a.w.wnx, 256);
         const long long nb = (long long)pg.n_pair_rows * pg.chunks_pair + (long long)(a.w.wny - pg.n_pair_rows) * pg.chunks_full;
+#ifdef OSSG_COORD_MAGIC_DIV
+        pg.magic_pair = ((1ull << 40) + pg.chunks_pair - 1) / pg.chunks_pair;     // (nb < 2^31 and chunks < 2^9 keep b * chunks below 2^40)
+        pg.magic_full = ((1ull << 40) + pg.chunks_full - 1) / pg.chunks_full;
+#endif
         coords_pair_kernel<FT><<<(unsigned)nb, block, 0, s>>>(a, pg);
         OSSG_LAUNCH_CHECK("coords_pair_kernel");
     } else {
