@@ -43,6 +43,17 @@ def test_struct_layouts_match_the_header(ossg):
                                                            L_.PeerField, L_.PeerHaloDesc, L_.PeerHaloField)]
 
 
+def test_constants_match_the_header(ossg):
+    # the #define'd limits and codes of include/ossg_b200.h against their ctypes mirror
+    import re
+    text = open(ossg._lib.HEADER_PATH).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(OSSG_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", text)}
+    for name in ("OSSG_MAX_PEERS", "OSSG_MAX_PEER_BATCH", "OSSG_CENTER", "OSSG_FACE", "OSSG_F64", "OSSG_F32",
+                 "OSSG_EINVAL", "OSSG_EODD_NX", "OSSG_EHALO", "OSSG_EWINDOW", "OSSG_EALIGN", "OSSG_ELOCATION", "OSSG_EWORKSPACE"):
+        assert name in defs, name
+        assert defs[name] == getattr(ossg._lib, name), name
+
+
 def test_argument_errors_do_not_need_a_device(ossg):
     """Validation happens before any CUDA call: same messages the reference throws."""
     from ossg_b200.grids import make_params
