@@ -315,7 +315,7 @@ def run_own(args):
 
     # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels)
     ms = C.c_float(); fl = C.c_double()
-    _lib.check(L.ossg_fp64_peak_probe(20000, C.byref(ms), C.byref(fl), stream.cuda_stream))
+    _lib.check_util(_lib.testutil().ossg_fp64_peak_probe(20000, C.byref(ms), C.byref(fl), stream.cuda_stream))
     fp64_peak_tflops = fl.value / (ms.value * 1e-3) / 1e12
 
     # ---- zipper halo fill (second half of the metric): 4 fields c,u,v,zeta on the local tile
@@ -425,7 +425,7 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
         _lib.FieldDesc(t.data_ptr(), _lib.OSSG_F64, nx, ny, Nz, H, H, H, loc[0], loc[1], 0, 0, s)
         for t, (loc, s) in zip(fields, specs)])
     for k in range(len(specs)):
-        _lib.check(L.ossg_synth_field(C.byref(descs[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
+        _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(descs[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     algo = 0
     for (loc, _) in specs:
@@ -501,7 +501,7 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
             _lib.FieldDesc(t.data_ptr(), _lib.OSSG_F64, nx, ny, Nz, H, H, H, loc[0], loc[1], 0, 0, s)
             for t, (loc, s) in zip(fields + more, specs + specs)])
         for k in range(4, 8):
-            _lib.check(L.ossg_synth_field(C.byref(descs8[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
+            _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(descs8[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
         for _ in range(5):
             _lib.check(L.ossg_zipper_fill_batch(descs8, 8, stream.cuda_stream))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -546,7 +546,7 @@ def bench_fold_exchange(world, rank, dev):
     L = _lib.lib()
     for k, f in enumerate(all_fields):
         d = f.descriptor()
-        _lib.check(L.ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
     for _ in range(3):
         fold_exchange(fields)
     torch.cuda.synchronize(dev)
@@ -636,7 +636,7 @@ def bench_distributed_fill(world, rank, dev):
     L = _lib.lib()
     for k, f in enumerate(fields):
         d = f.descriptor()
-        _lib.check(L.ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
     reps = 10
 
     def timed(fn):

@@ -42,6 +42,8 @@ extern "C" {
 #define OSSG_EALIGN      (-5)   /* device pointer not aligned to its element size                */
 #define OSSG_ELOCATION   (-6)   /* location code not 0 (Center) / 1 (Face)                       */
 #define OSSG_EWORKSPACE  (-7)   /* workspace too small                                           */
+#define OSSG_ENCCL       (-8)   /* libnccl.so.2 missing, or an NCCL call failed (message has the ncclResult_t) */
+#define OSSG_ETIMEOUT    (-9)   /* a peer-memory exchange of this rank gave up waiting for a partner */
 
 /* staggering codes: Oceananigans Center / Face */
 #define OSSG_CENTER 0
@@ -95,6 +97,19 @@ int         ossg_device_ok(void);               /* 0 iff a CUDA device of comput
  * are always computed from FP64 coordinates and rounded once at the end,
  * src/tripolar_grid.jl:308-328).                                                               */
 size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, int out_type);
+
+/* The workspace starts with a 128-byte header and the 1-D tables (ossg_tripolar_table_bytes() bytes in
+ * all).  The header holds validity stamps: a later build / coords / metrics call with the same
+ * workspace and the same (Nx, Ny, southernmost_latitude, north_poles_latitude) finds the x/y tables
+ * in place and does not recompute them (likewise the lat-lon rows for the same Hy and radius) --
+ * the fast path of with_halo and reconstruct_global_grid (src/with_halo.jl:5-44,
+ * src/distributed_tripolar_grid.jl:201-226), which re-run the constructor with other halos.
+ * Contract: call ossg_tripolar_workspace_init once after allocating a workspace (it zeroes the header,
+ * asynchronously on `stream`); do not write into the first ossg_tripolar_table_bytes() bytes between
+ * calls; one workspace serves one stream at a time.  To carry the tables over to a larger workspace
+ * (new halo), copy its first ossg_tripolar_table_bytes() bytes device-to-device.                  */
+int    ossg_tripolar_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+size_t ossg_tripolar_table_bytes(const ossg_tripolar_params* p);
 
 /* all 20 arrays; out[k] (k = OSSG_LAM_CC ...) has (nx+2Hx)(ny+2Hy) elements of out_type */
 int ossg_tripolar_build(const ossg_tripolar_params* p, int out_type, void* const out[20],
@@ -170,6 +185,55 @@ typedef struct ossg_fold_window {
 size_t ossg_fold_buffer_elems(const ossg_field_desc* f, const ossg_fold_window* w);
 int ossg_fold_pack(const ossg_field_desc* f, const ossg_fold_window* w, void* buffer, void* stream);
 int ossg_fold_unpack(const ossg_field_desc* f, const ossg_fold_window* w, const void* buffer, void* stream);
+
+/* ---- (x, y)-partitioned fold and ordinary halos through NCCL send/recv ----------------------- *
+ * north_star: "ordinary halos and the fold-partner exchange between mirror ranks in the top row go
+ * through NCCL send/recv over NVLink, replacing MPI".  Replaces, for a field whose north boundary is
+ * a ZipperBoundaryCondition on a Distributed grid, the communication that Oceananigans' distributed
+ * fill_halo_regions! performs with MPI (fold: src/zipper_boundary_condition.jl:70-155 applied across
+ * ranks; partition: src/distributed_tripolar_grid.jl:41-49, generalised from Y slabs to (x, y)).
+ *
+ * `nccl_comm` is the caller's ncclComm_t spanning all Rx*Ry ranks, rank r at (rx, ry) = (r / Ry,
+ * r % Ry) (Oceananigans' rank2index), tiles by the reference's rule (equal parts, the last rank takes
+ * the remainder).  `fields` are the LOCAL fields (Nx, Ny = this rank's tile), at most
+ * OSSG_MAX_PEER_BATCH per call.  One call enqueues on `stream`:
+ *   ossg_fold_exchange:  one pack kernel, one ncclGroup with one ncclSend + ncclRecv per partner
+ *                        rank (all fields and levels of the batch in one message), one unpack kernel
+ *                        (i-reversal and sign applied on the way out).  Ranks below the top row return 0.
+ *   ossg_halo_exchange:  south/north rows (whole rows), then west/east columns over the whole y extent,
+ *                        periodic in x (a local copy when Rx == 1): pack, group, unpack per phase.
+ * The workspace is caller-provided, persistent device memory of at least the *_workspace_bytes()
+ * size (0 when the rank has nothing to exchange); the library allocates nothing and never
+ * synchronises.  NCCL is resolved at run time from the libnccl.so.2 already loaded in the process.
+ * Every rank must make the matching call with the same field list.                              */
+typedef struct ossg_exchange_layout {
+    int32_t gNx, gNy;               /* global size[1], size[2]                                   */
+    int32_t Rx, Ry;                 /* Partition(x, y)                                           */
+    int32_t rank;                   /* this rank in nccl_comm                                    */
+    int32_t reserved;
+} ossg_exchange_layout;
+
+size_t ossg_fold_exchange_workspace_bytes(const ossg_field_desc* fields, int nfields, const ossg_exchange_layout* layout);
+int    ossg_fold_exchange(void* nccl_comm, const ossg_field_desc* fields, int nfields, const ossg_exchange_layout* layout,
+                          void* workspace, size_t workspace_bytes, void* stream);
+size_t ossg_halo_exchange_workspace_bytes(const ossg_field_desc* fields, int nfields, const ossg_exchange_layout* layout);
+int    ossg_halo_exchange(void* nccl_comm, const ossg_field_desc* fields, int nfields, const ossg_exchange_layout* layout,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* the messages of one fold exchange, identical on every rank (host only, no device needed): entry q
+ * says that rank src_rank sends global source columns [src_i0, src_i0+n) of field `field`, `rows`
+ * rows per level, to rank dst_rank.  Returns the number of messages (fills at most `capacity`).  */
+typedef struct ossg_fold_segment {
+    int32_t field, src_rank, dst_rank, src_i0, n, rows, wrapped, reserved;
+} ossg_fold_segment;
+int ossg_fold_exchange_plan(const ossg_field_desc* fields, int nfields, const ossg_exchange_layout* layout,
+                            ossg_fold_segment* out, int capacity);
+
+/* communicator helpers for hosts without their own NCCL binding (thin wrappers of ncclGetUniqueId /
+ * ncclCommInitRank / ncclCommDestroy); a Julia host passes NCCL.jl's communicator handle instead */
+int ossg_nccl_get_unique_id(unsigned char id[128]);
+int ossg_nccl_comm_init_rank(void** comm, int nranks, const unsigned char id[128], int rank);
+int ossg_nccl_comm_destroy(void* comm);
 
 /* ---- (x, y)-partitioned fold over NVLink peer memory: ONE kernel per rank, no staging ------- *
  * B200-native form of the exchange above for ranks of one NVSwitch node.  Every top-row rank maps
@@ -256,24 +320,6 @@ typedef struct ossg_peer_halo_field {
 } ossg_peer_halo_field;
 
 int ossg_halo_exchange_peer(const ossg_peer_halo_field* fields, int nfields, const ossg_peer_halo* halo, void* stream);
-
-/* ---- measurement / test utilities (not part of the reference surface) ---------------------- */
-/* interior(c)[i,j,k] = hash(seed, global i, j, k) in [-1, 1); halos are filled with a NaN payload */
-int ossg_synth_field(const ossg_field_desc* f, uint64_t seed, int32_t gi0, int32_t gj0, void* stream);
-/* sustained FP64 FMA rate of the current device: runs `iters` dependent-chain DFMA steps per
- * thread on a full grid; returns elapsed ms via *ms and executed flops via *flops              */
-int ossg_fp64_peak_probe(int iters, float* ms, double* flops, void* stream);
-/* device self-test of the branch-free sqrt / division used by the tile kernel's straight-line
- * path (csrc/ossg_math.cuh sqrt_nb, div_nb) against the IEEE operators on n pseudo-random
- * operands drawn from the ranges the kernel admits; mismatches[0] = sqrt, [1] = division
- * (host pointers; the call synchronises the stream)                                            */
-int ossg_selftest_sqrt_div(uint64_t n, uint64_t seed, uint64_t mismatches[2], void* stream);
-/* NVLink store-path probe: kernel-issued copy of `rows` contiguous source segments of seg_bytes to
- * dst + (r / group) * group_stride + (r % group) * pitch (dst usually peer-mapped); mode 0: 8-byte
- * stores, 1: 16-byte stores, 2: shared-memory staging + one bulk store per chunk, 3: bulk load +
- * bulk store; chunk_bytes <= 16384; blocks <= 0 selects 4 blocks per SM                          */
-int ossg_peer_copy_probe(void* dst, const void* src, uint64_t rows, uint32_t seg_bytes, uint64_t group,
-                         uint64_t group_stride, uint64_t pitch, uint32_t chunk_bytes, int mode, int blocks, void* stream);
 
 #ifdef __cplusplus
 }

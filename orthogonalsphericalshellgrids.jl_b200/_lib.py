@@ -11,9 +11,12 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("OSSG_B200_LIB") or os.path.join(_PKG, "libossg_b200.so")   # (override: kernel experiments)
 HEADER_PATH = os.path.join(_ROOT, "include", "ossg_b200.h")
+UTIL_LIB_PATH = os.path.join(_PKG, "libossg_b200_testutil.so")
+UTIL_HEADER_PATH = os.path.join(_ROOT, "include", "ossg_b200_testutil.h")
 
 # error codes (include/ossg_b200.h)
 OSSG_EINVAL, OSSG_EODD_NX, OSSG_EHALO, OSSG_EWINDOW, OSSG_EALIGN, OSSG_ELOCATION, OSSG_EWORKSPACE = -1, -2, -3, -4, -5, -6, -7
+OSSG_ENCCL, OSSG_ETIMEOUT = -8, -9
 OSSG_CENTER, OSSG_FACE = 0, 1
 OSSG_F64, OSSG_F32 = 0, 1
 
@@ -43,6 +46,15 @@ class FoldWindow(C.Structure):
 
 
 OSSG_MAX_PEERS, OSSG_MAX_PEER_BATCH = 8, 16
+
+
+class ExchangeLayout(C.Structure):
+    _fields_ = [("gNx", C.c_int32), ("gNy", C.c_int32), ("Rx", C.c_int32), ("Ry", C.c_int32),
+                ("rank", C.c_int32), ("reserved", C.c_int32)]
+
+
+class FoldSegment(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("field", "src_rank", "dst_rank", "src_i0", "n", "rows", "wrapped", "reserved")]
 
 
 class IpcHandle(C.Structure):
@@ -107,6 +119,9 @@ def lib() -> C.CDLL:
     L.ossg_device_ok.restype = C.c_int
     L.ossg_tripolar_workspace_bytes.argtypes = [C.POINTER(TripolarParams), C.c_int]
     L.ossg_tripolar_workspace_bytes.restype = C.c_size_t
+    L.ossg_tripolar_workspace_init.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.ossg_tripolar_table_bytes.argtypes = [C.POINTER(TripolarParams)]
+    L.ossg_tripolar_table_bytes.restype = C.c_size_t
     L.ossg_tripolar_build.argtypes = [C.POINTER(TripolarParams), C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p]
     L.ossg_tripolar_build_profiled.argtypes = [C.POINTER(TripolarParams), C.c_int, vpp, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
     L.ossg_tripolar_coords.argtypes = [C.POINTER(TripolarParams), vpp, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -119,17 +134,51 @@ def lib() -> C.CDLL:
     L.ossg_fold_buffer_elems.restype = C.c_size_t
     L.ossg_fold_pack.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow), C.c_void_p, C.c_void_p]
     L.ossg_fold_unpack.argtypes = [C.POINTER(FieldDesc), C.POINTER(FoldWindow), C.c_void_p, C.c_void_p]
-    L.ossg_synth_field.argtypes = [C.POINTER(FieldDesc), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
-    L.ossg_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
+    for name in ("ossg_fold_exchange", "ossg_halo_exchange"):
+        getattr(L, name).argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_int, C.POINTER(ExchangeLayout), C.c_void_p, C.c_size_t, C.c_void_p]
+        getattr(L, name + "_workspace_bytes").argtypes = [C.POINTER(FieldDesc), C.c_int, C.POINTER(ExchangeLayout)]
+        getattr(L, name + "_workspace_bytes").restype = C.c_size_t
+    L.ossg_fold_exchange_plan.argtypes = [C.POINTER(FieldDesc), C.c_int, C.POINTER(ExchangeLayout), C.POINTER(FoldSegment), C.c_int]
+    L.ossg_nccl_get_unique_id.argtypes = [C.c_char_p]
+    L.ossg_nccl_comm_init_rank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_int]
+    L.ossg_nccl_comm_destroy.argtypes = [C.c_void_p]
     L.ossg_ipc_export.argtypes = [C.c_void_p, C.POINTER(IpcHandle), C.POINTER(C.c_uint64)]
     L.ossg_ipc_open.argtypes = [C.POINTER(IpcHandle), C.c_uint64, C.POINTER(C.c_void_p)]
     L.ossg_zipper_fill_peer.argtypes = [C.POINTER(PeerField), C.c_int, C.POINTER(PeerFoldDesc), C.c_void_p]
     L.ossg_halo_exchange_peer.argtypes = [C.POINTER(PeerHaloField), C.c_int, C.POINTER(PeerHaloDesc), C.c_void_p]
-    L.ossg_selftest_sqrt_div.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
-    L.ossg_peer_copy_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
-                                       C.c_uint32, C.c_int, C.c_int, C.c_void_p]
     _lib = L
     return L
+
+
+_util = None
+
+
+def testutil() -> C.CDLL:
+    """libossg_b200_testutil.so (include/ossg_b200_testutil.h): synthetic fields, probes, self-tests.
+    Test and measurement infrastructure -- nothing in the package's product path calls it."""
+    global _util
+    if _util is not None:
+        return _util
+    if not os.path.exists(UTIL_LIB_PATH):
+        raise ImportError(f"{UTIL_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    U = C.CDLL(UTIL_LIB_PATH)
+    U.ossg_testutil_last_error.restype = C.c_char_p
+    U.ossg_synth_field.argtypes = [C.POINTER(FieldDesc), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
+    U.ossg_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
+    U.ossg_selftest_sqrt_div.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
+    U.ossg_peer_copy_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
+                                       C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+    _util = U
+    return U
+
+
+def check_util(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = testutil().ossg_testutil_last_error().decode("utf-8", "replace")
+    if rc < 0:
+        raise ValueError(msg)
+    raise OSSGError(f"CUDA error {rc}: {msg}")
 
 
 def last_error() -> str:
@@ -152,9 +201,9 @@ def ptr_array(ptrs):
     return C.cast(arr, C.POINTER(C.c_void_p))
 
 
-def declared_symbols() -> list:
-    """Function names declared in include/ossg_b200.h (for the export test)."""
+def declared_symbols(path: str = None) -> list:
+    """Function names declared in include/ossg_b200.h (or the given header), for the export test."""
     import re
-    text = open(HEADER_PATH).read()
+    text = open(path or HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ossg_[a-z0-9_]+)\s*\(", text)))

@@ -1,6 +1,7 @@
 // csrc/ossg_api.cu -- housekeeping entry points of the C ABI (version, errors, device check).
 #include "ossg_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace ossg {
@@ -20,8 +21,20 @@ int set_error(int code, const char* fmt, ...)
     return code;
 }
 
+int env_int(const char* name, int fallback)
+{
+    const char* e = getenv(name);
+    if (!e || !*e) return fallback;
+    char* end = nullptr;
+    const long v = strtol(e, &end, 10);
+    return (end && *end == 0) ? (int)v : fallback;
+}
+
 }  // namespace ossg
 
+#ifdef OSSG_TESTUTIL_BUILD
+extern "C" const char* ossg_testutil_last_error(void) { return ossg::last_error_buffer(); }
+#else
 extern "C" int ossg_version(void) { return OSSG_VERSION_MAJOR * 100 + OSSG_VERSION_MINOR; }
 
 extern "C" const char* ossg_last_error(void) { return ossg::last_error_buffer(); }
@@ -39,3 +52,4 @@ extern "C" int ossg_device_ok(void)
                                dev, prop.name, prop.major, prop.minor);
     return 0;
 }
+#endif  // OSSG_TESTUTIL_BUILD

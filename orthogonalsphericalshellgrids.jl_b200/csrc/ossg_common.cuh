@@ -32,6 +32,25 @@ inline int cuda_fail(cudaError_t e, const char* what)
     } while (0)
 
 #if defined(__CUDACC__)
+// `sign * c[i', j', k]` of the fold (src/zipper_boundary_condition.jl:81,98,115,131): bc.condition is
+// an integer +-1 promoted to the field's float type, so the reference executes an IEEE
+// multiplication by +-1.0.  That is exact for every number, and for a NaN operand the CPU the
+// reference runs on (x86 mulsd/mulss, AArch64 fmul) returns that NaN QUIETED with its own sign and
+// payload -- multiplication by -1.0 does not flip a NaN's sign, a negation would.  The GPU's own
+// multiply returns a canonical NaN instead, so the NaN case is spelled out on the bits; the fold is
+// then bit-exact against the reference's CPU path for every input, NaN payloads included.
+__device__ __forceinline__ double quiet_nan(double v) { return __longlong_as_double(__double_as_longlong(v) | 0x0008000000000000ll); }
+__device__ __forceinline__ float quiet_nan(float v) { return __int_as_float(__float_as_int(v) | 0x00400000); }
+template <typename T>
+__device__ __forceinline__ T apply_sign(T v, double s)
+{
+    if (s == 1.0 || s == -1.0) {
+        if (v != v) return quiet_nan(v);
+        return s == 1.0 ? v : -v;
+    }
+    return (T)(s * (double)v);          // any other bc.condition: the oracle's (T)(s * c)
+}
+
 // Copy of one halo-width piece (Hx elements of a row).  The common case -- 4 doubles, both ends
 // 32-byte aligned -- is ONE 256-bit load and ONE 256-bit store (LDG.256 / STG.256, sm_100): one
 // DRAM sector, and over NVLink one 32-byte packet instead of four 8-byte ones.
@@ -61,5 +80,9 @@ __device__ __forceinline__ void copy_halo_piece(T* dst, const T* src, int Hx)
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// integer tuning knob from the environment; callers cache the value in a
+// function-local static, so the environment is read once per process and never on a launch path
+int env_int(const char* name, int fallback);
 
 }  // namespace ossg

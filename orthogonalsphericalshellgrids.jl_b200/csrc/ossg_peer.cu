@@ -33,14 +33,6 @@ constexpr int PB = 256;
 #define PEER_BLOCKS_PER_SM 4
 #endif
 
-template <typename T>
-__device__ __forceinline__ T peer_sign(T v, double s)
-{
-    if (s == 1.0) return v;
-    if (s == -1.0) return -v;
-    return (T)(s * (double)v);
-}
-
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -116,13 +108,13 @@ __device__ __forceinline__ void peer_column(const ossg_peer_field& p, const ossg
     for (; q + 4 <= Hy; q += 4) {
         const T v0 = peer_load(src - (ptrdiff_t)((q + 0) * sxr)), v1 = peer_load(src - (ptrdiff_t)((q + 1) * sxr));
         const T v2 = peer_load(src - (ptrdiff_t)((q + 2) * sxr)), v3 = peer_load(src - (ptrdiff_t)((q + 3) * sxr));
-        dst[(size_t)(q + 0) * sx] = peer_sign(v0, s);
-        dst[(size_t)(q + 1) * sx] = peer_sign(v1, s);
-        dst[(size_t)(q + 2) * sx] = peer_sign(v2, s);
-        dst[(size_t)(q + 3) * sx] = peer_sign(v3, s);
+        dst[(size_t)(q + 0) * sx] = apply_sign(v0, s);
+        dst[(size_t)(q + 1) * sx] = apply_sign(v1, s);
+        dst[(size_t)(q + 2) * sx] = apply_sign(v2, s);
+        dst[(size_t)(q + 3) * sx] = apply_sign(v3, s);
     }
-    for (; q < Hy; ++q) dst[(size_t)q * sx] = peer_sign(peer_load(src - (ptrdiff_t)(q * sxr)), s);
-    if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + Hx - 1)] = peer_sign(vrow, s);
+    for (; q < Hy; ++q) dst[(size_t)q * sx] = apply_sign(peer_load(src - (ptrdiff_t)(q * sxr)), s);
+    if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + Hx - 1)] = apply_sign(vrow, s);
 }
 
 // push form: the thread owns SOURCE column i of this rank and stores the folded values into the
@@ -156,13 +148,13 @@ __device__ __forceinline__ void peer_column_push(const ossg_peer_field& p, const
     for (; q + 4 <= Hy; q += 4) {
         const T v0 = src[-(ptrdiff_t)((q + 0) * sx)], v1 = src[-(ptrdiff_t)((q + 1) * sx)];
         const T v2 = src[-(ptrdiff_t)((q + 2) * sx)], v3 = src[-(ptrdiff_t)((q + 3) * sx)];
-        dst[(size_t)(q + 0) * sxr] = peer_sign(v0, s);
-        dst[(size_t)(q + 1) * sxr] = peer_sign(v1, s);
-        dst[(size_t)(q + 2) * sxr] = peer_sign(v2, s);
-        dst[(size_t)(q + 3) * sxr] = peer_sign(v3, s);
+        dst[(size_t)(q + 0) * sxr] = apply_sign(v0, s);
+        dst[(size_t)(q + 1) * sxr] = apply_sign(v1, s);
+        dst[(size_t)(q + 2) * sxr] = apply_sign(v2, s);
+        dst[(size_t)(q + 3) * sxr] = apply_sign(v3, s);
     }
-    for (; q < Hy; ++q) dst[(size_t)q * sxr] = peer_sign(src[-(ptrdiff_t)(q * sx)], s);
-    if (fix_row) dstb[(size_t)(Ny + Hy - 1) * sxr] = peer_sign(vrow, s);
+    for (; q < Hy; ++q) dst[(size_t)q * sxr] = apply_sign(src[-(ptrdiff_t)(q * sx)], s);
+    if (fix_row) dstb[(size_t)(Ny + Hy - 1) * sxr] = apply_sign(vrow, s);
 }
 
 // ---- push form with bulk stores (fold.push == 2).  The block stages the folded rows of one
@@ -237,7 +229,7 @@ __device__ __forceinline__ void peer_chunk_push_bulk(const ossg_peer_field& p, c
                 const int q = q0 + qq;
                 const bool fix = q == Hy;
                 if (fix && idg <= half) continue;                     // row Ny is overwritten for the right half only
-                const T v = peer_sign(fix ? c[(size_t)(Ny + Hy - 1) * sx] : c[(size_t)((f.locy ? Ny : Ny - 1) + Hy - 1 - q) * sx], s);
+                const T v = apply_sign(fix ? c[(size_t)(Ny + Hy - 1) * sx] : c[(size_t)((f.locy ? Ny : Ny - 1) + Hy - 1 - q) * sx], s);
                 T* d = dstb + (fix ? (size_t)(Ny + Hy - 1) : (size_t)(Ny + Hy + q)) * sxr;
                 const int clo = fix ? max(clo_halo, half + 1) : clo_halo;
                 bool direct = wrapped || reg >= BULK_NREG;

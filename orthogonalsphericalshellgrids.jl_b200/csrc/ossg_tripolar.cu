@@ -36,7 +36,8 @@ struct BuildArgs {
     GridDims g;
     Window w;
     double south, north_poles_latitude, first_pole_longitude, radius;
-    double* tables;               // workspace: tables_doubles() doubles
+    unsigned long long* stamp;    // workspace header: TABLE_HDR_WORDS 8-byte words (validity stamps of the tables)
+    double* tables;               // workspace + header: tables_doubles() doubles
     double* coords64[8];          // FP64 coordinates (outputs when FT = double, scratch otherwise)
     void* coords_out[8];          // FT coordinates (== coords64 when FT = double)
     void* metrics_out[12];        // FT metrics
@@ -53,38 +54,87 @@ __host__ __device__ inline Tables make_tables(const double* base, int Nx, int Ny
 }
 
 // ------------------------------------------------------------------ K0
-__global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, double north_poles_latitude,
-                                                     double radius, double* __restrict__ base)
+// The tables depend on a handful of scalars only, and every constructor call of a model run
+// (with_halo, reconstruct_global_grid, src/with_halo.jl:5-44, src/distributed_tripolar_grid.jl:201-226)
+// repeats them.  The workspace therefore carries two validity stamps in a small header:
+//   words 0..4   x/y tables:   magic, Nx, Ny, bits(south), bits(north_poles_latitude)
+//   words 5..10  lat-lon rows: magic, Nx, Ny, Hy, bits(south), bits(radius)
+//   word  11     arrival counter of the kernel that fills them
+// A launch whose keys match returns after reading the header (about 2 us instead of the 15 us
+// double-double chain); otherwise the last block to finish writes the keys.  The caller zeroes the
+// header once per allocation (ossg_tripolar_workspace_init), so stale memory never passes for a stamp.
+constexpr int TABLE_HDR_WORDS = 16;
+constexpr unsigned long long STAMP_XY = 0x4f5353475f58595full, STAMP_LL = 0x4f5353475f4c4c5full;   // "OSSG_XY_", "OSSG_LL_"
+
+struct TableKeys { unsigned long long xy[5], ll[6]; };
+__host__ __device__ inline TableKeys table_keys(const GridDims& g, double south, double npl, double radius)
 {
+    auto bits = [](double x) { unsigned long long u; memcpy(&u, &x, 8); return u; };
+    TableKeys k;
+    k.xy[0] = STAMP_XY; k.xy[1] = (unsigned)g.Nx; k.xy[2] = (unsigned)g.Ny; k.xy[3] = bits(south); k.xy[4] = bits(npl);
+    k.ll[0] = STAMP_LL; k.ll[1] = (unsigned)g.Nx; k.ll[2] = (unsigned)g.Ny; k.ll[3] = (unsigned)g.Hy; k.ll[4] = bits(south); k.ll[5] = bits(radius);
+    return k;
+}
+
+__global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, double north_poles_latitude,
+                                                     double radius, double* __restrict__ base, unsigned long long* stamp)
+{
+    const TableKeys key = table_keys(g, south, north_poles_latitude, radius);
+    bool xy_ok = true, ll_ok = true;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) xy_ok = xy_ok && __ldcg(stamp + q) == key.xy[q];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) ll_ok = ll_ok && __ldcg(stamp + 5 + q) == key.ll[q];
+    if (xy_ok && ll_ok) return;                             // (uniform over the grid: nobody writes the header before every block has read it)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int Nx = g.Nx, Ny = g.Ny;
     double* xs = base;
     double* ys = base + 4 * (size_t)Nx;
     double* ll = ys + 4 * (size_t)Ny;
     if (t < 2 * Nx) {
-        // x tables, stored in post-circshift order; one thread per (face|center, i)
-        const int face = t < Nx;
-        const int i = face ? t + 1 : t - Nx + 1;
-        const int ip = preshift(i, Nx);
-        const double a = focal_distance(north_poles_latitude);
-        const double lam = face ? lam_face(ip, Nx) : lam_center(ip, Nx);
-        const int o = face ? 0 : 2;
-        xs[(size_t)(o + 0) * Nx + (i - 1)] = a * m::sind(lam);      // generate_tripolar_coordinates.jl:67
-        xs[(size_t)(o + 1) * Nx + (i - 1)] = a * m::cosd(lam);      // :68
+        if (!xy_ok) {
+            // x tables, stored in post-circshift order; one thread per (face|center, i)
+            const int face = t < Nx;
+            const int i = face ? t + 1 : t - Nx + 1;
+            const int ip = preshift(i, Nx);
+            const double a = focal_distance(north_poles_latitude);
+            const double lam = face ? lam_face(ip, Nx) : lam_center(ip, Nx);
+            const int o = face ? 0 : 2;
+            xs[(size_t)(o + 0) * Nx + (i - 1)] = a * m::sind(lam);      // generate_tripolar_coordinates.jl:67
+            xs[(size_t)(o + 1) * Nx + (i - 1)] = a * m::cosd(lam);      // :68
+        }
     } else if (t < 2 * Nx + 2 * Ny) {
-        const int u = t - 2 * Nx;
-        const int face = u < Ny;
-        const int j = face ? u + 1 : u - Ny + 1;
-        const double a = focal_distance(north_poles_latitude);
-        const double phi = face ? phi_face(j, Ny, south) : phi_center(j, Ny, south);
-        const int o = face ? 0 : 2;
-        double psi, sh, ch;
-        m::asinh_sinh_cosh_cr(m::tand((90.0 - phi) / 2) / a, psi, sh, ch);   // :66-68
-        ys[(size_t)(o + 0) * Ny + (j - 1)] = ch;
-        ys[(size_t)(o + 1) * Ny + (j - 1)] = sh;
+        if (!xy_ok) {
+            const int u = t - 2 * Nx;
+            const int face = u < Ny;
+            const int j = face ? u + 1 : u - Ny + 1;
+            const double a = focal_distance(north_poles_latitude);
+            const double phi = face ? phi_face(j, Ny, south) : phi_center(j, Ny, south);
+            const int o = face ? 0 : 2;
+            double psi, sh, ch;
+            m::asinh_sinh_cosh_cr(m::tand((90.0 - phi) / 2) / a, psi, sh, ch);   // :66-68
+            ys[(size_t)(o + 0) * Ny + (j - 1)] = ch;
+            ys[(size_t)(o + 1) * Ny + (j - 1)] = sh;
+        }
     } else if (t < 2 * Nx + 2 * Ny + g.Hy + 1) {
-        const int r = t - 2 * Nx - 2 * Ny;                  // row r <-> j = r + 1 - Hy
-        latlon_row(r + 1 - g.Hy, Nx, Ny, g.Hy, south, radius, ll + (size_t)r * LL_NCOL);
+        if (!ll_ok) {
+            const int r = t - 2 * Nx - 2 * Ny;                  // row r <-> j = r + 1 - Hy
+            latlon_row(r + 1 - g.Hy, Nx, Ny, g.Hy, south, radius, ll + (size_t)r * LL_NCOL);
+        }
+    }
+    // the last block to arrive stamps the header (every block has read it by then)
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int* counter = reinterpret_cast<unsigned int*>(stamp + 11);
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            for (int q = 0; q < 5; ++q) stamp[q] = key.xy[q];
+            for (int q = 0; q < 6; ++q) stamp[5 + q] = key.ll[q];
+            *counter = 0u;
+        }
     }
 }
 
@@ -820,7 +870,7 @@ static int check_params(const ossg_tripolar_params* p, ossg_tripolar_params& q)
 
 static size_t table_bytes(const ossg_tripolar_params& q)
 {
-    size_t n = tables_doubles(q.Nx, q.Ny, q.Hy);
+    size_t n = TABLE_HDR_WORDS + tables_doubles(q.Nx, q.Ny, q.Hy);
     n = (n + 1) & ~(size_t)1;            // keep what follows 16-byte aligned
     return n * sizeof(double);
 }
@@ -837,13 +887,14 @@ static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* works
     a.north_poles_latitude = q.north_poles_latitude;
     a.first_pole_longitude = q.first_pole_longitude;
     a.radius = q.radius;
-    a.tables = static_cast<double*>(workspace);
+    a.stamp = static_cast<unsigned long long*>(workspace);
+    a.tables = static_cast<double*>(workspace) + TABLE_HDR_WORDS;
 }
 
 static int launch_tables(const BuildArgs& a, cudaStream_t s)
 {
     const int n = 2 * a.g.Nx + 2 * a.g.Ny + a.g.Hy + 1;
-    tables_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a.g, a.south, a.north_poles_latitude, a.radius, a.tables);
+    tables_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a.g, a.south, a.north_poles_latitude, a.radius, a.tables, a.stamp);
     OSSG_LAUNCH_CHECK("tables_kernel");
     return 0;
 }
@@ -875,19 +926,58 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
     return 0;
 }
 
-// Side stream of the current device (created once, never destroyed): the halo-frame kernel depends
-// on the coordinates only, so it runs next to the tile kernel instead of after it.
-static int side_stream(cudaStream_t* out)
+// Fork/join resources of the current device: the halo-frame kernel depends on the coordinates only,
+// so it runs on a side stream next to the tile kernel instead of after it.  One {stream, fork event,
+// join event} set per device, created on first use and reused by every call (no per-call
+// cudaEventCreate/Destroy).  The mutex is held from the fork record to the join wait: an event
+// record/wait pair captures the event's state at the time of the call, so calls from several host
+// threads (each on its own stream) may share the set as long as their pairs do not interleave.
+struct ForkJoin {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static std::mutex g_fork_mu;
+static ForkJoin g_fork[64];
+
+static int fork_join(ForkJoin** out)                       // call with g_fork_mu held
 {
-    static std::mutex mu;
-    static cudaStream_t side[64] = {};
     int dev = 0;
     OSSG_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return set_error(OSSG_EINVAL, "device ordinal %d not supported", dev);
-    std::lock_guard<std::mutex> lock(mu);
-    if (!side[dev]) OSSG_CUDA_TRY(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
-    *out = side[dev];
+    ForkJoin& fj = g_fork[dev];
+    if (!fj.side) OSSG_CUDA_TRY(cudaStreamCreateWithFlags(&fj.side, cudaStreamNonBlocking));
+    if (!fj.fork) OSSG_CUDA_TRY(cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming));
+    if (!fj.join) OSSG_CUDA_TRY(cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming));
+    *out = &fj;
     return 0;
+}
+
+// the tile kernels ask for more than 48 KB of dynamic shared memory: opt in once per device
+static int tile_attributes(int which /*0: double, 1: float*/, int kernel /*0: cp.async, 1: TMA, 2: pairs*/, const void* fn, size_t bytes)
+{
+    static std::mutex mu;
+    static unsigned long long done[2][3] = {};
+    int dev = 0;
+    OSSG_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && ((done[which][kernel] >> dev) & 1ull)) return 0;
+    OSSG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev >= 0 && dev < 64) done[which][kernel] |= 1ull << dev;
+    return 0;
+}
+
+// tile-kernel form, from the environment once per process: 0 = cp.async staging
+// (default, the measured best), 1 = TMA box loads (OSSG_TILE_STAGING=tma), 2 = mirror-pair clusters (OSSG_TILE_PAIRS=1)
+static int tile_form()
+{
+    static const int form = [] {
+        const char* staging = getenv("OSSG_TILE_STAGING");
+        const char* pairs = getenv("OSSG_TILE_PAIRS");
+        if (OSSG_USE_TMA || (staging && strcmp(staging, "tma") == 0)) return 1;
+        if (pairs && strcmp(pairs, "1") == 0) return 2;
+        return 0;
+    }();
+    return form;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -947,52 +1037,42 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
     // frame kernel: forked onto the side stream when there is a tile kernel to overlap with (the
     // profiled build keeps the two in sequence so that their times can be told apart)
     const bool fork = have_tile && nframe > 0 && !between;
-    cudaStream_t fs = s;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::unique_lock<std::mutex> fork_lock(g_fork_mu, std::defer_lock);
+    ForkJoin* fj = nullptr;
     if (fork) {
-        int rc = side_stream(&fs);
+        fork_lock.lock();
+        int rc = fork_join(&fj);
         if (rc) return rc;
-        OSSG_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        OSSG_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        OSSG_CUDA_TRY(cudaEventRecord(ev_fork, s));
-        OSSG_CUDA_TRY(cudaStreamWaitEvent(fs, ev_fork, 0));
-        metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, fs>>>(a, f);
+        OSSG_CUDA_TRY(cudaEventRecord(fj->fork, s));
+        OSSG_CUDA_TRY(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+        metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, fj->side>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
-        OSSG_CUDA_TRY(cudaEventRecord(ev_join, fs));
+        OSSG_CUDA_TRY(cudaEventRecord(fj->join, fj->side));
     }
     if (have_tile) {
-        static bool attr_set[2] = { false, false };
         const int which = sizeof(FT) == 4;
-        if (!attr_set[which]) {
-            OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<false>::SMEM_BYTES));
-            OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<true>::SMEM_BYTES));
-            attr_set[which] = true;
-        }
         dim3 block(TX, TY), grid(ceil_div(fr.nx, TX), ceil_div(fr.ny, TY));
         TileMaps tm;
         // Staging of the coordinate patches: cp.async by default.  The TMA form (eight 2-D box loads
         // issued by one thread) is complete and parity-tested but measured 3 % slower on the 1/12
         // degree grid (0.650 vs 0.631 ms: 3 % more patch points because of the 16-byte box
-        // alignment, and the patch arrives later than 256 threads' own loads), so it is opt-in:
-        // OSSG_TILE_STAGING=tma.
-        const char* staging = getenv("OSSG_TILE_STAGING");
-        const bool want_tma = OSSG_USE_TMA || (staging && strcmp(staging, "tma") == 0);
-        // Mirror-pair variant (clusters of two CTAs sharing the latitude part of the point stage):
-        // written at the end of round 1 and not yet measured, hence opt-in: OSSG_TILE_PAIRS=1.
-        const char* pairs = getenv("OSSG_TILE_PAIRS");
-        const bool want_pairs = pairs && strcmp(pairs, "1") == 0 && !want_tma && fr.I0 == 1 && fr.nx == a.g.Nx && a.g.Nx % 4 == 0;
+        // alignment, and the patch arrives later than 256 threads' own loads); the mirror-pair
+        // variant (clusters of two CTAs sharing the latitude part of the point stage) measured 17 %
+        // slower (0.724 vs 0.621 ms).  Both stay opt-in, see tile_form().
+        const int form = tile_form();
+        const bool want_tma = form == 1;
+        const bool want_pairs = form == 2 && fr.I0 == 1 && fr.nx == a.g.Nx && a.g.Nx % 4 == 0;
+        int rc = 0;
         if (want_pairs) {
-            static bool pair_attr_set[2] = { false, false };
-            if (!pair_attr_set[which]) {
-                OSSG_CUDA_TRY(cudaFuncSetAttribute(metrics_tile_pair_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<false>::SMEM_BYTES));
-                pair_attr_set[which] = true;
-            }
+            if ((rc = tile_attributes(which, 2, (const void*)metrics_tile_pair_kernel<FT>, TileGeom<false>::SMEM_BYTES))) return rc;
             const int nts = ceil_div(a.g.Nx / 4, TX);
             dim3 pgrid(4 * nts, ceil_div(fr.ny, TY));            // 2 quarters of A tiles x nts pairs x 2 members
             metrics_tile_pair_kernel<FT><<<pgrid, block, TileGeom<false>::SMEM_BYTES, s>>>(a, fr);
         } else if (want_tma && make_tile_maps(a, tm)) {
+            if ((rc = tile_attributes(which, 1, (const void*)metrics_tile_kernel<FT, true>, TileGeom<true>::SMEM_BYTES))) return rc;
             metrics_tile_kernel<FT, true><<<grid, block, TileGeom<true>::SMEM_BYTES, s>>>(a, fr, tm);
         } else {
+            if ((rc = tile_attributes(which, 0, (const void*)metrics_tile_kernel<FT, false>, TileGeom<false>::SMEM_BYTES))) return rc;
             memset(&tm, 0, sizeof(tm));
             metrics_tile_kernel<FT, false><<<grid, block, TileGeom<false>::SMEM_BYTES, s>>>(a, fr, tm);
         }
@@ -1000,9 +1080,7 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
     }
     if (between) OSSG_CUDA_TRY(cudaEventRecord(between, s));
     if (fork) {
-        OSSG_CUDA_TRY(cudaStreamWaitEvent(s, ev_join, 0));
-        cudaEventDestroy(ev_fork);          // (released when the recorded work completes)
-        cudaEventDestroy(ev_join);
+        OSSG_CUDA_TRY(cudaStreamWaitEvent(s, fj->join, 0));
     } else if (nframe > 0) {
         metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, s>>>(a, f);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
@@ -1070,6 +1148,21 @@ extern "C" size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, i
     size_t b = table_bytes(q);
     if (out_type == OSSG_F32) b += 8 * window_elems(q) * sizeof(double);
     return b;
+}
+
+extern "C" int ossg_tripolar_workspace_init(void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 16) return set_error(OSSG_EALIGN, "workspace must be a 16-byte aligned device pointer");
+    if (workspace_bytes < TABLE_HDR_WORDS * sizeof(unsigned long long)) return set_error(OSSG_EWORKSPACE, "workspace has %zu bytes, the header alone needs %zu", workspace_bytes, TABLE_HDR_WORDS * sizeof(unsigned long long));
+    OSSG_CUDA_TRY(cudaMemsetAsync(workspace, 0, TABLE_HDR_WORDS * sizeof(unsigned long long), as_stream(stream)));
+    return 0;
+}
+
+extern "C" size_t ossg_tripolar_table_bytes(const ossg_tripolar_params* p)
+{
+    ossg_tripolar_params q;
+    if (check_params(p, q)) return 0;
+    return table_bytes(q);
 }
 
 static int build_impl(const ossg_tripolar_params* p, int out_type, void* const out[20],

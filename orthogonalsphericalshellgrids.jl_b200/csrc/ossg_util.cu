@@ -1,9 +1,11 @@
-// csrc/ossg_util.cu -- measurement / test utilities exported next to the product entry points:
+// csrc/ossg_util.cu -- libossg_b200_testutil.so (include/ossg_b200_testutil.h): measurement / test
+// utilities kept OUT of the product library:
 // deterministic synthetic fields and an FP64 FMA rate probe that gives
 // the roofline denominator for the coordinate/metric kernels (MEASURED_PEAKS.json has no FP64
 // figure).  Nothing here is on the reference's path.
 #include "ossg_common.cuh"
 #include "ossg_math.cuh"
+#include "../../include/ossg_b200_testutil.h"
 
 namespace ossg {
 

@@ -18,14 +18,6 @@ struct FieldBatch {
     int n;
 };
 
-template <typename T>
-__device__ __forceinline__ T apply_sign(T v, double s)
-{
-    if (s == 1.0) return v;
-    if (s == -1.0) return -v;
-    return (T)(s * (double)v);
-}
-
 // rows handled per level: Hy halo rows (+1 for y-Center: the redundant half of row Ny)
 __device__ __host__ inline int fold_rows(const ossg_field_desc& f) { return f.Hy + (f.locy == OSSG_CENTER ? 1 : 0); }
 
@@ -149,7 +141,43 @@ __device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1
     }
 }
 
-// part B: one thread per (row, side), loads before stores
+// ---- part B.  A halo piece is Hx elements of a row; the common piece (4 doubles, 32-byte aligned) is
+// one 256-bit load and one 256-bit store.  Memory picture of two consecutive parent rows r, r+1
+// (row pitch (Nx+2Hx) elements): the last 2Hx elements of row r and the first 2Hx of row r+1 are
+// contiguous -- the "seam"
+//        [ E-interior(r) | E-halo(r) | W-halo(r+1) | W-interior(r+1) ]        (4 x 32 B = 128 B)
+// with  W-halo(r) <- E-interior(r)  and  E-halo(r) <- W-interior(r).
+struct Piece32 { double a, b, c, d; };
+template <int HINT>
+__device__ __forceinline__ Piece32 ld_piece32(const void* p)
+{
+    Piece32 v;
+    if (HINT == 1)      asm volatile("ld.global.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    else if (HINT == 2) asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    else                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_piece32(void* p, const Piece32& v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
+}
+__device__ __forceinline__ Piece32 shfl_piece(const Piece32& v, int delta /* +1: from lane-1, -1: from lane+1 */)
+{
+    Piece32 r;
+    if (delta > 0) { r.a = __shfl_up_sync(0xffffffffu, v.a, 1); r.b = __shfl_up_sync(0xffffffffu, v.b, 1); r.c = __shfl_up_sync(0xffffffffu, v.c, 1); r.d = __shfl_up_sync(0xffffffffu, v.d, 1); }
+    else { r.a = __shfl_down_sync(0xffffffffu, v.a, 1); r.b = __shfl_down_sync(0xffffffffu, v.b, 1); r.c = __shfl_down_sync(0xffffffffu, v.c, 1); r.d = __shfl_down_sync(0xffffffffu, v.d, 1); }
+    return r;
+}
+
+// rows whose periodic images part A writes: north-halo rows (and row Ny of y-Center fields) of the zipper levels
+__device__ __forceinline__ bool part_a_row(const ossg_field_desc& f, long long row)
+{
+    const int sy = f.Ny + 2 * f.Hy;
+    const int lev = (int)(row / sy), jrow = (int)(row - (long long)lev * sy);
+    return lev >= f.k0 && lev < f.k0 + f.nk && jrow >= f.Ny + f.Hy - (f.locy == OSSG_CENTER ? 1 : 0);
+}
+
+// variant 0: one thread per (row, side), load before store
 template <typename T>
 __device__ __forceinline__ void fused_periodic_row(const ossg_field_desc& f, size_t row, int side)
 {
@@ -160,11 +188,83 @@ __device__ __forceinline__ void fused_periodic_row(const ossg_field_desc& f, siz
     copy_halo_piece(dst, src, Hx);
 }
 
+// variants 1, 2: one thread per ROWS consecutive rows, both sides; all loads before the stores
+template <int ROWS, int HINT>
+__device__ __forceinline__ void fused_periodic_rows32(const ossg_field_desc& f, long long row0, long long rows, bool all_rows)
+{
+    const size_t pitch = (size_t)(f.Nx + 2 * f.Hx) * 8;
+    char* c = static_cast<char*>(f.data) + (size_t)row0 * pitch;
+    Piece32 e[ROWS], w[ROWS];
+    bool on[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        on[u] = row0 + u < rows && (all_rows || !part_a_row(f, row0 + u));
+        if (on[u]) { e[u] = ld_piece32<HINT>(c + u * pitch + (size_t)f.Nx * 8); w[u] = ld_piece32<HINT>(c + u * pitch + 32); }
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u)
+        if (on[u]) { st_piece32(c + u * pitch, e[u]); st_piece32(c + u * pitch + (size_t)f.Nx * 8 + 32, w[u]); }
+}
+
+// variant 3: one thread per seam t (between rows t-1 and t, t = 0..rows): it loads the two outer
+// pieces of its seam, trades them with its lane neighbours and stores the two inner pieces -- 64
+// contiguous bytes.  Every 128-byte seam is read once and written once by ONE thread.
+template <int HINT>
+__device__ __forceinline__ void fused_periodic_seam32(const ossg_field_desc& f, long long t, long long rows, bool all_rows)
+{
+    const size_t pitch = (size_t)(f.Nx + 2 * f.Hx) * 8;
+    char* base = static_cast<char*>(f.data);
+    const int lane = threadIdx.x & 31;
+    auto live = [&](long long r) { return r >= 0 && r < rows && (all_rows || !part_a_row(f, r)); };
+    const bool lo = live(t - 1), hi = live(t);              // row below / above the seam takes part
+    Piece32 e = {}, w = {};
+    if (lo) e = ld_piece32<HINT>(base + (size_t)(t - 1) * pitch + (size_t)f.Nx * 8);      // E-interior(t-1)
+    if (hi) w = ld_piece32<HINT>(base + (size_t)t * pitch + 32);                          // W-interior(t)
+    Piece32 w_lo = shfl_piece(w, +1);                         // W-interior(t-1), loaded by the thread of seam t-1
+    Piece32 e_hi = shfl_piece(e, -1);                         // E-interior(t),   loaded by the thread of seam t+1
+    if (lane == 0 && lo) w_lo = ld_piece32<HINT>(base + (size_t)(t - 1) * pitch + 32);
+    if (lane == 31 && hi) e_hi = ld_piece32<HINT>(base + (size_t)t * pitch + (size_t)f.Nx * 8);
+    if (lo) st_piece32(base + (size_t)(t - 1) * pitch + (size_t)f.Nx * 8 + 32, w_lo);     // E-halo(t-1)
+    if (hi) st_piece32(base + (size_t)t * pitch, e_hi);                                   // W-halo(t)
+}
+
 struct FusedBatch {
     FieldBatch b;
-    int blocksA[MAX_BATCH];          // part A blocks of field k: ceil(Nx / ZB) * nk
+    int blocksA[MAX_BATCH];          // part A blocks of field k: ceil(Nx / ZB) * nk  (0: part B covers every row)
     int chunksA[MAX_BATCH];          // ceil(Nx / ZB)
+    int variant;                     // part B form, see fill_variant()
 };
+
+// Part B form (experiment knob OSSG_FILL_VARIANT, read once; default = the measured best):
+//   0  thread per (row, side)            1  thread per row, both sides        2  thread per 2 rows
+//   3  thread per seam (lane exchange)   +10: loads carry an L2::128B prefetch hint   +20: L1::no_allocate
+//   +100: two launches (zipper_kernel, then part B over all rows) instead of one
+static int g_fill_variant_override = -1;          // EXPERIMENT HOOK (tools/fill_variants.py); removed once the default is chosen
+static int fill_variant()
+{
+    static const int v = env_int("OSSG_FILL_VARIANT", 0);
+    return g_fill_variant_override >= 0 ? g_fill_variant_override : v;
+}
+
+template <int HINT>
+__device__ __forceinline__ void fused_part_b(const ossg_field_desc& f, int form, long long t, bool all_rows)
+{
+    const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
+    const bool fast = f.elem_type == OSSG_F64 && f.Hx == 4 && (reinterpret_cast<uintptr_t>(f.data) & 31) == 0;
+    if (form == 0 || !fast) {
+        if (t >= 2 * rows) return;
+        const long long row = t >> 1;
+        if (!all_rows && part_a_row(f, row)) return;
+        if (f.elem_type == OSSG_F64) fused_periodic_row<double>(f, (size_t)row, (int)(t & 1));
+        else fused_periodic_row<float>(f, (size_t)row, (int)(t & 1));
+    } else if (form == 1) {
+        if (t < rows) fused_periodic_rows32<1, HINT>(f, t, rows, all_rows);
+    } else if (form == 2) {
+        if (2 * t < rows) fused_periodic_rows32<2, HINT>(f, 2 * t, rows, all_rows);
+    } else {
+        if (t <= (rows | 31)) fused_periodic_seam32<HINT>(f, t, rows, all_rows);   // (whole warps: the lane exchange is warp-wide)
+    }
+}
 
 __global__ void __launch_bounds__(ZB) fill_fused_kernel(const __grid_constant__ FusedBatch fb)
 {
@@ -179,19 +279,12 @@ __global__ void __launch_bounds__(ZB) fill_fused_kernel(const __grid_constant__ 
         else fused_column<float>(f, i, kk);
         return;
     }
-    const int sy = f.Ny + 2 * f.Hy;
-    const long long rows = (long long)sy * (f.Nz + 2 * f.Hz);
     const long long t = (long long)(blockIdx.x - nA) * ZB + threadIdx.x;
-    // rows whose periodic images part A writes: north-halo rows (and row Ny of y-Center fields) of the zipper levels
-    auto part_a_row = [&](long long row) {
-        const int lev = (int)(row / sy), jrow = (int)(row - (long long)lev * sy);
-        return lev >= f.k0 && lev < f.k0 + f.nk && jrow >= f.Ny + f.Hy - (f.locy == OSSG_CENTER ? 1 : 0);
-    };
-    if (t >= 2 * rows) return;
-    const long long row = t >> 1;
-    if (part_a_row(row)) return;
-    if (f.elem_type == OSSG_F64) fused_periodic_row<double>(f, (size_t)row, (int)(t & 1));
-    else fused_periodic_row<float>(f, (size_t)row, (int)(t & 1));
+    const int form = fb.variant % 10, hint = (fb.variant / 10) % 10;
+    const bool all_rows = nA == 0;
+    if (hint == 1) fused_part_b<1>(f, form, t, all_rows);
+    else if (hint == 2) fused_part_b<2>(f, form, t, all_rows);
+    else fused_part_b<0>(f, form, t, all_rows);
 }
 
 // ------------------------------------------------------------------ (x,y)-partition fold: pack / unpack
@@ -293,22 +386,33 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
         if (fusable) {                       // zipper + periodic in one launch
             FusedBatch fb;
             fb.b = b;
+            fb.variant = fill_variant() % 100;
+            const bool two_launches = fill_variant() >= 100;
+            const int form = fb.variant % 10;
             long long gxf = 0;
+            int zx = 0, zy = 0;
             for (int k = 0; k < b.n; ++k) {
                 const ossg_field_desc& f = b.f[k];
                 fb.chunksA[k] = ceil_div(f.Nx, ZB);
-                fb.blocksA[k] = fb.chunksA[k] * f.nk;
+                fb.blocksA[k] = two_launches ? 0 : fb.chunksA[k] * f.nk;
+                zx = max(zx, fb.chunksA[k]); zy = max(zy, f.nk);
                 const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
-                const long long blocks = fb.blocksA[k] + (2 * rows + ZB - 1) / ZB;
+                const bool fast = f.elem_type == OSSG_F64 && f.Hx == 4 && (reinterpret_cast<uintptr_t>(f.data) & 31) == 0;
+                const long long threadsB = (form == 0 || !fast) ? 2 * rows : form == 1 ? rows : form == 2 ? (rows + 1) / 2 : (rows | 31) + 1;
+                const long long blocks = fb.blocksA[k] + (threadsB + ZB - 1) / ZB;
                 gxf = gxf > blocks ? gxf : blocks;
             }
             if (gxf > 0x7fffffffLL) return set_error(OSSG_EINVAL, "field too large for one launch");
+            if (two_launches) {
+                if (zy > 65535) return set_error(OSSG_EINVAL, "too many levels for one launch: %d", zy);
+                zipper_kernel<<<dim3(zx, zy, b.n), ZB, 0, s>>>(b);
+                OSSG_LAUNCH_CHECK("zipper_kernel");
+            }
             fill_fused_kernel<<<dim3((unsigned)gxf, b.n), ZB, 0, s>>>(fb);
             OSSG_LAUNCH_CHECK("fill_fused_kernel");
             continue;
         }
-        for (int k = 0; k < b.n; ++k) {
-            if (b.f[k].Hy == 0) continue;
+        for (int k = 0; k < b.n; ++k) {      // (Hy = 0: zipper_column still performs the row-Ny overwrite of y-Center fields, :102, :135)
             gx = max(gx, ceil_div(b.f[k].Nx, ZB));
             gy = max(gy, b.f[k].nk);
             const size_t prow = (size_t)(b.f[k].Ny + 2 * b.f[k].Hy) * (size_t)(b.f[k].Nz + 2 * b.f[k].Hz) * (size_t)(2 * b.f[k].Hx);
@@ -330,6 +434,8 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
 }  // namespace ossg
 
 using namespace ossg;
+
+extern "C" int ossg_experiment_fill_variant(int v) { ossg::g_fill_variant_override = v; return 0; }
 
 extern "C" int ossg_zipper_fill(const ossg_field_desc* f, void* stream)
 {

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from ._lib import ARRAY_NAMES, FoldWindow
 from .grids import (GPU, Float64, OffsetArray, OrthogonalSphericalShellGrid, R_Earth, Tripolar,
-                    _generate_z, _require_cuda, build_arrays, make_params)
+                    _generate_z, _require_cuda, build_arrays, build_arrays_cached, make_params)
 
 
 @dataclass(frozen=True)
@@ -85,7 +85,7 @@ def tile_of(Nx: int, Ny: int, Rx: int, Ry: int, rx: int, ry: int):
 
 
 def DistributedTripolarGrid(arch: Distributed, FT=Float64, *, size, southernmost_latitude=-80, halo=(4, 4, 4),
-                            radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70):
+                            radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70, _tables=None):
     Nx, Ny, Nz = (int(s) for s in size)
     Hx, Hy, Hz = (int(h) for h in halo)
     if Nx % 2 == 1:
@@ -93,11 +93,13 @@ def DistributedTripolarGrid(arch: Distributed, FT=Float64, *, size, southernmost
     i0, j0, nx, ny = tile_of(Nx, Ny, arch.Rx, arch.Ry, arch.rx, arch.ry)
     if ny - 1 < Hy and arch.is_top_row():
         raise ValueError(f"top-row tile has {ny} rows: the fold needs at least Hy+1 = {Hy + 1}")
+    if (arch.Ry > 1 and ny < Hy) or (arch.Rx > 1 and nx < Hx):      # a neighbour's halo is filled from INTERIOR rows / columns
+        raise ValueError(f"tile {nx}x{ny} of rank {arch.local_rank} is smaller than the halo ({Hx}, {Hy})")
     params = make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius,
                          tile=(i0, j0, nx, ny))
     _require_cuda()
     device = arch.torch_device()
-    parents = build_arrays(params, FT, device)
+    parents, tables = build_arrays_cached(params, FT, device, tables=_tables)
     zc = _generate_z(z, Nz)
     LX = "Periodic" if arch.Rx == 1 else "FullyConnected"
     LY = "RightConnected" if arch.ry == 0 else "FullyConnected"     # :75
@@ -106,7 +108,7 @@ def DistributedTripolarGrid(arch: Distributed, FT=Float64, *, size, southernmost
         conformal_mapping=Tripolar(north_poles_latitude, first_pole_longitude, southernmost_latitude),
         dtype=parents[0].dtype, topology=(LX, LY, "Bounded"),
         arrays={n: OffsetArray(t, Hx, Hy) for n, t in zip(ARRAY_NAMES, parents)},
-        i0=i0, j0=j0, global_size=(Nx, Ny, Nz))
+        i0=i0, j0=j0, global_size=(Nx, Ny, Nz), tables=tables)
 
 
 def reconstruct_global_grid(grid: OrthogonalSphericalShellGrid):
@@ -118,7 +120,8 @@ def reconstruct_global_grid(grid: OrthogonalSphericalShellGrid):
     return TripolarGrid(arch.child_architecture, grid.dtype, halo=grid.halo, size=grid.global_size,
                         north_poles_latitude=cm.north_poles_latitude,
                         first_pole_longitude=cm.first_pole_longitude,
-                        southernmost_latitude=cm.southernmost_latitude, z=grid.z.zf)
+                        southernmost_latitude=cm.southernmost_latitude, z=grid.z.zf,
+                        _tables=getattr(grid, "tables", None))      # a tile's 1-D tables are the global ones (same Nx, Ny)
 
 
 # ---------------------------------------------------------------- fold communication plan
@@ -250,6 +253,74 @@ def fold_exchange(fields: Sequence, packer=None, group=None) -> None:
         for (f, w, ne) in sel:
             packer.unpack(f, w, buf[off:off + ne], stream)
             off += ne
+
+
+class NcclExchange:
+    """fill_halo_regions! of fields on an (x, y)-partitioned tripolar grid through NCCL send/recv in
+    libossg_b200.so (ossg_fold_exchange + ossg_halo_exchange): per phase ONE pack kernel, ONE
+    ncclGroup with one message per partner, ONE unpack kernel, on the caller's stream, with a
+    persistent buffer -- no per-call allocation and no host wait.  This is the north-star's NCCL
+    arm; PeerFold / PeerHalo are the peer-memory forms measured against it.
+
+    Collective constructor over `group` (all ranks, same field list).  torch.distributed does not
+    expose its ncclComm_t, so the constructor creates one through ossg_nccl_comm_init_rank (the
+    unique id travels over `group`); a Julia host passes NCCL.jl's communicator instead."""
+
+    _comms: dict = {}
+
+    def __init__(self, fields: Sequence, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.fields = list(fields)
+        arch = self.fields[0].grid.architecture
+        self.arch = arch
+        L = _lib.lib()
+        dev = self.fields[0].data.device
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        key = (id(group), dev.index, world)
+        if key not in NcclExchange._comms:
+            uid = C.create_string_buffer(128)
+            if rank == 0:
+                _lib.check(L.ossg_nccl_get_unique_id(uid))
+            box = [bytes(uid.raw)]
+            dist.broadcast_object_list(box, src=0, group=group)
+            comm = C.c_void_p()
+            with torch.cuda.device(dev):
+                _lib.check(L.ossg_nccl_comm_init_rank(C.byref(comm), world, box[0], rank))
+            NcclExchange._comms[key] = comm
+        self.comm = NcclExchange._comms[key]
+        gN = self.fields[0].grid.global_size
+        self.layout = _lib.ExchangeLayout(gN[0], gN[1], arch.Rx, arch.Ry, rank, 0)
+        B = _lib.OSSG_MAX_PEER_BATCH
+        self._batches = []
+        need = 16
+        for b0 in range(0, len(self.fields), B):
+            chunk = self.fields[b0:b0 + B]
+            arr = (_lib.FieldDesc * len(chunk))(*[f.descriptor() for f in chunk])
+            self._batches.append((arr, len(chunk)))
+            need = max(need, L.ossg_fold_exchange_workspace_bytes(arr, len(chunk), C.byref(self.layout)),
+                       L.ossg_halo_exchange_workspace_bytes(arr, len(chunk), C.byref(self.layout)))
+        self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+
+    def fold(self, stream=None) -> None:
+        self._run(_lib.lib().ossg_fold_exchange, stream)
+
+    def halos(self, stream=None) -> None:
+        self._run(_lib.lib().ossg_halo_exchange, stream)
+
+    def _run(self, fn, stream) -> None:
+        import ctypes as C
+        dev = self.fields[0].data.device
+        stream = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        for (arr, n) in self._batches:
+            rc = fn(self.comm, arr, n, C.byref(self.layout), self.workspace.data_ptr(), self.workspace.numel(), stream)
+            if rc:
+                _lib.check(rc)
+
+    def __call__(self, stream=None) -> None:
+        """fold on the top row, then south/north rows, then west/east columns (asynchronous)."""
+        self.fold(stream)
+        self.halos(stream)
 
 
 class PeerFold:
@@ -469,8 +540,16 @@ def distributed_fill_halo_regions(fields: Sequence, stream=None, packer=None, gr
     """fill_halo_regions! for fields on a distributed tripolar grid: fold exchange on the top row
     (interior columns), then -- when x is not partitioned -- the local periodic west/east fill.
     Ordinary south/north and west/east neighbour exchanges are ordinary_halo_exchange()."""
-    fold_exchange(fields, packer=packer, group=group)
-    ordinary_halo_exchange(fields, packer=packer, group=group)
+    import contextlib
+    ctx = contextlib.nullcontext()
+    if stream is not None and fields and fields[0].data.is_cuda:
+        # `stream`: a torch.cuda.Stream (or a raw cudaStream_t); every pack / send / recv / unpack of
+        # the exchange is enqueued on it, ordered with the caller's producer kernels
+        ts = stream if isinstance(stream, torch.cuda.Stream) else torch.cuda.ExternalStream(int(stream), device=fields[0].data.device)
+        ctx = torch.cuda.stream(ts)
+    with ctx:
+        fold_exchange(fields, packer=packer, group=group)
+        ordinary_halo_exchange(fields, packer=packer, group=group)
 
 
 def ordinary_halo_exchange(fields: Sequence, packer=None, group=None) -> None:

@@ -167,6 +167,8 @@ class OrthogonalSphericalShellGrid:
     i0: int = 1
     j0: int = 1
     global_size: Optional[tuple] = None
+    # header + 1-D tables of the construction workspace (device); with_halo hands them to the next build
+    tables: Optional[torch.Tensor] = None
 
     _ALIASES = {"λ": "lam", "φ": "phi", "Δx": "dx", "Δy": "dy", "Az": "az"}
 
@@ -213,16 +215,17 @@ def y_domain(grid):
     return (float(grid.arrays["phi_ff"].parent.min()), 90)
 
 
-# ---- workspace cache (device scratch for the 1-D tables / FP64 coordinates) ---------------------
-_workspaces: dict = {}
-
-
-def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    key = (device.type, device.index)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+# ---- workspace (device scratch: header + 1-D tables, plus the FP64 coordinates of Float32 grids) --
+# Every build owns its workspace (two builds on different streams never share scratch).  The small
+# table prefix stays alive with the grid (`grid.tables`): with_halo / reconstruct_global_grid hand
+# it to the next build, whose table kernel then finds valid stamps and returns at once.
+def _new_workspace(nbytes: int, device: torch.device, stream_ptr: int, tables: Optional[torch.Tensor]) -> torch.Tensor:
+    L = _lib.lib()
+    ws = torch.empty(max(int(nbytes), 128), dtype=torch.uint8, device=device)
+    _lib.check(L.ossg_tripolar_workspace_init(ws.data_ptr(), ws.numel(), stream_ptr))
+    if tables is not None and tables.device == ws.device:
+        n = min(tables.numel(), ws.numel())
+        ws[:n].copy_(tables[:n], non_blocking=True)        # stamps + tables of the earlier grid (same stream)
     return ws
 
 
@@ -243,10 +246,12 @@ def make_params(size, halo, southernmost_latitude, north_poles_latitude, first_p
                           int(i0), int(j0), int(nx), int(ny))
 
 
-def build_arrays(params: TripolarParams, FT, device: torch.device, out: Optional[Sequence[torch.Tensor]] = None,
-                 stream: Optional[torch.cuda.Stream] = None) -> list:
-    """Run the construction kernels for the window described by `params` and return the 20
-    parent tensors, shape (ny+2Hy, nx+2Hx).  Asynchronous on `stream` (default: current)."""
+def build_arrays_cached(params: TripolarParams, FT, device: torch.device, out: Optional[Sequence[torch.Tensor]] = None,
+                        stream: Optional[torch.cuda.Stream] = None, tables: Optional[torch.Tensor] = None):
+    """Run the construction kernels for the window described by `params`; returns (the 20 parent
+    tensors of shape (ny+2Hy, nx+2Hx), the table prefix of the workspace to keep with the grid).
+    Asynchronous on `stream` (default: current); allocations and copies are made on that stream too.
+    `tables`: the table prefix of an earlier grid with the same size / latitudes (with_halo)."""
     L = _lib.lib()
     et = _elem_type(FT)
     tdt = torch.float64 if et == _lib.OSSG_F64 else torch.float32
@@ -257,18 +262,28 @@ def build_arrays(params: TripolarParams, FT, device: torch.device, out: Optional
     if nbytes == 0:
         _lib.check(L.ossg_tripolar_build(C.byref(params), et, _lib.ptr_array([0] * 20), None, 0, None))
     with torch.cuda.device(device):
-        if out is None:
-            out = [torch.empty(shape, dtype=tdt, device=device) for _ in range(20)]
-        ws = _workspace(nbytes, device)
         s = torch.cuda.current_stream(device) if stream is None else stream
-        rc = L.ossg_tripolar_build(C.byref(params), et, _lib.ptr_array([t.data_ptr() for t in out]),
-                                   ws.data_ptr(), ws.numel(), s.cuda_stream)
-    _lib.check(rc)
-    return list(out)
+        with torch.cuda.stream(s):
+            if out is None:
+                out = [torch.empty(shape, dtype=tdt, device=device) for _ in range(20)]
+            ws = _new_workspace(nbytes, device, s.cuda_stream, tables)
+            rc = L.ossg_tripolar_build(C.byref(params), et, _lib.ptr_array([t.data_ptr() for t in out]),
+                                       ws.data_ptr(), ws.numel(), s.cuda_stream)
+            _lib.check(rc)
+            tb = int(L.ossg_tripolar_table_bytes(C.byref(params)))
+            # Float32 grids: the workspace also holds 8 FP64 coordinate arrays; keep only the table prefix
+            keep = ws if ws.numel() <= 2 * tb else ws[:tb].clone()
+    return list(out), keep
+
+
+def build_arrays(params: TripolarParams, FT, device: torch.device, out: Optional[Sequence[torch.Tensor]] = None,
+                 stream: Optional[torch.cuda.Stream] = None) -> list:
+    """build_arrays_cached without the table prefix."""
+    return build_arrays_cached(params, FT, device, out, stream)[0]
 
 
 def TripolarGrid(arch=None, FT=Float64, *, size, southernmost_latitude=-80, halo=(4, 4, 4),
-                 radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70):
+                 radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70, _tables=None):
     """Return an OrthogonalSphericalShellGrid tripolar grid on the sphere
     (src/tripolar_grid.jl:59-333).  `arch` defaults to GPU(); a Distributed architecture
     dispatches to the distributed constructor (src/distributed_tripolar_grid.jl:24)."""
@@ -279,7 +294,7 @@ def TripolarGrid(arch=None, FT=Float64, *, size, southernmost_latitude=-80, halo
         return DistributedTripolarGrid(arch, FT, size=size, southernmost_latitude=southernmost_latitude,
                                        halo=halo, radius=radius, z=z,
                                        north_poles_latitude=north_poles_latitude,
-                                       first_pole_longitude=first_pole_longitude)
+                                       first_pole_longitude=first_pole_longitude, _tables=_tables)
     Nx, Ny, Nz = (int(s) for s in size)
     Hx, Hy, Hz = (int(h) for h in halo)
     if Nx % 2 == 1:          # src/tripolar_grid.jl:81-83
@@ -287,26 +302,40 @@ def TripolarGrid(arch=None, FT=Float64, *, size, southernmost_latitude=-80, halo
     params = make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius)
     _require_cuda()
     device = arch.torch_device() if isinstance(arch, GPU) else torch.device("cuda", torch.cuda.current_device())
-    parents = build_arrays(params, FT, device)
+    parents, tables = build_arrays_cached(params, FT, device, tables=_tables)
     if isinstance(arch, CPU):
-        parents = [t.cpu() for t in parents]      # synchronising D2H of the 20 arrays
+        parents = _to_host(parents)               # one pinned staging buffer, one synchronisation
     zc = _generate_z(z, Nz)
     tdt = parents[0].dtype
     grid = OrthogonalSphericalShellGrid(
         architecture=arch, Nx=Nx, Ny=Ny, Nz=Nz, Hx=Hx, Hy=Hy, Hz=Hz, Lz=zc.Lz, z=zc, radius=float(radius),
         conformal_mapping=Tripolar(north_poles_latitude, first_pole_longitude, southernmost_latitude),
         dtype=tdt, arrays={n: OffsetArray(t, Hx, Hy) for n, t in zip(ARRAY_NAMES, parents)},
-        global_size=(Nx, Ny, Nz))
+        global_size=(Nx, Ny, Nz), tables=tables)
     return grid
+
+
+def _to_host(parents: Sequence[torch.Tensor]) -> list:
+    """Device -> host copy of the 20 arrays for TripolarGrid(CPU()): all copies are queued
+    asynchronously into ONE pinned allocation and the stream is synchronised once (20 pageable
+    `.cpu()` calls would each stage through a bounce buffer and synchronise)."""
+    n = parents[0].numel()
+    host = torch.empty((len(parents),) + tuple(parents[0].shape), dtype=parents[0].dtype, pin_memory=True)
+    for k, t in enumerate(parents):
+        host[k].copy_(t, non_blocking=True)
+    torch.cuda.current_stream(parents[0].device).synchronize()
+    return [host[k] for k in range(len(parents))]
 
 
 def with_halo(new_halo, old_grid: OrthogonalSphericalShellGrid):
     """Rebuild the grid with a different halo (src/with_halo.jl:5-23, 25-44): re-runs the
-    constructor, as the reference does."""
+    constructor, as the reference does, on the old grid's 1-D tables (their stamps are still valid,
+    so the table kernel returns at once)."""
     from .distributed import Distributed
     cm = old_grid.conformal_mapping
     kw = dict(z=old_grid.z.zf, halo=new_halo, north_poles_latitude=cm.north_poles_latitude,
-              first_pole_longitude=cm.first_pole_longitude, southernmost_latitude=cm.southernmost_latitude)
+              first_pole_longitude=cm.first_pole_longitude, southernmost_latitude=cm.southernmost_latitude,
+              _tables=getattr(old_grid, "tables", None))      # fast path: the 1-D tables do not depend on the halo
     if isinstance(old_grid.architecture, Distributed):
         # src/with_halo.jl:25-44: global size from the local sizes; `radius` is not forwarded there
         return TripolarGrid(old_grid.architecture, old_grid.dtype, size=old_grid.global_size, **kw)

@@ -21,6 +21,13 @@ def test_library_loads_and_exports_every_declared_symbol(ossg):
         assert hasattr(L, n), f"{n} declared in include/ossg_b200.h but not exported"
     assert L.ossg_version() == 1
     assert isinstance(L.ossg_last_error(), bytes)
+    # the measurement / test utilities live in their own library, outside the product ABI
+    U = ossg._lib.testutil()
+    util_names = ossg._lib.declared_symbols(ossg._lib.UTIL_HEADER_PATH)
+    assert set(util_names) >= {"ossg_synth_field", "ossg_fp64_peak_probe", "ossg_selftest_sqrt_div", "ossg_peer_copy_probe"}
+    for n in util_names:
+        assert hasattr(U, n), f"{n} declared in include/ossg_b200_testutil.h but not exported"
+        assert n == "ossg_testutil_last_error" or not hasattr(L, n), f"{n} must not be exported by the product library"
 
 
 def test_header_cites_the_reference_for_each_entry_point(ossg):
@@ -70,8 +77,12 @@ def test_argument_errors_do_not_need_a_device(ossg):
     assert L.ossg_tripolar_build(C.byref(p), 7, out, 16, 1 << 20, None) == ossg._lib.OSSG_EINVAL
     assert L.ossg_tripolar_build(C.byref(p), 0, out, 16, 8, None) == ossg._lib.OSSG_EWORKSPACE
     assert L.ossg_tripolar_build(C.byref(p), 0, ossg._lib.ptr_array([4] * 20), 16, 1 << 20, None) == ossg._lib.OSSG_EALIGN
-    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 0) == ((4 * 60 + 4 * 30 + 9 * 5 + 1) // 2 * 2) * 8
-    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 1) == ((4 * 60 + 4 * 30 + 9 * 5 + 1) // 2 * 2) * 8 + 8 * 68 * 38 * 8
+    tb = ((16 + 4 * 60 + 4 * 30 + 9 * 5 + 1) // 2 * 2) * 8          # 128-byte stamp header + x/y tables + lat-lon rows
+    assert L.ossg_tripolar_table_bytes(C.byref(p)) == tb
+    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 0) == tb
+    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 1) == tb + 8 * 68 * 38 * 8
+    assert L.ossg_tripolar_workspace_init(None, 1 << 20, None) == ossg._lib.OSSG_EALIGN
+    assert L.ossg_tripolar_workspace_init(16, 64, None) == ossg._lib.OSSG_EWORKSPACE
     f = ossg._lib.FieldDesc(8, 0, 10, 10, 1, 4, 4, 4, 2, 0, 0, 0, 1.0)
     assert L.ossg_zipper_fill(C.byref(f), None) == ossg._lib.OSSG_ELOCATION
     f = ossg._lib.FieldDesc(8, 0, 11, 10, 1, 4, 4, 4, 0, 0, 0, 0, 1.0)

@@ -61,7 +61,7 @@ for lname, (rows, seg, group, gs, pitch, base) in layouts.items():
     for mode, chunk in ((0, 2048), (1, 4096), (2, 2048), (2, 8192), (2, 16384), (3, 2048), (3, 8192), (3, 16384)):
         for blocks in ((148 * 4,) if mode < 3 else (148 * 4, 148 * 8)):
             def fn():
-                _lib.check(L.ossg_peer_copy_probe(peer + base, src.data_ptr(), rows, seg, group, gs, pitch, chunk, mode, blocks, stream.cuda_stream))
+                _lib.check_util(_lib.testutil().ossg_peer_copy_probe(peer + base, src.data_ptr(), rows, seg, group, gs, pitch, chunk, mode, blocks, stream.cuda_stream))
             ms = timed(fn)
             results.append({"layout": lname, "mode": mode, "chunk": chunk, "blocks": blocks, "bytes": vol, "ms": ms, "gbs": vol / ms / 1e6})
             if rank == 0:
