@@ -45,11 +45,46 @@ PROFILE_TAG = "r01i"
 
 
 def partition_for(n):
-    """Construction partition at N GPUs: Y slabs, the reference's own (and only) distributed layout
-    (src/distributed_tripolar_grid.jl:28-31).  Every rank keeps the full x extent, so the
-    coordinate kernel's mirror-pair form applies.  (x, y) partitions are exercised by the parity
-    tests (every factorisation of N) and by the fold-exchange benchmark below, which uses (N, 1)."""
+    """Headline construction partition at N GPUs: Y slabs, the reference's own (and only) distributed
+    layout (src/distributed_tripolar_grid.jl:28-31).  Every rank keeps the full x extent, so the
+    coordinate kernel's mirror-pair form applies.  Every other factorisation of N is timed next to it
+    (`partition_sweep`) and checked against the oracle (`parity`)."""
     return (1, n)
+
+
+def factorisations(n):
+    return [(rx, n // rx) for rx in range(1, n + 1) if n % rx == 0]
+
+
+def mixed_partition(n):
+    """the (x, y) partition of the distributed fill benchmark / parity: both directions split when N allows"""
+    return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(n, (n, 1))
+
+
+# ------------------------------------------------------------------ independent host restatement of the synthetic field
+def host_synth_levels(seed, Nx, Ny, H, ks):
+    """numpy restatement of libossg_b200_testutil's ossg_synth_field (csrc/ossg_util.cu hash_value) for the GLOBAL
+    field at the 1-based interior levels `ks`: parent array (len(ks), Ny+2H, Nx+2H), halos poisoned with
+    the NaN payload 0x7ff8dead0000beef.  Independent of the device code it checks."""
+    import numpy as np
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def splitmix(x):
+        with np.errstate(over="ignore"):
+            x = x + np.uint64(0x9E3779B97F4A7C15)
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return (x ^ (x >> np.uint64(31))) & M
+
+    out = np.empty((len(ks), Ny + 2 * H, Nx + 2 * H), dtype=np.float64)
+    out.view(np.uint64)[...] = np.uint64(0x7ff8dead0000beef)
+    gi = np.arange(1, Nx + 1, dtype=np.uint64)[None, :]
+    gj = np.arange(1, Ny + 1, dtype=np.uint64)[:, None]
+    for n, k in enumerate(ks):
+        key = gi | (gj << np.uint64(21)) | (np.uint64(k) << np.uint64(42))
+        h = splitmix(np.uint64(seed) ^ splitmix(key))
+        out[n, H:H + Ny, H:H + Nx] = (h >> np.uint64(40)).astype(np.int64).astype(np.float64) * (1.0 / 8388608.0) - 1.0
+    return out
 
 
 # ------------------------------------------------------------------ clocks
@@ -195,149 +230,349 @@ def workload_config(n):
 
 
 # ------------------------------------------------------------------ own arm
-def run_own(args):
-    import torch
-    import torch.distributed as dist
-    import ossg_b200 as ossg
-    from ossg_b200 import _lib
-    from ossg_b200.distributed import tile_of
-    from ossg_b200.grids import make_params
+class Ctx:
+    """what every section needs: libraries, device, stream, rank layout"""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from ossg_b200 import _lib
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    # (NCCL_DEBUG is left as the environment has it: unset, NCCL prints nothing and stdout is the one JSON line)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the first communicator is created; stdout must
-        # carry the one JSON line only, so fd 1 points at stderr until that has happened
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-        finally:
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        pin_to_gpu_numa_node(self.local_rank)
+        if self.world > 1:
+            # NCCL prints its version banner on stdout when the first communicator is created; stdout must
+            # carry the one JSON line only, so fd 1 points at stderr until that has happened
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    L = _lib.lib()
-    if L.ossg_device_ok() != 0:
-        raise SystemExit("no usable CUDA device: " + _lib.last_error())
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()
+                torch.cuda.synchronize(self.dev)
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+        self.L = _lib.lib()
+        self.U = _lib.testutil()
+        if self.L.ossg_device_ok() != 0:
+            raise SystemExit("no usable CUDA device: " + _lib.last_error())
+        self.stream = torch.cuda.current_stream(self.dev)
 
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return int(x)
+        t = self.torch.tensor([int(x)], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def timed(self, fn, reps, warm=3):
+        """device ms per call of fn: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(reps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1) / reps)
+
+
+def pin_to_gpu_numa_node(index):
+    """run this process (and place its pinned host buffers, first touch) on the NUMA node the GPU hangs off;
+    best effort, silent when sysfs does not say"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+        if bus is None:
+            q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                               capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = q[-12:].lower() if q else None
+        if not bus:
+            return None
+        if isinstance(bus, int):
+            return None
+        node = int(open(f"/sys/bus/pci/devices/{str(bus).lower()}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:               # noqa: BLE001
+        return None
+
+
+class Construction:
+    """one rank's window of the workload grid under an (Rx, Ry) partition: contiguous output block,
+    own workspace (header initialised once, so steady-state builds find their 1-D tables in place)"""
+
+    def __init__(self, ctx, Rx, Ry):
+        from ossg_b200.distributed import tile_of
+        from ossg_b200.grids import make_params
+        torch, _lib, L, W = ctx.torch, ctx._lib, ctx.L, WORKLOAD
+        self.ctx, self.Rx, self.Ry = ctx, Rx, Ry
+        rx, ry = ctx.rank // Ry, ctx.rank % Ry
+        self.tile = tile_of(W["Nx"], W["Ny"], Rx, Ry, rx, ry)
+        i0, j0, nx, ny = self.tile
+        H = W["halo"]
+        self.params = make_params((W["Nx"], W["Ny"], W["Nz"]), (H, H, H), W["south"], W["north_poles_latitude"],
+                                  W["first_pole_longitude"], W["radius"], tile=self.tile)
+        self.shape = (ny + 2 * H, nx + 2 * H)
+        self.block = torch.empty((20,) + self.shape, dtype=torch.float64, device=ctx.dev)
+        self.optr = _lib.ptr_array([self.block[k].data_ptr() for k in range(20)])
+        nbytes = L.ossg_tripolar_workspace_bytes(C.byref(self.params), _lib.OSSG_F64)
+        self.ws = torch.empty(max(nbytes, 128), dtype=torch.uint8, device=ctx.dev)
+        _lib.check(L.ossg_tripolar_workspace_init(self.ws.data_ptr(), self.ws.numel(), ctx.stream.cuda_stream))
+
+    def step(self):
+        c = self.ctx
+        c._lib.check(c.L.ossg_tripolar_build(C.byref(self.params), c._lib.OSSG_F64, self.optr, self.ws.data_ptr(), self.ws.numel(),
+                                             c.stream.cuda_stream))
+
+    def cold_step(self):
+        """a build that cannot reuse the tables (fresh header): what the first constructor call of a run costs"""
+        c = self.ctx
+        c._lib.check(c.L.ossg_tripolar_workspace_init(self.ws.data_ptr(), self.ws.numel(), c.stream.cuda_stream))
+        self.step()
+
+
+def oracle_reference_to_shm(ctx):
+    """rank 0 builds the workload grid with the deterministic CPU oracle (all host threads) and leaves the 20
+    arrays in /dev/shm; every rank maps them.  Returns ({name: memmap}, seconds, cleanup)."""
+    import numpy as np
+    from oracle import oracle as orc
     W = WORKLOAD
-    Rx, Ry = partition_for(world)
-    rx, ry = rank // Ry, rank % Ry
-    i0, j0, nx, ny = tile_of(W["Nx"], W["Ny"], Rx, Ry, rx, ry)
+    d = f"/dev/shm/ossg_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if ctx.world > 1 else os.getpid()}"
+    secs = 0.0
+    if ctx.rank == 0:
+        os.makedirs(d, exist_ok=True)
+        o = orc.Oracle()
+        o.set_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        ref = o.build(orc.make_params((W["Nx"], W["Ny"], 1), (W["halo"],) * 3, W["south"], W["north_poles_latitude"],
+                                      W["first_pole_longitude"], W["radius"]))
+        secs = time.perf_counter() - t0
+        for n in orc.ALL_NAMES:
+            np.save(os.path.join(d, n + ".npy"), ref[n])
+        del ref
+    if ctx.world > 1:
+        box = [d]
+        ctx.dist.broadcast_object_list(box, src=0)
+        d = box[0]
+    ctx.barrier()
+    ref = {n: np.load(os.path.join(d, n + ".npy"), mmap_mode="r") for n in orc.ALL_NAMES}
+
+    def cleanup():
+        ctx.barrier()
+        if ctx.rank == 0:
+            for n in orc.ALL_NAMES:
+                try:
+                    os.remove(os.path.join(d, n + ".npy"))
+                except OSError:
+                    pass
+            try:
+                os.rmdir(d)
+            except OSError:
+                pass
+    return ref, secs, cleanup
+
+
+def parity_construction(ctx, partitions):
+    """every rank's 20 arrays under each partition against the matching slice of the oracle's serial grid
+    (src/distributed_tripolar_grid.jl:112-120: a tile IS that slice), bit for bit"""
+    import numpy as np
+    from oracle import oracle as orc
+    ref, secs, cleanup = oracle_reference_to_shm(ctx)
+    H = WORKLOAD["halo"]
+    out = {"oracle": "deterministic CPU restatement, full 1/12 degree grid, built once on rank 0", "oracle_build_s": secs}
+    try:
+        for (Rx, Ry) in partitions:
+            con = Construction(ctx, Rx, Ry)
+            con.step()
+            ctx.torch.cuda.synchronize(ctx.dev)
+            i0, j0, nx, ny = con.tile
+            bad, worst = 0, 0.0
+            for k, n in enumerate(orc.ALL_NAMES):
+                got = con.block[k].cpu().numpy()
+                want = np.ascontiguousarray(ref[n][j0 - 1:j0 - 1 + ny + 2 * H, i0 - 1:i0 - 1 + nx + 2 * H])
+                diff = got.view(np.uint64) != want.view(np.uint64)
+                nb = int(diff.sum())
+                if nb:
+                    bad += nb
+                    denom = np.maximum(np.abs(want[diff]), np.finfo(np.float64).tiny)
+                    worst = max(worst, float((np.abs(got[diff] - want[diff]) / denom).max()))
+            total = ctx.sum_over_ranks(bad)
+            out[f"({Rx},{Ry})"] = {"mismatches": total, "max_rel_err": ctx.max_over_ranks(worst), "arrays": 20,
+                                   "elements_per_array_global": (WORKLOAD["Nx"] + 2 * H) * (WORKLOAD["Ny"] + 2 * H)}
+            del con
+            ctx.torch.cuda.empty_cache()
+    finally:
+        cleanup()
+    out["mismatches"] = sum(v["mismatches"] for v in out.values() if isinstance(v, dict))
+    return out
+
+
+def run_own(args):
+    ctx = Ctx(args)
+    torch, dist, _lib, L = ctx.torch, ctx.dist, ctx._lib, ctx.L
+    import ossg_b200 as ossg
+    world, rank, dev, stream = ctx.world, ctx.rank, ctx.dev, ctx.stream
+    W = WORKLOAD
     H = W["halo"]
-    params = make_params((W["Nx"], W["Ny"], W["Nz"]), (H, H, H), W["south"], W["north_poles_latitude"],
-                         W["first_pole_longitude"], W["radius"], tile=(i0, j0, nx, ny))
-    shape = (ny + 2 * H, nx + 2 * H)
-    out = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(20)]
-    optr = _lib.ptr_array([t.data_ptr() for t in out])
-    nbytes = L.ossg_tripolar_workspace_bytes(C.byref(params), _lib.OSSG_F64)
-    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    Rx, Ry = partition_for(world)
+    con = Construction(ctx, Rx, Ry)
+    i0, j0, nx, ny = con.tile
+    shape = con.shape
 
-    def step():
-        _lib.check(L.ossg_tripolar_build(C.byref(params), _lib.OSSG_F64, optr, ws.data_ptr(), ws.numel(), stream.cuda_stream))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    # ---- the timed region: K steps of the full construction (tables in place after the first step, as in any
+    # run that constructs more than one grid of a size: with_halo, reconstruct_global_grid)
     for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
+        con.step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        step()
+        con.step()
     e1.record(stream)
-    barrier()
-    ms_local = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    else:
-        ms_total = ms_local
-    ms_step = ms_total / args.steps
+    ctx.barrier()
+    ms_step = ctx.max_over_ranks(e0.elapsed_time(e1)) / args.steps
     cells_global = W["Nx"] * W["Ny"]
     value = cells_global / (ms_step * 1e-3)
+    # the same with a fresh workspace header before every build (the 1-D tables recomputed: a first constructor call)
+    ms_cold = ctx.timed(con.cold_step, max(3, min(args.steps, 10)))
 
     # ---- per-kernel device times (events between the kernels), same workload
     prof = (C.c_float * 4)()
     acc = [0.0] * 4
     nprof = max(3, min(args.steps, 10))
     for _ in range(nprof):
-        _lib.check(L.ossg_tripolar_build_profiled(C.byref(params), _lib.OSSG_F64, optr, ws.data_ptr(), ws.numel(),
+        _lib.check(L.ossg_tripolar_build_profiled(C.byref(con.params), _lib.OSSG_F64, con.optr, con.ws.data_ptr(), con.ws.numel(),
                                                   stream.cuda_stream, prof))
         for k in range(4):
             acc[k] += prof[k] / nprof
     kernel_ms = dict(zip(["tables", "coords", "metrics_tile", "metrics_frame"], acc))
 
-    # ---- end to end through the public API with host buffers: construct + D2H of the 20 arrays
-    host = [torch.empty(shape, dtype=torch.float64).pin_memory() for _ in range(20)]
-    pin_params = bytes(params)       # the only input: 64 bytes of scalars, passed as kernel arguments
+    # ---- end to end with host buffers: construct + ONE device-to-host copy of the contiguous 20-array block
+    # into pinned memory allocated on the GPU's NUMA node (what TripolarGrid(CPU()) delivers)
+    host = torch.empty((20,) + shape, dtype=torch.float64, pin_memory=True)
+    pin_params = bytes(con.params)       # the only input: 64 bytes of scalars, passed as kernel arguments
 
     def e2e_step():
-        step()
-        for h, d in zip(host, out):
-            h.copy_(d, non_blocking=True)
+        con.step()
+        host.copy_(con.block, non_blocking=True)
 
     e2e_steps = max(1, min(args.steps, 5))
     e2e_step()
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize(dev)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_local = (time.perf_counter() - t0) / e2e_steps
+    ctx.barrier()
+    e2e_s = ctx.max_over_ranks(e2e_local)
     d2h_bytes = 20 * shape[0] * shape[1] * 8
     clocks = sampler.stop() if rank == 0 else None
+    del host
+
+    # ---- wall clock of the public constructor call (allocation of the 20 arrays and the workspace included)
+    def public_call():
+        if world == 1:
+            g = ossg.TripolarGrid(ossg.GPU(dev.index), size=(W["Nx"], W["Ny"], W["Nz"]), halo=(H, H, H))
+        else:
+            g = ossg.TripolarGrid(ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(Rx, Ry)), size=(W["Nx"], W["Ny"], W["Nz"]), halo=(H, H, H))
+        torch.cuda.synchronize(dev)
+        return g
+    del con.block
+    public_call()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        public_call()
+    public_ms = ctx.max_over_ranks((time.perf_counter() - t0) / 3 * 1e3)
+    torch.cuda.empty_cache()
 
     # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels)
     ms = C.c_float(); fl = C.c_double()
-    _lib.check_util(_lib.testutil().ossg_fp64_peak_probe(20000, C.byref(ms), C.byref(fl), stream.cuda_stream))
+    _lib.check_util(ctx.U.ossg_fp64_peak_probe(20000, C.byref(ms), C.byref(fl), stream.cuda_stream))
     fp64_peak_tflops = fl.value / (ms.value * 1e-3) / 1e12
-
-    # ---- zipper halo fill (second half of the metric): 4 fields c,u,v,zeta on the local tile
-    # (last GPU section: whatever happens in the peer-memory plumbing, the construction numbers above stand)
-    del out, ws
+    del con
     torch.cuda.empty_cache()
+
+    # ---- parity under the driver's eyes: this rank's arrays against the oracle, for the headline partition, (N,1)
+    # and one mixed factorisation (N = 1: the serial grid)
+    parts = [(Rx, Ry)]
+    for cand in ((world, 1), mixed_partition(world)):
+        if cand not in parts:
+            parts.append(cand)
+    parity = {"construction": parity_construction(ctx, parts)}
+
+    extra = {}
     if world == 1:
         zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny)
+        extra["configs"] = bench_small_configs(ctx)
     else:
+        # every factorisation of N, timed like the headline (BASELINE config 4; SURVEY section 8e)
+        sweep = {}
+        for (sx_, sy_) in factorisations(world):
+            c2 = Construction(ctx, sx_, sy_)
+            t = ctx.timed(c2.step, max(5, min(args.steps, 20)))
+            sweep[f"({sx_},{sy_})"] = {"ms_per_step": t, "cells_per_s": cells_global / (t * 1e-3),
+                                       "coords_kernel": "mirror pairs" if sx_ == 1 else "per element"}
+            del c2
+            torch.cuda.empty_cache()
+        extra["partition_sweep"] = sweep
         # (a failure of the peer-memory plumbing -- e.g. CUDA IPC unavailable in the container -- must not
         # take the construction number down with it)
         zipper = {}
-        for key, fn in (("distributed_fill_halo_regions", bench_distributed_fill), ("fold_exchange", bench_fold_exchange)):
+        for key, fn in (("fold_exchange", bench_fold_exchange), ("distributed_fill_halo_regions", bench_distributed_fill)):
             try:
-                zipper[key] = fn(world, rank, dev)
+                zipper[key] = fn(ctx)
+                par = zipper[key].pop("parity", None)
+                if par is not None:
+                    parity[key] = par
             except Exception as e:          # noqa: BLE001
                 zipper[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()
+    parity["mismatches"] = sum(int(v.get("mismatches", 0)) for v in parity.values() if isinstance(v, dict))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if parity["mismatches"]:
+            sys.exit(3)
         return
 
     peaks = {}
@@ -374,14 +609,7 @@ def run_own(args):
 
     roofline_zipper = None
     if world == 1 and isinstance(zipper, dict):
-        best = zipper.get("repeat100_zipper_batch8_larger_than_l2")
-        if not best or "gbs" not in best:
-            best = zipper.get("batch4")
-        if best and "gbs" in best:
-            roofline_zipper = {"bound": "hbm", "kernel": "zipper_kernel", "achieved": best["gbs"], "peak": hbm_peak,
-                               "unit": "GB/s", "frac": best["gbs"] / hbm_peak, "peak_source": peak_src,
-                               "algorithmic_bytes_per_launch": best["algorithmic_bytes"],
-                               "measured_on": "repeat100_zipper_batch8_larger_than_l2" if "what" in best and "8 fields" in best["what"] else "batch4"}
+        roofline_zipper = zipper_roofline(zipper, hbm_peak, peak_src)
     cpu_threads = os.cpu_count() or 1
     cpu_rate, cpu_dt, cpu_what = cpu_construct_rate(cpu_threads, 3, 1)
     if world == 1 and isinstance(zipper, dict):
@@ -392,23 +620,117 @@ def run_own(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
         "kernel_ms": kernel_ms,
+        "first_call": {"ms_per_step": ms_cold, "cells_per_s": cells_global / (ms_cold * 1e-3),
+                       "what": "workspace header reset before every build: the 1-D tables are recomputed (tables_kernel's full cost)"},
         "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_zipper": roofline_zipper,
         "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": cpu_what + ", 3 steps, CPU restatement of reference v0.2.1 (glibc libm); "
                                    "Julia is not installed"},
         "e2e": {"value": cells_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": len(pin_params),
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
-                "what": "ossg_tripolar_build + copy of the 20 arrays to pinned host buffers (TripolarGrid(CPU()) equivalent)"},
+                "what": "ossg_tripolar_build + ONE copy of the contiguous 20-array block to a pinned host buffer on the GPU's NUMA node "
+                        "(TripolarGrid(CPU()) equivalent)",
+                "public_constructor_wall_ms": public_ms,
+                "public_constructor_what": "wall clock of ossg.TripolarGrid(GPU(), size=...) per call, allocation of the 20 arrays and "
+                                           "the workspace included, device synchronised"},
         "gpu_launches": args.steps * 4,
+        "parity": parity,
         "clocks": clocks,
         "zipper": zipper,
     }
+    line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         try:
             dist.destroy_process_group()
         except Exception:               # noqa: BLE001  (the line is out; a teardown error changes nothing)
             pass
+    if parity["mismatches"]:
+        sys.exit(3)
+
+
+# FLUSHED configuration first (the headline of the zipper roofline), the repeat loop beside it; `traffic` = DRAM bytes per
+# launch from the committed ncu captures of the SAME loops (tools/prof_fill.py; profiles/r02_fill_dram.md)
+NCU_TRAFFIC_ZIPPER_FLUSH4 = None
+NCU_TRAFFIC_ZIPPER_LOOP8 = None
+NCU_TRAFFIC_FILL_FLUSH4 = None
+
+
+def zipper_roofline(zipper, hbm_peak, peak_src):
+    out = None
+    head = zipper.get("batch4_clean_flush") or zipper.get("batch4")
+    if head and "gbs" in head:
+        out = {"bound": "hbm", "kernel": "zipper_kernel", "achieved": head["gbs"], "peak": hbm_peak, "unit": "GB/s",
+               "frac": head["gbs"] / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": head["algorithmic_bytes"],
+               "traffic": NCU_TRAFFIC_ZIPPER_FLUSH4,
+               "measured_on": "batch4_clean_flush: c,u,v,zeta per launch, L2 flushed (256 MB write + 256 MB read) before every timed launch"}
+        for key, traffic in (("batch4", NCU_TRAFFIC_ZIPPER_FLUSH4), ("repeat100_zipper_batch8_larger_than_l2", NCU_TRAFFIC_ZIPPER_LOOP8),
+                             ("fill_halo_regions_batch4", NCU_TRAFFIC_FILL_FLUSH4)):
+            z = zipper.get(key)
+            if z and "gbs" in z:
+                out[key] = {"achieved": z["gbs"], "frac": z["gbs"] / hbm_peak, "algorithmic_bytes_per_launch": z["algorithmic_bytes"],
+                            "traffic": traffic}
+    return out
+
+
+def bench_small_configs(ctx):
+    """BASELINE.json configs A, B, C (60x30, 360x180x50, 1440x720x75; Float64 and Float32): device time of the full
+    construction and of fill_halo_regions! of c,u,v,zeta, next to the CPU restatement of the reference on one thread
+    (step for step like the reference's own kernels) and on all host threads."""
+    import numpy as np
+    from oracle import oracle as orc
+    from ossg_b200.grids import make_params
+    torch, _lib, L, W = ctx.torch, ctx._lib, ctx.L, WORKLOAD
+    out = {}
+    o = orc.Oracle(libm=True)
+    H = W["halo"]
+    for name, (Nx, Ny, Nz) in (("A_60x30x1", (60, 30, 1)), ("B_360x180x50", (360, 180, 50)), ("C_1440x720x75", (1440, 720, 75))):
+        res = {}
+        p = make_params((Nx, Ny, Nz), (H, H, H), W["south"], W["north_poles_latitude"], W["first_pole_longitude"], W["radius"])
+        for et, tdt, tag in ((_lib.OSSG_F64, torch.float64, "f64"), (_lib.OSSG_F32, torch.float32, "f32")):
+            shape = (Ny + 2 * H, Nx + 2 * H)
+            block = torch.empty((20,) + shape, dtype=tdt, device=ctx.dev)
+            optr = _lib.ptr_array([block[k].data_ptr() for k in range(20)])
+            nb = L.ossg_tripolar_workspace_bytes(C.byref(p), et)
+            ws = torch.empty(max(nb, 128), dtype=torch.uint8, device=ctx.dev)
+            _lib.check(L.ossg_tripolar_workspace_init(ws.data_ptr(), ws.numel(), ctx.stream.cuda_stream))
+
+            def step():
+                _lib.check(L.ossg_tripolar_build(C.byref(p), et, optr, ws.data_ptr(), ws.numel(), ctx.stream.cuda_stream))
+
+            def cold():
+                _lib.check(L.ossg_tripolar_workspace_init(ws.data_ptr(), ws.numel(), ctx.stream.cuda_stream))
+                step()
+            t = ctx.timed(step, 50, warm=5)
+            tc = ctx.timed(cold, 50, warm=5)
+            res[f"construct_{tag}"] = {"ms": t, "cells_per_s": Nx * Ny / (t * 1e-3), "first_call_ms": tc}
+            # fill_halo_regions! of c,u,v,zeta, repeated back to back (BASELINE config 3: "repeated fill_halo_regions!")
+            fshape = (Nz + 2 * H, Ny + 2 * H, Nx + 2 * H)
+            specs = [((0, 0), 1.0), ((1, 0), -1.0), ((0, 1), -1.0), ((1, 1), 1.0)]
+            fields = [torch.zeros(fshape, dtype=tdt, device=ctx.dev) for _ in specs]
+            descs = (_lib.FieldDesc * 4)(*[_lib.FieldDesc(f.data_ptr(), et, Nx, Ny, Nz, H, H, H, loc[0], loc[1], 0, 0, sg)
+                                            for f, (loc, sg) in zip(fields, specs)])
+            esz = 8 if et == _lib.OSSG_F64 else 4
+            algo = sum(2 * H * Nx * Nz * esz + (Nx * Nz * esz if loc[1] == 0 else 0) for loc, _ in specs)
+            algo_full = algo + 4 * (Ny + 2 * H) * (Nz + 2 * H) * 2 * (2 * H) * esz
+            tz = ctx.timed(lambda: _lib.check(L.ossg_zipper_fill_batch(descs, 4, ctx.stream.cuda_stream)), 200, warm=5)
+            tf = ctx.timed(lambda: _lib.check(L.ossg_fill_halo_regions_batch(descs, 4, ctx.stream.cuda_stream)), 200, warm=5)
+            res[f"zipper_batch4_{tag}"] = {"us": tz * 1e3, "algorithmic_bytes": algo, "gbs": algo / (tz * 1e-3) / 1e9}
+            res[f"fill_halo_regions_batch4_{tag}"] = {"us": tf * 1e3, "algorithmic_bytes": algo_full, "gbs": algo_full / (tf * 1e-3) / 1e9}
+            del fields, block, ws
+        # CPU restatement: one thread (a default `julia` session), then all host threads
+        po = orc.make_params((Nx, Ny, 1), (H, H, H), W["south"], W["north_poles_latitude"], W["first_pole_longitude"], W["radius"])
+        for threads, tag in ((1, "cpu_1_thread"), (os.cpu_count() or 1, "cpu_all_threads")):
+            o.set_threads(threads)
+            o.build(po)
+            reps = 3 if Nx * Ny < 500000 else 1
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                o.build(po)
+            dt = (time.perf_counter() - t0) / reps
+            res[tag] = {"ms": dt * 1e3, "cells_per_s": Nx * Ny / dt, "threads": threads, "kind": "port"}
+        out[name] = res
+    return out
 
 
 def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
@@ -520,77 +842,153 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
     return res
 
 
-# ------------------------------------------------------------------ fold exchange (N > 1)
-def bench_fold_exchange(world, rank, dev):
-    """Fold exchange of c,u,v,zeta (FP64, Nz=100, Hy=4) on the 1/12 degree grid split (N,1)."""
-    import torch
-    import torch.distributed as dist
-    import ossg_b200 as ossg
-    from ossg_b200 import _lib
-    from ossg_b200.distributed import PeerFold, fold_exchange, tile_of
-    Nx, Ny, Nz, H = 4320, 2160, 100, 4
-    arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(world, 1))
-    i0, j0, nx, ny = tile_of(Nx, Ny, world, 1, arch.rx, arch.ry)
+# ------------------------------------------------------------------ distributed fields (N > 1)
+class _StubGrid:
+    """only what Field / the exchange classes read from a grid (the construction arrays are not needed here)"""
 
-    class G:        # grid stub: only sizes are needed by Field / fold_exchange
-        pass
-    g = G()
+
+def make_fields(ctx, Rx, Ry, nfields):
+    """c, u, v, zeta (repeated) on this rank's tile of the workload grid, synthetic values by global index"""
+    import ossg_b200 as ossg
+    from ossg_b200.distributed import tile_of
+    torch = ctx.torch
+    W = WORKLOAD
+    Nx, Ny, Nz, H = W["Nx"], W["Ny"], W["Nz"], W["halo"]
+    arch = ossg.Distributed(ossg.GPU(ctx.dev.index), ossg.Partition(Rx, Ry))
+    i0, j0, nx, ny = tile_of(Nx, Ny, Rx, Ry, arch.rx, arch.ry)
+    g = _StubGrid()
     g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz = nx, ny, Nz, H, H, H
     g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
     g.size, g.halo = (nx, ny, Nz), (H, H, H)
     C_, F_ = ossg.Center, ossg.Face
-    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)] * 4      # c, u, v, zeta four times: batches of up to 16
+    locs = ([(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)] * ((nfields + 3) // 4))[:nfields]
     shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
-    all_fields = [ossg.Field(loc, g, data=torch.empty(shape, dtype=torch.float64, device=dev)) for loc in locs]
-    fields = all_fields[:4]
-    L = _lib.lib()
-    for k, f in enumerate(all_fields):
-        d = f.descriptor()
-        _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
-    for _ in range(3):
-        fold_exchange(fields)
-    torch.cuda.synchronize(dev)
-    dist.barrier()
-    reps = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fold_exchange(fields)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    # bytes each rank receives per exchange: Hy rows (+1 for y-Center) x nx columns x Nz levels per field
-    # (the row-Ny overwrite only concerns the right half of the globe: half the ranks on average)
-    recv = sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fields)
-    out = {"partition": f"({world},1)", "fields": 4, "recv_bytes_per_rank": recv,
-           "nccl_pack_send_unpack": {"ms_per_exchange": float(ms.item()),
-                                     "gbs_per_direction_per_gpu": recv / (float(ms.item()) * 1e-3) / 1e9}}
-    # ---- the same exchange as ONE kernel per rank over NVLink peer memory; 1, 2 and 4 fields per
-    # launch separate the fixed cost (launch + two flag barriers) from the bandwidth
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(reps):
-            fn()
-        a1.record()
-        torch.cuda.synchronize(dev)
-        t = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    fields = [ossg.Field(loc, g, data=torch.empty(shape, dtype=torch.float64, device=ctx.dev)) for loc in locs]
+    return fields, arch, (i0, j0, nx, ny)
 
+
+def synth(ctx, fields, tile):
+    for k, f in enumerate(fields):
+        d = f.descriptor()
+        ctx._lib.check_util(ctx.U.ossg_synth_field(C.byref(d), 0x5EED + k, tile[0], tile[1], ctx.stream.cuda_stream))
+
+
+class FillReference:
+    """The expected result of ONE fill of the synthetic fields at the first and the last interior level: the GLOBAL
+    field regenerated on the host by an independent numpy restatement of the hash (host_synth_levels), filled by the
+    oracle (zipper, or zipper + periodic x = fill_halo_regions!), of which every rank owns a window
+    (src/distributed_tripolar_grid.jl:112-120).  Rank 0 generates, everybody maps."""
+
+    def __init__(self, ctx, nfields):
+        import numpy as np
+        W = WORKLOAD
+        self.ctx, self.ks = ctx, [1, W["Nz"]]
+        d = f"/dev/shm/ossg_fill_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        if ctx.rank == 0:
+            os.makedirs(d, exist_ok=True)
+            for k in range(nfields):
+                np.save(os.path.join(d, f"f{k}.npy"), host_synth_levels(0x5EED + k, W["Nx"], W["Ny"], W["halo"], self.ks))
+        box = [d]
+        ctx.dist.broadcast_object_list(box, src=0)
+        self.dir = box[0]
+        ctx.barrier()
+        self.base = [np.load(os.path.join(self.dir, f"f{k}.npy"), mmap_mode="r") for k in range(nfields)]
+        self.cache = {}
+
+    def expected(self, k, f, full):
+        import numpy as np
+        from oracle import oracle as orc
+        key = (k, full)
+        if key not in self.cache:
+            W = WORKLOAD
+            o = FillReference._oracle = getattr(FillReference, "_oracle", None) or orc.Oracle()
+            c = np.array(self.base[k])                                   # (2, Ny+2H, Nx+2H): two levels, no z halo
+            d = f.descriptor()
+            fn = o.fill_halo_regions if full else o.zipper
+            fn(c, W["Nx"], W["Ny"], 2, W["halo"], W["halo"], 0, d.locx, d.locy, d.sign)
+            self.cache[key] = c
+        return self.cache[key]
+
+    def mismatches(self, fields, tile, full):
+        """differing bit patterns between this rank's tiles (two levels per field, whole window: interior and
+        every halo) and the oracle's global result"""
+        import numpy as np
+        W = WORKLOAD
+        H, Nz = W["halo"], W["Nz"]
+        i0, j0, nx, ny = tile
+        bad = 0
+        for k, f in enumerate(fields):
+            want = self.expected(k, f, full)[:, j0 - 1:j0 - 1 + ny + 2 * H, i0 - 1:i0 - 1 + nx + 2 * H]
+            got = self.ctx.torch.stack([f.data[H + kk - 1] for kk in self.ks]).cpu().numpy()
+            bad += int((got.view(np.uint64) != np.ascontiguousarray(want).view(np.uint64)).sum())
+        return bad
+
+    def close(self):
+        self.ctx.barrier()
+        if self.ctx.rank == 0:
+            for n in os.listdir(self.dir):
+                os.remove(os.path.join(self.dir, n))
+            os.rmdir(self.dir)
+
+
+# ------------------------------------------------------------------ fold exchange (N > 1)
+def bench_fold_exchange(ctx):
+    """Fold exchange of c,u,v,zeta (FP64, Nz=100, Hy=4) on the 1/12 degree grid split (N,1): the NCCL arm of the C ABI
+    (ossg_fold_exchange: pack kernel, one ncclGroup, unpack kernel) against ONE kernel per rank over NVLink peer memory
+    (pull, push, bulk push).  Every form is first checked against the oracle on freshly generated fields."""
+    from ossg_b200.distributed import NcclExchange, PeerFold
+    world = ctx.world
+    H, Nz = WORKLOAD["halo"], WORKLOAD["Nz"]
+    all_fields, arch, tile = make_fields(ctx, world, 1, 16)
+    nx = tile[2]
+    fields = all_fields[:4]
+    reps = 20
+
+    def recv_bytes(fs):
+        # bytes each rank receives per exchange: Hy rows (+1 for y-Center) x nx columns x Nz levels per field
+        # (the row-Ny overwrite only concerns the right half of the globe: half the ranks on average)
+        return sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fs)
+
+    ref = FillReference(ctx, 4)
+    parity = {"what": "one exchange of freshly generated c,u,v,zeta; both boundary levels of every tile, whole window, against "
+                      "oracle.zipper of the global field regenerated on the host (numpy hash)", "partition": f"({world},1)"}
+    out = {"partition": f"({world},1)", "fields": 4, "recv_bytes_per_rank": recv_bytes(fields)}
+
+    # ---- NCCL arm (library path)
+    nccl = NcclExchange(fields)
+    synth(ctx, fields, tile)
+    nccl.fold()
+    ctx.torch.cuda.synchronize(ctx.dev)
+    parity["nccl"] = {"mismatches": ctx.sum_over_ranks(ref.mismatches(fields, tile, full=False))}
+    res = {}
+    for nf in (4, 8, 16):
+        ex = NcclExchange(all_fields[:nf])
+        t = ctx.timed(ex.fold, reps)
+        rb = recv_bytes(all_fields[:nf])
+        res[f"fields{nf}"] = {"ms_per_exchange": t, "recv_bytes_per_rank": rb, "gbs_per_direction_per_gpu": rb / (t * 1e-3) / 1e9}
+        del ex
+    res["what"] = "ossg_fold_exchange: one pack kernel, one ncclGroup (one ncclSend + ncclRecv per partner), one unpack kernel; persistent buffer"
+    out["nccl_pack_send_unpack"] = res
+
+    # ---- the same exchange as ONE kernel per rank over NVLink peer memory; 1 ... 16 fields per
+    # launch separate the fixed cost (launch + flag round trips) from the bandwidth
     for push in (False, True, "bulk"):
         res = {}
         key_out = "peer_kernel_push_bulk" if push == "bulk" else "peer_kernel_push" if push else "peer_kernel_pull"
         try:
+            pf = PeerFold(fields, push=push)
+            synth(ctx, fields, tile)
+            ctx.barrier()
+            pf()
+            ctx.torch.cuda.synchronize(ctx.dev)
+            parity[key_out] = {"mismatches": ctx.sum_over_ranks(ref.mismatches(fields, tile, full=False))}
+            pf.close()
             for nf in (1, 2, 4, 8, 16):
-                t = timed(PeerFold(all_fields[:nf], push=push))
-                rb = sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in all_fields[:nf])
+                pf = PeerFold(all_fields[:nf], push=push)
+                t = ctx.timed(pf, reps)
+                rb = recv_bytes(all_fields[:nf])
                 res[f"fields{nf}"] = {"ms_per_exchange": t, "recv_bytes_per_rank": rb, "gbs_per_direction_per_gpu": rb / (t * 1e-3) / 1e9}
+                pf.close()
         except Exception as e:          # noqa: BLE001  (one form failing must not drop the others)
             res["error"] = f"{type(e).__name__}: {e}"[:300]
             out[key_out] = res
@@ -599,71 +997,58 @@ def bench_fold_exchange(world, rank, dev):
         slope = (t8["ms_per_exchange"] - t1["ms_per_exchange"]) / (t8["recv_bytes_per_rank"] - t1["recv_bytes_per_rank"])
         res["marginal_gbs"] = 1e-6 / slope
         res["fixed_us"] = 1e3 * (t1["ms_per_exchange"] - slope * t1["recv_bytes_per_rank"])
-        # NVLink 5 nominal 900 GB/s per direction; 735 GB/s is what a bidirectional cudaMemcpyPeer
-        # reaches on this pool (tools/p2p_probe.py, profiles/r01_p2p_probe.txt)
+        # NVLink 5 nominal 900 GB/s per direction; 770 GB/s is what the driver's own copy probe measured on this pool
+        # (VERDICT round 1), 731-741 what a cudaMemcpyPeer reaches (tools/p2p_probe.py, profiles/r01_p2p_probe.txt)
         for key in ("fields4", "fields8", "fields16"):
             res[key]["frac_of_nvlink_900"] = res[key]["gbs_per_direction_per_gpu"] / 900.0
-            res[key]["frac_of_measured_copy_735"] = res[key]["gbs_per_direction_per_gpu"] / 735.0
+            res[key]["frac_of_measured_770"] = res[key]["gbs_per_direction_per_gpu"] / 770.0
         out[key_out] = res
+    ref.close()
+    parity["mismatches"] = sum(v["mismatches"] for v in parity.values() if isinstance(v, dict))
+    out["parity"] = parity
     return out
 
 
-def bench_distributed_fill(world, rank, dev):
+def bench_distributed_fill(ctx):
     """fill_halo_regions! of c,u,v,zeta (FP64, Nz=100, halo 4) on the 1/12 degree grid in an (x, y)
     partition -- the distributed_bickley_jet-style halo-fill loop (BASELINE config 5): fold on the
-    top row + south/north rows + west/east columns.  NCCL form (pack/send/recv/unpack through
-    torch.distributed) against the NVLink peer-memory form (three kernels per fill, PeerHalo)."""
-    import torch
-    import torch.distributed as dist
-    import ossg_b200 as ossg
-    from ossg_b200 import _lib
-    from ossg_b200.distributed import PeerHalo, distributed_fill_halo_regions, tile_of
-    Nx, Ny, Nz, H = 4320, 2160, 100, 4
-    Rx, Ry = {2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
-    arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(Rx, Ry))
-    i0, j0, nx, ny = tile_of(Nx, Ny, Rx, Ry, arch.rx, arch.ry)
-
-    class G:
-        pass
-    g = G()
-    g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz = nx, ny, Nz, H, H, H
-    g.architecture, g.dtype, g.arrays, g.i0, g.j0, g.global_size = arch, torch.float64, {}, i0, j0, (Nx, Ny, Nz)
-    g.size, g.halo = (nx, ny, Nz), (H, H, H)
-    C_, F_ = ossg.Center, ossg.Face
-    locs = [(C_, C_, C_), (F_, C_, C_), (C_, F_, C_), (F_, F_, C_)]
-    shape = (Nz + 2 * H, ny + 2 * H, nx + 2 * H)
-    fields = [ossg.Field(loc, g, data=torch.zeros(shape, dtype=torch.float64, device=dev)) for loc in locs]
-    L = _lib.lib()
-    for k, f in enumerate(fields):
-        d = f.descriptor()
-        _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(d), 0x5EED + k, i0, j0, torch.cuda.current_stream(dev).cuda_stream))
+    top row + south/north rows + west/east columns.  NCCL arm of the C ABI (ossg_fold_exchange +
+    ossg_halo_exchange) against the NVLink peer-memory form (three or four kernels per fill, PeerHalo);
+    the eager torch.distributed form of round 1 stays as a third line."""
+    from ossg_b200.distributed import NcclExchange, PeerHalo, distributed_fill_halo_regions
+    world = ctx.world
+    H, Nz = WORKLOAD["halo"], WORKLOAD["Nz"]
+    Rx, Ry = mixed_partition(world)
+    fields, arch, tile = make_fields(ctx, Rx, Ry, 4)
+    i0, j0, nx, ny = tile
     reps = 10
-
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(reps):
-            fn()
-        a1.record()
-        torch.cuda.synchronize(dev)
-        t = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    t_nccl = timed(lambda: distributed_fill_halo_regions(fields))
-    t_peer = timed(PeerHalo(fields))
+    ref = FillReference(ctx, 4)
+    parity = {"what": "one fill of freshly generated c,u,v,zeta; both boundary levels of every tile, whole window (interior, fold, "
+                      "south/north and west/east halos, corners), against oracle.fill_halo_regions of the global field", "partition": f"({Rx},{Ry})"}
+    nccl = NcclExchange(fields)
+    peer = PeerHalo(fields)
+    for name, fn in (("nccl", nccl), ("peer_memory", peer), ("torch_eager_nccl", lambda: distributed_fill_halo_regions(fields))):
+        synth(ctx, fields, tile)
+        ctx.barrier()
+        fn()
+        ctx.torch.cuda.synchronize(ctx.dev)
+        parity[name] = {"mismatches": ctx.sum_over_ranks(ref.mismatches(fields, tile, full=True))}
+    ref.close()
+    t_nccl = ctx.timed(nccl, reps)
+    t_peer = ctx.timed(peer, reps)
+    t_eager = ctx.timed(lambda: distributed_fill_halo_regions(fields), 5)
+    peer.close()
     # bytes a rank receives per fill: fold rows (top row only), 2 x Hy rows, 2 x Hx columns over the parent extent
     levels, sx, sy = Nz + 2 * H, nx + 2 * H, ny + 2 * H
     recv = len(fields) * 8 * ((2 if Ry > 1 else 0) * H * sx * levels * (0.5 if Ry == 2 else 1.0) + 2 * H * sy * levels)
     if arch.is_top_row():
         recv += sum((H + (0.5 if f.descriptor().locy == 0 else 0)) * nx * Nz * 8 for f in fields)
+    parity["mismatches"] = sum(v["mismatches"] for v in parity.values() if isinstance(v, dict))
     return {"partition": f"({Rx},{Ry})", "fields": len(fields), "approx_recv_bytes_top_row_rank": recv,
-            "nccl": {"ms_per_fill": t_nccl}, "peer_memory": {"ms_per_fill": t_peer, "kernels_per_fill": 3 if arch.is_top_row() else 2},
-            "speedup": t_nccl / t_peer}
+            "nccl": {"ms_per_fill": t_nccl, "what": "ossg_fold_exchange + ossg_halo_exchange (C ABI): per phase one pack kernel, one ncclGroup, one unpack kernel"},
+            "peer_memory": {"ms_per_fill": t_peer, "kernels_per_fill": 4 if arch.is_top_row() else 3},
+            "torch_eager_nccl": {"ms_per_fill": t_eager, "what": "round-1 arm: eager slicing + batch_isend_irecv + host waits"},
+            "speedup_peer_over_nccl": t_nccl / t_peer, "parity": parity}
 
 
 def main():

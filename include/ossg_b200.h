@@ -240,9 +240,11 @@ int ossg_nccl_comm_destroy(void* comm);
  * the field arrays of the other top-row ranks (CUDA IPC, ossg_ipc_export / ossg_ipc_open) and its
  * zipper kernel loads the source rows straight from the owner (the mirror rank; for x-Face fields
  * also one column of its neighbour) while writing its own north halo -- each element crosses
- * NVLink once.  Ranks order themselves with release/acquire epoch flags in IPC-mapped device
- * memory (data-ready barrier at kernel start, read-done barrier at kernel end); the host never
- * synchronises and no NCCL call is on this path.  Same result as ossg_zipper_fill on the global
+ * NVLink once.  Ranks order themselves with release/acquire flags in IPC-mapped device memory (an
+ * "arrived" epoch at kernel start; at kernel end every block signals its partners and block 0 waits
+ * for all partners' blocks); the host never synchronises and no NCCL call is on this path.  A rank
+ * that never makes the matching call is a programming error: the waiting kernels trap after
+ * OSSG_PEER_TIMEOUT_MS and the next CUDA call of the process fails.  Same result as ossg_zipper_fill on the global
  * field (src/zipper_boundary_condition.jl:70-155), bit for bit.                                 */
 #define OSSG_MAX_PEERS 8
 #define OSSG_MAX_PEER_BATCH 16
@@ -252,16 +254,21 @@ typedef struct ossg_ipc_handle { unsigned char bytes[OSSG_IPC_HANDLE_BYTES]; } o
 int ossg_ipc_export(const void* device_ptr, ossg_ipc_handle* handle, uint64_t* offset);
 /* maps a peer's allocation into this process (once per handle; cached) and returns base+offset  */
 int ossg_ipc_open(const ossg_ipc_handle* handle, uint64_t offset, void** peer_ptr);
+/* one ossg_ipc_close per successful ossg_ipc_open; the mapping goes away with the last one (the
+ * caller makes sure no kernel that uses the mapped pointers is still in flight)                  */
+int ossg_ipc_close(const ossg_ipc_handle* handle);
 
 typedef struct ossg_peer_fold {
     int32_t gNx;                            /* global Nx                                         */
     int32_t me, nranks;                     /* this rank's x-index in the top row, Rx (<= 8)     */
     int32_t i0[OSSG_MAX_PEERS];             /* global first interior column of top-row rank r    */
     int32_t nx[OSSG_MAX_PEERS];             /* its width                                         */
-    void*   flags_local;                    /* this rank's flag block: 2*OSSG_MAX_PEERS uint64 +
-                                               uint32 block counter + uint32 error word (set to 1
-                                               when a peer did not show up within ~2 s), i.e.
-                                               2*OSSG_MAX_PEERS+1 uint64, zero-initialised once   */
+    void*   flags_local;                    /* this rank's flag block: ready[OSSG_MAX_PEERS] epochs,
+                                               done[OSSG_MAX_PEERS] arrival counts (uint64), then one
+                                               uint64 whose upper half is the error word (set to 1 when
+                                               a partner did not show up within OSSG_PEER_TIMEOUT_MS,
+                                               default 120 s; the kernel then TRAPS): 2*OSSG_MAX_PEERS+1
+                                               uint64, zero-initialised once, never reset            */
     void*   flags_peer[OSSG_MAX_PEERS];     /* the peers' flag blocks, peer-mapped ([me] unused)  */
     uint64_t epoch;                         /* 1, 2, 3, ... one per call, the same on all ranks  */
     int32_t push;                           /* 0: each rank loads its sources from the owners;
@@ -270,7 +277,9 @@ typedef struct ossg_peer_fold {
                                                2: as 1, rows staged in shared memory in destination
                                                order and sent as bulk copies (cp.async.bulk, one
                                                transfer per row segment); same on all ranks        */
-    int32_t reserved;
+    int32_t bulk_waves;                     /* push == 2: work items per resident block the kernel aims for when
+                                               it narrows its chunks; 0 = library default (3, or
+                                               OSSG_PEER_BULK_WAVES), < 0 = always the widest chunks  */
 } ossg_peer_fold;
 
 typedef struct ossg_peer_field {

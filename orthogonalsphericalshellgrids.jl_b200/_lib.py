@@ -65,7 +65,7 @@ class PeerFoldDesc(C.Structure):
     _fields_ = [("gNx", C.c_int32), ("me", C.c_int32), ("nranks", C.c_int32),
                 ("i0", C.c_int32 * OSSG_MAX_PEERS), ("nx", C.c_int32 * OSSG_MAX_PEERS),
                 ("flags_local", C.c_void_p), ("flags_peer", C.c_void_p * OSSG_MAX_PEERS),
-                ("epoch", C.c_uint64), ("push", C.c_int32), ("reserved", C.c_int32)]
+                ("epoch", C.c_uint64), ("push", C.c_int32), ("bulk_waves", C.c_int32)]
 
 
 class PeerField(C.Structure):
@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
     L.ossg_nccl_comm_destroy.argtypes = [C.c_void_p]
     L.ossg_ipc_export.argtypes = [C.c_void_p, C.POINTER(IpcHandle), C.POINTER(C.c_uint64)]
     L.ossg_ipc_open.argtypes = [C.POINTER(IpcHandle), C.c_uint64, C.POINTER(C.c_void_p)]
+    L.ossg_ipc_close.argtypes = [C.POINTER(IpcHandle)]
     L.ossg_zipper_fill_peer.argtypes = [C.POINTER(PeerField), C.c_int, C.POINTER(PeerFoldDesc), C.c_void_p]
     L.ossg_halo_exchange_peer.argtypes = [C.POINTER(PeerHaloField), C.c_int, C.POINTER(PeerHaloDesc), C.c_void_p]
     _lib = L

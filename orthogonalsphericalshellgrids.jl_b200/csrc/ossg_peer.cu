@@ -10,15 +10,24 @@
 // rows from the owner's field through a peer-mapped pointer (CUDA IPC) and writes its own halo: one
 // launch, every element crosses NVLink once and is written once, no staging buffer.
 //
-// Ordering between ranks (no host synchronisation, no NCCL call on this path):
-//   start: block 0 publishes epoch -> ready[me] on every peer (st.release.sys); every block waits
-//          until ready[r] >= epoch for all r (ld.acquire.sys).  A rank's kernel is stream-ordered
-//          after the kernels that produced its interior, so "kernel started" == "interior ready".
-//   end:   the last block to finish publishes epoch -> done[me] on every peer and waits for
-//          done[r] >= epoch from all r before it exits, so work queued behind this kernel cannot
-//          overwrite rows a peer is still reading.
-// Flags live in a small per-rank device array that is itself IPC-mapped by the peers; epochs only
-// grow, nothing is ever reset.
+// Ordering between ranks (no host synchronisation, no NCCL call on this path).  Every rank owns a flag
+// block in device memory that its partners map through CUDA IPC: ready[r] (an epoch) and done[r] (an
+// arrival count), r = partner rank.
+//   start: block 0 stores epoch -> ready[me] on every partner (st.release.sys).  Every warp prefetches
+//          the local rows of its first work item, then waits until ready[r] >= epoch for all partners r
+//          (ld.acquire.sys on LOCAL memory).  A rank's kernel is stream-ordered after the kernels that
+//          produced its interior and consumed its halo, so "kernel started" == "interior ready, halo free".
+//   end:   every block, once its stores (or peer loads) are done, fences at system scope and adds to
+//          done[me] on every partner (red.release.sys.add).  The arrivals of one kernel always sum to
+//          PEER_ARRIVALS (block 0 adds the remainder), so "rank r has finished exchange e" is
+//          done[r] >= e * PEER_ARRIVALS with no per-exchange state.  Only block 0 waits for that, from
+//          all partners, before it exits: work queued behind the kernel then sees a complete halo (push)
+//          and cannot overwrite rows a partner still reads (pull).  No block counter, no local barrier
+//          between the blocks: the fences of different blocks overlap.
+// Flags only grow, nothing is ever reset.  A partner that never shows up (a rank that did not make the
+// matching call) is a programming error: after OSSG_PEER_TIMEOUT_MS (default 120 s, 0 = wait forever)
+// the waiting kernel raises the error word of its flag block and TRAPS -- the next CUDA call of this
+// process fails loudly instead of continuing on stale halos.
 #include <mutex>
 #include <vector>
 #include <cstring>
@@ -43,16 +52,75 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Bounded wait for a peer's epoch: a missing partner (a rank that never made the matching call)
-// must not hang the GPU.  After ~2 s (4e9 cycles) the wait gives up and raises the error word in
-// this rank's flag block (uint32 right after the block counter); the fill is then incomplete.
-__device__ __forceinline__ void wait_epoch(const unsigned long long* flag, unsigned long long epoch, unsigned int* error_word)
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v)
 {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flag) < epoch) {
-        if (clock64() - t0 > 4000000000ll) { atomicExch(error_word, 1u); break; }
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long PEER_ARRIVALS = 1ull << 20;     // arrivals per kernel and partner (more than any grid has blocks)
+
+// Wait until *flag >= target.  A missing partner must not hang the GPU for ever and must not pass
+// silently either: on timeout the error word is raised (for post-mortem inspection) and the kernel traps.
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long target, unsigned int* error_word,
+                                          unsigned long long timeout_ns)
+{
+    if (ld_acquire_sys(flag) >= target) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(flag) < target) {
+        if (timeout_ns && (++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+            atomicExch(error_word, 1u);
+            __threadfence_system();
+            __trap();
+        }
     }
 }
+
+struct PeerSync {
+    unsigned long long* mine;            // this rank's flag block: ready[MAX_PEERS], done[MAX_PEERS], {unused, error word}
+    void* const* peer;                   // the partners' flag blocks
+    int me, nranks;
+    unsigned partners;
+    unsigned long long epoch, timeout_ns;
+    __device__ __forceinline__ unsigned int* error_word() const { return reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1; }
+    __device__ __forceinline__ bool is_partner(int r) const { return r < nranks && r != me && ((partners >> r) & 1u); }
+
+    // block 0 announces this rank (call before the prefetch of the first item)
+    __device__ __forceinline__ void announce() const
+    {
+        const int t = threadIdx.x;
+        if (blockIdx.x == 0 && is_partner(t))
+            st_release_sys(static_cast<unsigned long long*>(peer[t]) + me, epoch);
+    }
+    // every warp waits for all partners' announcements (lane r polls partner r)
+    __device__ __forceinline__ void wait_ready() const
+    {
+        const int lane = threadIdx.x & 31;
+        if (is_partner(lane)) wait_flag(mine + lane, epoch, error_word(), timeout_ns);
+        __syncwarp();
+    }
+    // end of the block's work: signal every partner; block 0 then waits for every partner's kernel
+    __device__ __forceinline__ void finish() const
+    {
+        __syncthreads();                                              // the block's stores / peer loads are issued ...
+        const int t = threadIdx.x;
+        if (t < 32) {
+            __threadfence_system();                                   // ... and performed, as far as any observer of the signal is concerned
+            if (is_partner(t)) {
+                const unsigned long long n = blockIdx.x == 0 ? PEER_ARRIVALS - (gridDim.x - 1) : 1ull;
+                red_release_sys_add(static_cast<unsigned long long*>(peer[t]) + OSSG_MAX_PEERS + me, n);
+                if (blockIdx.x == 0) wait_flag(mine + OSSG_MAX_PEERS + t, epoch * PEER_ARRIVALS, error_word(), timeout_ns);
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // loads of peer memory: system-scope relaxed, so that no non-coherent cache serves an older epoch
 __device__ __forceinline__ double peer_load(const double* p)
@@ -76,6 +144,7 @@ struct PeerBatch {
     int chunks, levels;          // work items: n fields x levels x chunks of PB columns (bulk push: of bulk_cw columns)
     int bulk_cw;
     long long nitems;
+    unsigned long long timeout_ns;
 };
 
 // one thread per (local column i, level): all Hy source rows are loaded (over NVLink) before any
@@ -269,26 +338,38 @@ __device__ __forceinline__ void peer_chunk_push_bulk(const ossg_peer_field& p, c
     }
 }
 
+// local source rows of the block's first work item, requested from DRAM while the announcements travel
+__device__ __forceinline__ void prefetch_first_item(const PeerBatch& b)
+{
+    if ((long long)blockIdx.x >= b.nitems || !b.fold.push || (threadIdx.x & 7)) return;
+    const int chunk = (int)(blockIdx.x % b.chunks);
+    const long long rest = blockIdx.x / b.chunks;
+    const int kk = (int)(rest % b.levels), fi = (int)(rest / b.levels);
+    const ossg_field_desc& f = b.pf[fi].f;
+    if (kk >= f.nk) return;
+    const size_t esz = f.elem_type == OSSG_F64 ? 8 : 4;
+    const size_t sx = (size_t)(f.Nx + 2 * f.Hx), sxy = sx * (size_t)(f.Ny + 2 * f.Hy);
+    const int cw = b.fold.push == 2 ? b.bulk_cw : PB;
+    const char* base = static_cast<const char*>(f.data) + ((size_t)(f.k0 + kk) * sxy + (size_t)f.Hx) * esz;
+    const int rows = f.Hy + (f.locy == OSSG_CENTER ? 1 : 0);
+    for (int col = chunk * cw + threadIdx.x; col < min((chunk + 1) * cw, f.Nx); col += PB)
+        for (int q = 0; q < rows; ++q) {
+            const int row = q == f.Hy ? f.Ny + f.Hy - 1 : (f.locy ? f.Ny : f.Ny - 1) + f.Hy - 1 - q;
+            prefetch_l2(base + ((size_t)row * sx + col) * esz);
+        }
+}
+
 __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(const __grid_constant__ PeerBatch b)
 {
     const ossg_peer_fold& fd = b.fold;
-    unsigned long long* mine = static_cast<unsigned long long*>(fd.flags_local);
     __shared__ __align__(128) unsigned char s_bulk[BULK_NREG * BULK_ROWS * BULK_RS * sizeof(double)];   // staging rows of the bulk push form
-    // ---- start barrier with the partner ranks (owners of the mirror columns): lane r talks to rank r
-    const int t = threadIdx.x;
-    const bool partner = t < fd.nranks && t != fd.me && ((b.partners >> t) & 1u);
-    unsigned int* error_word = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1;
-    if (partner) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[t]) + fd.me, fd.epoch);
-        }
-        wait_epoch(mine + t, fd.epoch, error_word);
-    }
-    __syncthreads();
+    const PeerSync sync{ static_cast<unsigned long long*>(fd.flags_local), fd.flags_peer, fd.me, fd.nranks, b.partners, fd.epoch, b.timeout_ns };
+    sync.announce();
+    prefetch_first_item(b);
+    sync.wait_ready();
 
-    // persistent blocks: one flag wait per block, then a block-stride loop over the work items
-    // (field, level, chunk of PB columns) -- few waves, many NVLink loads in flight per SM
+    // persistent blocks: a block-stride loop over the work items (field, level, chunk of PB columns)
+    // -- few waves, many NVLink transfers in flight per SM
     for (long long item = blockIdx.x; item < b.nitems; item += gridDim.x) {
         const int chunk = (int)(item % b.chunks);
         const long long rest = item / b.chunks;
@@ -313,28 +394,11 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) zipper_peer_kernel(con
         }
     }
 
-    // ---- end barrier (last block only, lane r talks to rank r)
-    __shared__ int is_last;
-    if (fd.push == 2) {                                               // bulk stores of this block complete and ordered
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // before the generic-proxy release below
+    if (fd.push == 2) {                                               // bulk stores of this thread complete (async proxy) and
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // ordered before the generic-proxy signal in finish()
         asm volatile("fence.proxy.async;" ::: "memory");
     }
-    __syncthreads();
-    if (t == 0) {
-        unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);
-        __threadfence();                                              // release this block's stores ...
-        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-        if (is_last) {
-            __threadfence();                                          // ... and acquire everybody else's
-            atomicExch(counter, 0u);                                  // ready for the next launch (stream-ordered)
-        }
-    }
-    __syncthreads();
-    if (is_last && partner) {
-        __threadfence_system();
-        st_release_sys(static_cast<unsigned long long*>(fd.flags_peer[t]) + OSSG_MAX_PEERS + fd.me, fd.epoch);
-        wait_epoch(mine + OSSG_MAX_PEERS + t, fd.epoch, error_word);
-    }
+    sync.finish();
 }
 
 // ------------------------------------------------------------------ ordinary halos (push)
@@ -345,6 +409,7 @@ struct HaloBatch {
     unsigned int partners;
     long long items_per_field;           // phase 0: 2 directions x Hy rows x parent levels x column chunks
     int chunks;                          // phase 0: ceil((Nx + 2Hx) / PB); phase 1: ceil(rows / PB)
+    unsigned long long timeout_ns;
 };
 
 template <typename T>
@@ -413,18 +478,9 @@ __device__ __forceinline__ void halo_cols_push(const ossg_peer_halo_field& h, lo
 __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) halo_peer_kernel(const __grid_constant__ HaloBatch b)
 {
     const ossg_peer_halo& hd = b.halo;
-    unsigned long long* mine = static_cast<unsigned long long*>(hd.flags_local);
-    const int t = threadIdx.x;
-    const bool partner = t < hd.nranks && t != hd.me && ((b.partners >> t) & 1u);
-    unsigned int* error_word = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS) + 1;
-    if (partner) {                                                    // start barrier (see zipper_peer_kernel)
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            st_release_sys(static_cast<unsigned long long*>(hd.flags_peer[t]) + hd.me, hd.epoch);
-        }
-        wait_epoch(mine + t, hd.epoch, error_word);
-    }
-    __syncthreads();
+    const PeerSync sync{ static_cast<unsigned long long*>(hd.flags_local), hd.flags_peer, hd.me, hd.nranks, b.partners, hd.epoch, b.timeout_ns };
+    sync.announce();
+    sync.wait_ready();                                                // (see zipper_peer_kernel)
 
     const long long nitems = b.items_per_field * b.n;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -442,28 +498,18 @@ __global__ void __launch_bounds__(PB, PEER_BLOCKS_PER_SM) halo_peer_kernel(const
             else halo_cols_push<float>(h, it, b.chunks);
         }
     }
+    sync.finish();
+}
 
-    __shared__ int is_last;                                           // end barrier
-    __syncthreads();
-    if (t == 0) {
-        unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);
-        __threadfence();
-        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-        if (is_last) {
-            __threadfence();
-            atomicExch(counter, 0u);
-        }
-    }
-    __syncthreads();
-    if (is_last && partner) {
-        __threadfence_system();
-        st_release_sys(static_cast<unsigned long long*>(hd.flags_peer[t]) + OSSG_MAX_PEERS + hd.me, hd.epoch);
-        wait_epoch(mine + OSSG_MAX_PEERS + t, hd.epoch, error_word);
-    }
+// how long a kernel waits for a partner before it traps (OSSG_PEER_TIMEOUT_MS, read once; 0 = for ever)
+static unsigned long long peer_timeout_ns()
+{
+    static const int ms = env_int("OSSG_PEER_TIMEOUT_MS", 120000);
+    return ms <= 0 ? 0ull : (unsigned long long)ms * 1000000ull;
 }
 
 // ------------------------------------------------------------------ CUDA IPC plumbing
-struct OpenedHandle { unsigned char h[64]; void* base; };
+struct OpenedHandle { unsigned char h[64]; void* base; int refs; };
 static std::mutex g_ipc_mu;
 static std::vector<OpenedHandle> g_opened;
 
@@ -512,8 +558,9 @@ extern "C" int ossg_ipc_open(const ossg_ipc_handle* handle, uint64_t offset, voi
 {
     if (!handle || !peer_ptr) return set_error(OSSG_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lock(g_ipc_mu);
-    for (const OpenedHandle& o : g_opened)
+    for (OpenedHandle& o : g_opened)
         if (std::memcmp(o.h, handle->bytes, 64) == 0) {
+            ++o.refs;
             *peer_ptr = static_cast<char*>(o.base) + offset;
             return 0;
         }
@@ -524,9 +571,25 @@ extern "C" int ossg_ipc_open(const ossg_ipc_handle* handle, uint64_t offset, voi
     OpenedHandle o;
     std::memcpy(o.h, handle->bytes, 64);
     o.base = base;
+    o.refs = 1;
     g_opened.push_back(o);
     *peer_ptr = static_cast<char*>(base) + offset;
     return 0;
+}
+
+extern "C" int ossg_ipc_close(const ossg_ipc_handle* handle)
+{
+    if (!handle) return set_error(OSSG_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lock(g_ipc_mu);
+    for (size_t k = 0; k < g_opened.size(); ++k)
+        if (std::memcmp(g_opened[k].h, handle->bytes, 64) == 0) {
+            if (--g_opened[k].refs > 0) return 0;
+            void* base = g_opened[k].base;
+            g_opened.erase(g_opened.begin() + (long)k);
+            OSSG_CUDA_TRY(cudaIpcCloseMemHandle(base));
+            return 0;
+        }
+    return set_error(OSSG_EINVAL, "handle is not open");
 }
 
 extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields, const ossg_peer_fold* fold, void* stream)
@@ -579,8 +642,8 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
         const int nx = fd.nx[fd.me];
         const int nch_min = ceil_div(nx, BULK_CW);
         const int nch_cap = max(nch_min, nx / PB);
-        int waves = 3;                                                // (OSSG_PEER_BULK_WAVES=0: always the widest chunks)
-        if (const char* e = getenv("OSSG_PEER_BULK_WAVES")) waves = atoi(e) < 0 ? 0 : atoi(e);
+        static const int env_waves = env_int("OSSG_PEER_BULK_WAVES", 3);  // (read once; 0: always the widest chunks)
+        const int waves = fd.bulk_waves > 0 ? fd.bulk_waves : fd.bulk_waves < 0 ? 0 : (env_waves < 0 ? 0 : env_waves);
         const int nch_bal = ceil_div((long long)waves * resident, (long long)nfields * gy);
         const int nch = min(max(nch_bal, nch_min), nch_cap);
         b.bulk_cw = ceil_div(nx, nch);
@@ -605,6 +668,7 @@ extern "C" int ossg_zipper_fill_peer(const ossg_peer_field* fields, int nfields,
     b.chunks = gx;
     b.levels = gy;
     b.nitems = (long long)gx * gy * nfields;
+    b.timeout_ns = peer_timeout_ns();
     const int grid = (int)(b.nitems < resident ? b.nitems : resident);
     zipper_peer_kernel<<<grid, PB, 0, as_stream(stream)>>>(b);
     OSSG_LAUNCH_CHECK("zipper_peer_kernel");
@@ -672,6 +736,7 @@ extern "C" int ossg_halo_exchange_peer(const ossg_peer_halo_field* fields, int n
     if (items == 0) return 0;
     b.items_per_field = items;
     b.chunks = chunks;
+    b.timeout_ns = peer_timeout_ns();
     int dev = 0, sms = 0;
     OSSG_CUDA_TRY(cudaGetDevice(&dev));
     OSSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -148,6 +148,11 @@ __device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1
 //        [ E-interior(r) | E-halo(r) | W-halo(r+1) | W-interior(r+1) ]        (4 x 32 B = 128 B)
 // with  W-halo(r) <- E-interior(r)  and  E-halo(r) <- W-interior(r).
 struct Piece32 { double a, b, c, d; };
+// every halo piece of the field is a 32-byte aligned run of 4 doubles (base, row pitch and Nx all multiples of 32 bytes)
+__host__ __device__ inline bool piece32_ok(const ossg_field_desc& f)
+{
+    return f.elem_type == OSSG_F64 && f.Hx == 4 && f.Nx % 4 == 0 && (reinterpret_cast<uintptr_t>(f.data) & 31) == 0;
+}
 template <int HINT>
 __device__ __forceinline__ Piece32 ld_piece32(const void* p)
 {
@@ -250,7 +255,7 @@ template <int HINT>
 __device__ __forceinline__ void fused_part_b(const ossg_field_desc& f, int form, long long t, bool all_rows)
 {
     const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
-    const bool fast = f.elem_type == OSSG_F64 && f.Hx == 4 && (reinterpret_cast<uintptr_t>(f.data) & 31) == 0;
+    const bool fast = piece32_ok(f);
     if (form == 0 || !fast) {
         if (t >= 2 * rows) return;
         const long long row = t >> 1;
@@ -397,7 +402,7 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
                 fb.blocksA[k] = two_launches ? 0 : fb.chunksA[k] * f.nk;
                 zx = max(zx, fb.chunksA[k]); zy = max(zy, f.nk);
                 const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
-                const bool fast = f.elem_type == OSSG_F64 && f.Hx == 4 && (reinterpret_cast<uintptr_t>(f.data) & 31) == 0;
+                const bool fast = piece32_ok(f);
                 const long long threadsB = (form == 0 || !fast) ? 2 * rows : form == 1 ? rows : form == 2 ? (rows + 1) / 2 : (rows | 31) + 1;
                 const long long blocks = fb.blocksA[k] + (threadsB + ZB - 1) / ZB;
                 gxf = gxf > blocks ? gxf : blocks;

@@ -370,10 +370,13 @@ class PeerFold:
         top = {g["rx"]: g for g in gathered if g is not None}
         assert sorted(top) == list(range(arch.Rx)), "every top-row rank must construct the same PeerFold"
 
+        self._opened = []
+
         def open_(hb, off):
             h, out = _lib.IpcHandle(), C.c_void_p()
             C.memmove(h.bytes, hb, 64)
             _lib.check(L.ossg_ipc_open(C.byref(h), off, C.byref(out)))
+            self._opened.append(hb)
             return out.value
 
         gNx = self.fields[0].grid.global_size[0]
@@ -418,9 +421,24 @@ class PeerFold:
                 _lib.check(rc)
 
     def timed_out(self) -> bool:
-        """True when a kernel of this rank gave up waiting for a peer (synchronises the device)."""
+        """True when a kernel of this rank gave up waiting for a peer (synchronises the device).  The
+        kernel traps in that case, so normally the synchronisation itself raises first."""
         word = int(self.flags[2 * _lib.OSSG_MAX_PEERS].item())
         return (word >> 32) != 0
+
+    def close(self) -> None:
+        """Release the peer mappings (collective in spirit: call it on every rank once no exchange is
+        in flight; the fields themselves stay alive as long as this object does)."""
+        import ctypes as C
+        if getattr(self, "_opened", None):
+            torch.cuda.synchronize(self.fields[0].data.device)
+            L = _lib.lib()
+            for hb in self._opened:
+                h = _lib.IpcHandle()
+                C.memmove(h.bytes, hb, 64)
+                L.ossg_ipc_close(C.byref(h))
+            self._opened = []
+        self.active = False
 
 
 class PeerHalo:
@@ -449,10 +467,13 @@ class PeerHalo:
             _lib.check(L.ossg_ipc_export(ptr, C.byref(h), C.byref(off)))
             return bytes(h.bytes), int(off.value)
 
+        self._opened = []
+
         def open_(hb, off):
             h, out = _lib.IpcHandle(), C.c_void_p()
             C.memmove(h.bytes, hb, 64)
             _lib.check(L.ossg_ipc_open(C.byref(h), off, C.byref(out)))
+            self._opened.append(hb)
             return out.value
 
         # staging buffers of the column phase (x split only): [batch][from_west | from_east], 8 bytes per element
@@ -534,6 +555,18 @@ class PeerHalo:
     def timed_out(self) -> bool:
         w = [int(t[2 * _lib.OSSG_MAX_PEERS].item()) >> 32 for t in self.flags]
         return any(w) or (self.fold.active and self.fold.timed_out())
+
+    def close(self) -> None:
+        import ctypes as C
+        self.fold.close()
+        if self._opened:
+            torch.cuda.synchronize(self.fields[0].data.device)
+            L = _lib.lib()
+            for hb in self._opened:
+                h = _lib.IpcHandle()
+                C.memmove(h.bytes, hb, 64)
+                L.ossg_ipc_close(C.byref(h))
+            self._opened = []
 
 
 def distributed_fill_halo_regions(fields: Sequence, stream=None, packer=None, group=None) -> None:

@@ -5,7 +5,10 @@ One rank per GPU over NCCL.  For every (Rx, Ry) factorisation of N:
   * DistributedTripolarGrid tiles == slices of the serial oracle grid (bit for bit);
   * distributed fill_halo_regions (fold pack -> NCCL send/recv -> unpack, then ordinary halos) of
     c, u, v, zeta == slices of the serial oracle fill (bit for bit).
-With --bench it also times the fold exchange on the 1/12 degree fields.
+Two grids: 48x40x3 (tiles as narrow as 6 columns) and 4320x64x4 (tiles of 540 columns at 8 ranks: the
+row length of the 1/12 degree benchmark, one bulk-copy chunk per row).  The NCCL arm of the C ABI
+(ossg_fold_exchange + ossg_halo_exchange), the eager torch.distributed arm, the peer-memory fold
+(pull, push, bulk push) and the peer-memory halo exchange are all checked.
 Used by tests/test_gpu_distributed.py (skipped on a single-GPU box) and by hand through gpurun."""
 import argparse
 import json
@@ -20,8 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import ossg_b200 as ossg                                    # noqa: E402
-from ossg_b200.distributed import (PeerFold, PeerHalo, distributed_fill_halo_regions, fold_exchange,   # noqa: E402
-                                   ordinary_halo_exchange, tile_of)
+from ossg_b200.distributed import (NcclExchange, PeerFold, PeerHalo, distributed_fill_halo_regions,   # noqa: E402
+                                   fold_exchange, ordinary_halo_exchange, tile_of)
 from oracle import oracle as orc                            # noqa: E402
 
 
@@ -29,14 +32,15 @@ def factorisations(n):
     return [(rx, n // rx) for rx in range(1, n + 1) if n % rx == 0]
 
 
-def check(world, rank, dev):
+def check(world, rank, dev, size=(48, 40, 3), halo=(4, 4, 2)):
     o = orc.Oracle()
-    size, halo = (48, 40, 3), (4, 4, 2)
     Nx, Ny, Nz = size
     Hx, Hy, Hz = halo
     ref = o.build(orc.make_params(size, halo))
     failures = []
     for (Rx, Ry) in factorisations(world):
+        if Ny // Ry < Hy + 1 or Nx // Rx < Hx:
+            continue                      # (tiles smaller than the halo: rejected by the constructor, tested on the CPU)
         arch = ossg.Distributed(ossg.GPU(dev.index), ossg.Partition(Rx, Ry))
         grid = ossg.TripolarGrid(arch, ossg.Float64, size=size, halo=halo)
         i0, j0, nx, ny = tile_of(Nx, Ny, Rx, Ry, arch.rx, arch.ry)
@@ -69,6 +73,20 @@ def check(world, rank, dev):
                 bad = np.argwhere(~same)[0]
                 failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: fill differs at {bad.tolist()}")
         dist.barrier()
+        # the NCCL arm of the C ABI: ossg_fold_exchange + ossg_halo_exchange (pack kernel, one ncclGroup, unpack kernel), two rounds
+        nccl = NcclExchange(fields)
+        for rep in range(2):
+            for f, p0 in zip(fields, pristine):
+                f.data.copy_(p0)
+            nccl()
+            torch.cuda.synchronize(dev)
+            for f, want, (loc, code) in zip(fields, wants, specs):
+                a, b = f.data.cpu().numpy()[Hz:Hz + Nz], want[Hz:Hz + Nz]
+                same = (a == b) | (np.isnan(a) & np.isnan(b))
+                if not same.all():
+                    bad = np.argwhere(~same)[0]
+                    failures.append(f"({Rx},{Ry}) rank {rank} loc {code}: C-ABI NCCL fill (round {rep + 1}) differs at {bad.tolist()}")
+            dist.barrier()
         # the same fill with the fold served by the one-kernel NVLink peer path (pull, push and
         # bulk-push forms), three epochs each
         for push in (False, True, "bulk"):
@@ -133,25 +151,20 @@ def check(world, rank, dev):
     return failures
 
 
-def bench_fold(world, rank, dev):
-    import bench
-    return bench.bench_fold_exchange(world, rank, dev)
-
-
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--bench", action="store_true")
+    ap.add_argument("--small-only", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     failures = check(world, rank, dev)
+    if not args.small_only:
+        failures += [f"[4320x64x4] {x}" for x in check(world, rank, dev, size=(4320, 64, 4), halo=(4, 4, 2))]
     gathered = [None] * world
     dist.all_gather_object(gathered, failures)
     out = {"world": world, "failures": [x for fl in gathered for x in fl]}
-    if args.bench:
-        out["fold_exchange"] = bench_fold(world, rank, dev)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.destroy_process_group()

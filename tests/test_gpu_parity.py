@@ -423,7 +423,7 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
     lib_ = ossg._lib
     L = lib_.lib()
     Ny, Hx, Hz = 10, 3, 1
-    # (dtype, form, global Nx, Hy, widest); widest: OSSG_PEER_BULK_WAVES=0, i.e. chunks of up to 544
+    # (dtype, form, global Nx, Hy, widest); widest: bulk_waves < 0, i.e. chunks of up to 544
     # columns (one chunk per row of a 540-column tile: three columns per thread) instead of the
     # load-balanced narrower ones
     Nz = 2
@@ -432,10 +432,6 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
              (np.float64, 2, 1030, 6, 0), (np.float32, 2, 778, 3, 0), (np.float64, 2, 1080, 4, 1), (np.float32, 2, 1086, 3, 1),
              (np.float64, 2, 1100, 6, 1)]
     for npdt, push, gNx, Hy, widest in cases:
-        if widest:
-            _os.environ["OSSG_PEER_BULK_WAVES"] = "0"
-        else:
-            _os.environ.pop("OSSG_PEER_BULK_WAVES", None)
         for Rx in (1, 2, 3, 4) + ((7, 8) if gNx > 24 else ()):
             sx = local_sizes(gNx, Rx)
             starts = [1 + sum(sx[:r]) for r in range(Rx)]
@@ -452,6 +448,7 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
                 for r in range(Rx):
                     fd = lib_.PeerFoldDesc()
                     fd.gNx, fd.me, fd.nranks, fd.epoch, fd.push = gNx, r, Rx, epoch, push
+                    fd.bulk_waves = -1 if widest else 0
                     for q in range(Rx):
                         fd.i0[q], fd.nx[q] = starts[q], sx[q]
                         fd.flags_peer[q] = None if q == r else flags[q].data_ptr()
@@ -469,7 +466,6 @@ def test_peer_fold_kernel_equals_zipper(ossg, oracle):
                         got = tiles[k][r].cpu().numpy()[:, :, Hx:Hx + sx[r]]
                         exp = wants[k][:, :, starts[r] - 1 + Hx:starts[r] - 1 + Hx + sx[r]]
                         assert _same_bits(np.ascontiguousarray(got), np.ascontiguousarray(exp)), (npdt, push, gNx, Rx, loc, sign, r, epoch)
-    _os.environ.pop("OSSG_PEER_BULK_WAVES", None)
 
 
 # ------------------------------------------------------------------ argument errors through the ABI
@@ -685,3 +681,188 @@ def test_full_size_fill_round_trip(ossg):
             img = src[:, 1:].flip(-1)                  # i = 2..Nx  <-  i' = Nx..2
             assert torch.equal(once[k, H + Ny, H + 1:H + Nx], sign * img)
             assert torch.equal(once[k, H + Ny, H], abs(sign) * src[:, 0])   # i = 1 wraps: |sign|
+
+
+# ---------------------------------------------------------------- round 2: NaN payloads, Hy = 0, fill forms, table cache, with_halo
+@pytest.mark.parametrize("npdt", [np.float64, np.float32])
+@pytest.mark.parametrize("sign", [1, -1])
+def test_fold_of_nan_sources_matches_the_cpu_multiplication(ossg, oracle, npdt, sign):
+    """`sign * c` (src/zipper_boundary_condition.jl:81) is an IEEE multiplication by +-1: a NaN source
+    comes back quieted with ITS OWN sign and payload on the CPUs the reference runs on.  Sources
+    here contain quiet and signalling NaNs of both signs; the device result equals the oracle's
+    (x86 mulsd / mulss) bit for bit."""
+    dims = (20, 12, 2, 4, 4, 1)
+    Nx, Ny, Nz, Hx, Hy, Hz = dims
+    shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
+    rng = np.random.default_rng(11)
+    host = rng.standard_normal(shape).astype(npdt)
+    if npdt == np.float64:
+        pats = np.array([0x7ff8000000000001, 0xfff8dead0000beef, 0x7ff0000000000123, 0xfff00000000beef1], dtype=np.uint64)
+        bits = host.view(np.uint64)
+    else:
+        pats = np.array([0x7fc00001, 0xffc0dead, 0x7f800123, 0xff80beef], dtype=np.uint32)
+        bits = host.view(np.uint32)
+    mask = rng.random(shape) < 0.2
+    bits[mask] = pats[rng.integers(0, 4, size=int(mask.sum()))]
+    for locname, loc in LOCS.items():
+        dev = torch.as_tensor(host.copy()).cuda()
+        d = _desc(ossg, dev, dims, loc, sign)
+        ossg._lib.check(ossg._lib.lib().ossg_fill_halo_regions_batch(C.byref(d), 1, None))
+        torch.cuda.synchronize()
+        want = oracle.fill_halo_regions(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+        assert _same_bits(dev.cpu().numpy(), want), locname
+
+
+def test_zero_y_halo_still_overwrites_the_fold_row(ossg, oracle):
+    """Hy = 0: the j-loop of fold_north_* is empty, but the row-Ny overwrite of y-Center fields
+    (:102, :135) does not depend on Hy; alone and inside a batch with periodic fill."""
+    Nx, Ny, Nz, Hx, Hz = 16, 9, 2, 3, 1
+    rng = np.random.default_rng(5)
+    hosts, devs, descs = [], [], []
+    for (loc, Hy, sign) in (((0, 0), 0, 1), ((1, 0), 0, -1), ((0, 1), 0, -1), ((0, 0), 2, 1)):
+        dims = (Nx, Ny, Nz, Hx, Hy, Hz)
+        h = rng.standard_normal((Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx))
+        hosts.append((h, dims, loc, sign))
+        devs.append(torch.as_tensor(h.copy()).cuda())
+        descs.append(_desc(ossg, devs[-1], dims, loc, sign))
+    arr = (ossg._lib.FieldDesc * len(descs))(*descs)
+    ossg._lib.check(ossg._lib.lib().ossg_fill_halo_regions_batch(arr, len(descs), None))
+    torch.cuda.synchronize()
+    for (h, dims, loc, sign), dv in zip(hosts, devs):
+        want = oracle.fill_halo_regions(h.copy(), *dims, loc[0], loc[1], sign)
+        assert _same_bits(dv.cpu().numpy(), want), (dims, loc)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 11, 13, 21, 23, 100, 101, 103])
+def test_fill_halo_regions_forms_are_bit_identical(ossg, oracle, variant):
+    """Every part-B form of the fused fill (csrc/ossg_zipper.cu fill_variant) against the oracle, on a
+    grid whose rows are 32-byte aligned (the 256-bit piece path) and on one whose rows are not."""
+    L = ossg._lib.lib()
+    L.ossg_experiment_fill_variant(variant)
+    try:
+        for dims in ((60, 30, 3, 4, 4, 2), (62, 21, 5, 4, 3, 1), (34, 17, 2, 3, 9, 1)):
+            Nx, Ny, Nz, Hx, Hy, Hz = dims
+            shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
+            fields = []
+            for q, (locname, loc) in enumerate(LOCS.items()):
+                sign = -1 if loc[0] != loc[1] else 1
+                host = _poisoned_field(shape, Nx, Ny, Nz, Hx, Hy, Hz, np.float64, seed=31 + q)
+                dev = torch.as_tensor(host).cuda()
+                fields.append((host, dev, loc, sign, _desc(ossg, dev, dims, loc, sign)))
+            arr = (ossg._lib.FieldDesc * 4)(*[f[4] for f in fields])
+            ossg._lib.check(L.ossg_fill_halo_regions_batch(arr, 4, None))
+            torch.cuda.synchronize()
+            for host, dev, loc, sign, _ in fields:
+                want = oracle.fill_halo_regions(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+                assert _same_bits(dev.cpu().numpy(), want), (variant, dims, loc)
+    finally:
+        L.ossg_experiment_fill_variant(-1)
+
+
+def test_table_cache_in_the_workspace(ossg, oracle):
+    """The workspace header stamps the 1-D tables: a second build on the same workspace skips the
+    table computation, other latitudes / sizes on the same workspace recompute; results equal the
+    oracle every time."""
+    from ossg_b200.grids import make_params
+    L = ossg._lib.lib()
+    dev = torch.device("cuda", 0)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+    ws.fill_(0xAB)                                                  # garbage, then the init the contract asks for
+    ossg._lib.check(L.ossg_tripolar_workspace_init(ws.data_ptr(), ws.numel(), None))
+    cases = [((60, 30, 1), (4, 4, 4), {}), ((60, 30, 1), (4, 4, 4), {}), ((60, 30, 1), (4, 7, 4), {}),
+             ((60, 30, 1), (4, 4, 4), dict(north_poles_latitude=45)), ((40, 34, 1), (5, 31, 5), dict(southernmost_latitude=-70)),
+             ((60, 30, 1), (4, 4, 4), dict(radius=1.0)), ((60, 30, 1), (4, 4, 4), {})]
+    for size, halo, kw in cases:
+        p = make_params(size, halo, kw.get("southernmost_latitude", -80), kw.get("north_poles_latitude", 55),
+                        kw.get("first_pole_longitude", 70), kw.get("radius", orc.R_EARTH))
+        shape = (size[1] + 2 * halo[1], size[0] + 2 * halo[0])
+        out = [torch.full(shape, float("nan"), dtype=torch.float64, device=dev) for _ in range(20)]
+        ossg._lib.check(L.ossg_tripolar_build(C.byref(p), 0, ossg._lib.ptr_array([t.data_ptr() for t in out]), ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        ref = oracle.build(orc.make_params(size, halo, **kw))
+        got = {n: t.cpu().numpy() for n, t in zip(orc.ALL_NAMES, out)}
+        assert assert_grid_matches(got, ref) == 0, (size, halo, kw)
+    # the stamp is in place: words 0 and 5 of the header carry the magic numbers
+    hdr = ws[:128].cpu().numpy().view(np.uint64)
+    assert hdr[0] == 0x4f5353475f58595f and hdr[5] == 0x4f5353475f4c4c5f and hdr[1] == 60 and hdr[2] == 30
+
+
+def test_with_halo_on_device_reuses_the_tables(ossg, oracle):
+    """src/with_halo.jl:5-23, test/runtests.jl:52-71: the grid rebuilt with a larger halo equals the
+    oracle's grid with that halo (the 1-D tables travel with the grid), Float64 and Float32."""
+    for FT in (ossg.Float64, ossg.Float32):
+        grid = ossg.TripolarGrid(ossg.GPU(), FT, size=(40, 34, 2), halo=(4, 4, 4), north_poles_latitude=45, first_pole_longitude=35)
+        assert grid.tables is not None
+        big = ossg.with_halo((5, 31, 5), grid)
+        assert big.halo == (5, 31, 5) and big.size == grid.size and big.tables is not None
+        kw = dict(north_poles_latitude=45, first_pole_longitude=35)
+        ref = oracle.build(orc.make_params((40, 34, 2), (5, 31, 5), **kw))
+        got = to_np(big)
+        if FT is ossg.Float32:
+            for n in orc.ALL_NAMES:
+                assert np.array_equal(got[n].view(np.uint32), ref[n].astype(np.float32).view(np.uint32)), n
+        else:
+            assert assert_grid_matches(got, ref) == 0
+        small = ossg.with_halo((2, 2, 2), big)
+        ref2 = oracle.build(orc.make_params((40, 34, 2), (2, 2, 2), **kw))
+        got2 = to_np(small)
+        for n in orc.ALL_NAMES:
+            want = ref2[n] if FT is ossg.Float64 else ref2[n].astype(np.float32)
+            assert np.array_equal(got2[n], want, equal_nan=True), n
+
+
+def test_two_streams_build_concurrently(ossg, oracle):
+    """Re-entrancy: builds on two streams, each with its own workspace, share only the per-device
+    fork/join resources; both results are the oracle's."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    from ossg_b200.grids import build_arrays, make_params
+    dev = torch.device("cuda", 0)
+    pa = make_params((360, 180, 1), (4, 4, 4), -80, 55, 70, orc.R_EARTH)
+    pb = make_params((120, 60, 1), (5, 5, 5), -80, 45, 25, orc.R_EARTH)
+    outs = []
+    for it in range(3):
+        a = build_arrays(pa, ossg.Float64, dev, stream=s1)
+        b = build_arrays(pb, ossg.Float32, dev, stream=s2)
+        outs = [a, b]
+    torch.cuda.synchronize()
+    ra = oracle.build(orc.make_params((360, 180, 1), (4, 4, 4)))
+    rb = oracle.build(orc.make_params((120, 60, 1), (5, 5, 5), north_poles_latitude=45, first_pole_longitude=25))
+    assert assert_grid_matches({n: t.cpu().numpy() for n, t in zip(orc.ALL_NAMES, outs[0])}, ra) == 0
+    for n, t in zip(orc.ALL_NAMES, outs[1]):
+        assert np.array_equal(t.cpu().numpy().view(np.uint32), rb[n].astype(np.float32).view(np.uint32)), n
+
+
+def test_missing_partner_traps_instead_of_passing_silently(ossg):
+    """A rank whose partner never makes the matching call must fail loudly: the
+    waiting kernel traps after OSSG_PEER_TIMEOUT_MS and the next CUDA call of that process raises.
+    Runs in a child process (a trap takes the CUDA context with it)."""
+    import subprocess, sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import torch, ossg_b200
+from ossg_b200 import _lib
+L = _lib.lib()
+Nx, Ny, Nz, H = 24, 10, 2, 3
+tiles = [torch.zeros((Nz + 2, Ny + 2 * H, Nx // 2 + 2 * H), dtype=torch.float64, device="cuda") for _ in range(2)]
+flags = [torch.zeros(17, dtype=torch.int64, device="cuda") for _ in range(2)]
+fd = _lib.PeerFoldDesc()
+fd.gNx, fd.me, fd.nranks, fd.epoch, fd.push = Nx, 0, 2, 1, 1
+for q in range(2):
+    fd.i0[q], fd.nx[q] = 1 + q * (Nx // 2), Nx // 2
+fd.flags_peer[1] = flags[1].data_ptr()
+fd.flags_local = flags[0].data_ptr()
+arr = (_lib.PeerField * 1)()
+arr[0].f = _lib.FieldDesc(tiles[0].data_ptr(), 0, Nx // 2, Ny, Nz, H, H, 1, 0, 0, 0, 0, 1.0)
+arr[0].peer[0], arr[0].peer[1] = tiles[0].data_ptr(), tiles[1].data_ptr()
+_lib.check(L.ossg_zipper_fill_peer(arr, 1, C.byref(fd), None))      # rank 1 never calls
+try:
+    torch.cuda.synchronize()
+except Exception as e:
+    print("RAISED", type(e).__name__)
+    sys.exit(7)
+print("PASSED SILENTLY")
+''' % ROOT
+    env = dict(_os.environ, OSSG_PEER_TIMEOUT_MS="300")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
+    assert "PASSED SILENTLY" not in r.stdout and r.returncode != 0, (r.returncode, r.stdout[-300:], r.stderr[-300:])

@@ -158,3 +158,77 @@ def test_oracle_equals_the_multiprecision_restatement(oracle, size, kw):
                 if (a, i, j) in values and (b, i, j) in values:
                     want = values[(a, i, j)] * values[(b, i, j)]
                     assert abs(mpf(float(g[j - 1, i - 1])) - want) <= mpf("1e-12") * abs(want), (name, i, j)
+
+
+@pytest.mark.parametrize("size,kw", [
+    ((60, 30, 1), {}),
+    ((36, 22, 1), dict(north_poles_latitude=35, first_pole_longitude=75, southernmost_latitude=-75)),
+    ((10, 10, 1), {}),                                                       # Nx % 4 != 0: no Center column sits on an axis
+])
+def test_pole_meridians_and_pole_row_against_their_limits(oracle, size, kw):
+    """The points the test above leaves out: lambda_1D a multiple of 90 degrees (x == 0 or y == 0 in the
+    ellipse/hyperbola map, generate_tripolar_coordinates.jl:67-68) and the pole row phi_1D == 90.  There
+    the latitude is still unambiguous -- phi = 90 - (360/pi) atan(|y|) resp. atan(|x|), :78 -- and is
+    checked exactly; the longitude hangs on the sign of a zero (atan(y / +-0), :77), which Julia's sind /
+    cosd decide: whatever they decide, the result must be one of the two one-sided limits of the map, and
+    exactly on the two poles (x == 0 and y == 0) the reference prescribes it itself (:73-75).  Together
+    with the generic test, every interior coordinate of the grid is now accounted for."""
+    Nx, Ny, _ = size
+    p = orc.make_params(size, **kw)
+    south, poles, fpl = mpf(p.southernmost_latitude), mpf(p.north_poles_latitude), mpf(p.first_pole_longitude)
+    got = oracle.build(p)
+    a = mp.tan(_rad((90 - poles) / 2))
+    lamF = [-180 + mpf(i - 1) * 360 / Nx for i in range(1, Nx + 1)]
+    lamC = [lf + mpf(180) / Nx for lf in lamF]
+    phiC = [south + mpf(j - 1) * (90 - south) / (Ny - 1) for j in range(1, Ny + 1)]
+    dphi = phiC[1] - phiC[0]
+    phiF = [pc - dphi / 2 for pc in phiC]
+    eps = mpf("1e-25")
+
+    def general(l1, ph1, ip):
+        psi = mp.asinh(mp.tan(_rad((90 - ph1) / 2)) / a)
+        x, y = a * mp.sin(_rad(l1)) * mp.cosh(psi), a * mp.cos(_rad(l1)) * mp.sinh(psi)
+        lam = -(180 / mp.pi) * mp.atan(y / x) + (-90 if ip <= Nx // 2 else 90) + fpl + 90
+        return (mp.fmod(lam, 360) + 360) % 360, 90 - (360 / mp.pi) * mp.atan(mp.sqrt(x * x + y * y))
+
+    checked = poles_seen = 0
+    for name, lam1, phi1 in (("ff", lamF, phiF), ("fc", lamF, phiC), ("cf", lamC, phiF), ("cc", lamC, phiC)):
+        glam, gphi = orc.interior(got["lam_" + name], p), orc.interior(got["phi_" + name], p)
+        for j in range(1, Ny + 1):
+            for i in range(1, Nx + 1):
+                # C3 (tripolar_grid.jl:137-199): interior row Ny of the y-Center coordinates is overwritten by its
+                # fold mirror for i > Nx/2 (zipper_boundary_condition.jl:102, :135) -- the expected value is the source's
+                isrc = i
+                if name in ("fc", "cc") and j == Ny and i > Nx // 2:
+                    isrc = Nx - i + (2 if name == "fc" else 1)
+                    if isrc > Nx:
+                        isrc -= Nx
+                ip = isrc - Nx // 4                                             # tripolar_grid.jl:121-130
+                if ip < 1:
+                    ip += Nx
+                on_axis = lam1[ip - 1] % 90 == 0
+                if not (on_axis or phi1[j - 1] == 90):
+                    continue
+                have_l, have_p = mpf(float(glam[j - 1, i - 1])), mpf(float(gphi[j - 1, i - 1]))
+                at_pole = phi1[j - 1] == 90 and lam1[ip - 1] % 180 == 0        # x == 0 and y == 0
+                if at_pole:
+                    want = (mpf(-90 if ip == 1 else 90) + (-90 if ip <= Nx // 2 else 90) + fpl + 90) % 360     # :73-75, :82, :86-87
+                    d = abs(have_l - want)
+                    assert min(d, abs(360 - d)) < mpf("1e-12") and abs(have_p - 90) < mpf("1e-12"), (name, ip, j)
+                    poles_seen += 1
+                    continue
+                # one-sided limits in whichever variable crosses an axis
+                dl = eps if on_axis else 0
+                dp = eps if phi1[j - 1] == 90 else 0
+                cands = [general(lam1[ip - 1] + s * dl, phi1[j - 1] - dp, ip) for s in ((-1, 1) if on_axis else (1,))]
+                if phi1[j - 1] == 90 and not on_axis:
+                    cands.append(((cands[0][0] + 180) % 360, cands[0][1]))      # sinh(psi) = +-0: atan(+-0 / x)
+                assert abs(have_p - cands[0][1]) < mpf("1e-12"), (name, ip, j, float(have_p), float(cands[0][1]))
+                ds = []
+                for (cl, _) in cands:
+                    d = abs(have_l - cl)
+                    ds.append(min(d, abs(360 - d)))
+                assert min(ds) < mpf("1e-12"), (name, ip, j, float(have_l), [float(c[0]) for c in cands])
+                checked += 1
+    assert poles_seen == 2                                        # two pole values in the FC row Ny (for Nx % 4 != 0 the overwrite repeats the first)
+    assert checked >= 2 * (2 * Ny - 1)
