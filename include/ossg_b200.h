@@ -79,7 +79,14 @@ typedef struct ossg_tripolar_params {
      * exactly partition_tripolar_metric's slice.  Serial grid: i0 = j0 = 1, nx = Nx, ny = Ny.
      * Setting nx = 0 (or ny = 0) means "whole grid" for that direction.                          */
     int32_t i0, j0, nx, ny;
+    /* OSSG_LAMBDA1D_F32: the 1-D longitudes are Float32 values (rounded once from the correctly rounded
+     * Float64 ones) widened back to Float64 before the map -- one reading of
+     * generate_coordinate(FT, ...) at src/tripolar_grid.jl:89 for FT = Float32; 0 (default): they stay
+     * Float64 for every FT.  See DESIGN.md section 4.                                             */
+    int32_t flags;
+    int32_t reserved;
 } ossg_tripolar_params;
+#define OSSG_LAMBDA1D_F32 1
 
 /* ---- housekeeping ------------------------------------------------------------------------- */
 int         ossg_version(void);                 /* major*100 + minor                             */

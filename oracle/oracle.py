@@ -98,6 +98,11 @@ class Oracle:
     def set_threads(self, n: int) -> None:
         self.lib.ossg_oracle_set_threads(int(n))
 
+    def set_lambda_f32(self, on: bool) -> None:
+        """FT = Float32 reading of generate_coordinate: 1-D longitudes rounded to Float32 before the map."""
+        self.lib.ossg_oracle_set_lambda_f32.restype = None
+        self.lib.ossg_oracle_set_lambda_f32(int(bool(on)))
+
     def max_threads(self) -> int:
         return int(self.lib.ossg_oracle_max_threads())
 

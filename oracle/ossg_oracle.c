@@ -51,6 +51,10 @@ static inline size_t psize(const ossg_oracle_params *p)
  * (pthreads; used only when the caller asks for more than one thread -- the reference's
  * KernelAbstractions CPU backend splits its ndrange over Julia threads the same way) */
 static int g_threads = 1;
+/* Reading of `generate_coordinate(FT, ...)` (src/tripolar_grid.jl:89) for FT = Float32: 0 = the 1-D
+ * longitudes stay Float64 (default); 1 = they are Float32 values (rounded once) widened back to
+ * Float64 before the map.  See DESIGN.md section 4; neither can be pinned without Julia. */
+static int g_lambda_f32 = 0;
 typedef void (*row_fn)(void *ctx, int j);
 typedef struct { row_fn fn; void *ctx; int j0, j1; } row_job;
 static void *row_worker(void *arg)
@@ -108,6 +112,7 @@ void ossg_oracle_coordinate_vectors(const ossg_oracle_params *p,
         /* longitude = (-180, 180), Periodic: faces at -180 + (i-1)*360/Nx, centres half a cell on */
         lamF[i - 1] = rational_point(-180.0, (double)(Nx - (i - 1)), 180.0, (double)(i - 1), (double)Nx);
         lamC[i - 1] = rational_point(-180.0, (double)(2 * Nx - (2 * i - 1)), 180.0, (double)(2 * i - 1), (double)(2 * Nx));
+        if (g_lambda_f32) { lamF[i - 1] = (double)(float)lamF[i - 1]; lamC[i - 1] = (double)(float)lamC[i - 1]; }
     }
     const double south = p->southernmost_latitude;
     for (int j = 1; j <= Ny; ++j)   /* range(south, 90, length = Ny) */
@@ -508,6 +513,8 @@ int ossg_oracle_max_threads(void)
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+
+void ossg_oracle_set_lambda_f32(int on) { g_lambda_f32 = on ? 1 : 0; }
 
 void ossg_oracle_set_threads(int n)
 {

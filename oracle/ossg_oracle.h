@@ -37,6 +37,7 @@ void ossg_oracle_periodic_x_f32(float *c, int Nx, int Ny, int Nz, int Hx, int Hy
 int  ossg_oracle_uses_libm(void);
 int  ossg_oracle_max_threads(void);
 void ossg_oracle_set_threads(int n);
+void ossg_oracle_set_lambda_f32(int on);   /* 1: 1-D longitudes pre-rounded to Float32 (FT = Float32 reading) */
 int  ossg_oracle_math_eval(int fn, const double *x, double *y, size_t n);
 void ossg_oracle_cartesian_nodes(const double *lam, const double *phi, size_t n, double radius,
                                  double *x, double *y, double *z);

@@ -19,6 +19,7 @@ OSSG_EINVAL, OSSG_EODD_NX, OSSG_EHALO, OSSG_EWINDOW, OSSG_EALIGN, OSSG_ELOCATION
 OSSG_ENCCL, OSSG_ETIMEOUT = -8, -9
 OSSG_CENTER, OSSG_FACE = 0, 1
 OSSG_F64, OSSG_F32 = 0, 1
+OSSG_LAMBDA1D_F32 = 1
 
 ARRAY_NAMES = ["lam_cc", "lam_fc", "lam_cf", "lam_ff", "phi_cc", "phi_fc", "phi_cf", "phi_ff",
                "dx_cc", "dx_fc", "dx_cf", "dx_ff", "dy_cc", "dy_cf", "dy_fc", "dy_ff",
@@ -29,7 +30,8 @@ class TripolarParams(C.Structure):
     _fields_ = [("Nx", C.c_int32), ("Ny", C.c_int32), ("Hx", C.c_int32), ("Hy", C.c_int32),
                 ("southernmost_latitude", C.c_double), ("north_poles_latitude", C.c_double),
                 ("first_pole_longitude", C.c_double), ("radius", C.c_double),
-                ("i0", C.c_int32), ("j0", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32)]
+                ("i0", C.c_int32), ("j0", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FieldDesc(C.Structure):

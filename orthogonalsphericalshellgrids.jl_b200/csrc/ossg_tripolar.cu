@@ -34,6 +34,7 @@ struct Window {
 
 struct BuildArgs {
     GridDims g;
+    int flags;                    // ossg_tripolar_params.flags
     Window w;
     double south, north_poles_latitude, first_pole_longitude, radius;
     unsigned long long* stamp;    // workspace header: TABLE_HDR_WORDS 8-byte words (validity stamps of the tables)
@@ -67,19 +68,19 @@ constexpr int TABLE_HDR_WORDS = 16;
 constexpr unsigned long long STAMP_XY = 0x4f5353475f58595full, STAMP_LL = 0x4f5353475f4c4c5full;   // "OSSG_XY_", "OSSG_LL_"
 
 struct TableKeys { unsigned long long xy[5], ll[6]; };
-__host__ __device__ inline TableKeys table_keys(const GridDims& g, double south, double npl, double radius)
+__host__ __device__ inline TableKeys table_keys(const GridDims& g, int flags, double south, double npl, double radius)
 {
     auto bits = [](double x) { unsigned long long u; memcpy(&u, &x, 8); return u; };
     TableKeys k;
-    k.xy[0] = STAMP_XY; k.xy[1] = (unsigned)g.Nx; k.xy[2] = (unsigned)g.Ny; k.xy[3] = bits(south); k.xy[4] = bits(npl);
+    k.xy[0] = STAMP_XY; k.xy[1] = (unsigned)g.Nx | ((unsigned long long)(unsigned)flags << 32); k.xy[2] = (unsigned)g.Ny; k.xy[3] = bits(south); k.xy[4] = bits(npl);
     k.ll[0] = STAMP_LL; k.ll[1] = (unsigned)g.Nx; k.ll[2] = (unsigned)g.Ny; k.ll[3] = (unsigned)g.Hy; k.ll[4] = bits(south); k.ll[5] = bits(radius);
     return k;
 }
 
-__global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, double north_poles_latitude,
+__global__ void __launch_bounds__(128) tables_kernel(GridDims g, int flags, double south, double north_poles_latitude,
                                                      double radius, double* __restrict__ base, unsigned long long* stamp)
 {
-    const TableKeys key = table_keys(g, south, north_poles_latitude, radius);
+    const TableKeys key = table_keys(g, flags, south, north_poles_latitude, radius);
     bool xy_ok = true, ll_ok = true;
 #pragma unroll
     for (int q = 0; q < 5; ++q) xy_ok = xy_ok && __ldcg(stamp + q) == key.xy[q];
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(128) tables_kernel(GridDims g, double south, d
             const int i = face ? t + 1 : t - Nx + 1;
             const int ip = preshift(i, Nx);
             const double a = focal_distance(north_poles_latitude);
-            const double lam = face ? lam_face(ip, Nx) : lam_center(ip, Nx);
+            double lam = face ? lam_face(ip, Nx) : lam_center(ip, Nx);
+            if (flags & OSSG_LAMBDA1D_F32) lam = (double)(float)lam;    // generate_coordinate(Float32, ...) reading, tripolar_grid.jl:89
             const int o = face ? 0 : 2;
             xs[(size_t)(o + 0) * Nx + (i - 1)] = a * m::sind(lam);      // generate_tripolar_coordinates.jl:67
             xs[(size_t)(o + 1) * Nx + (i - 1)] = a * m::cosd(lam);      // :68
@@ -204,8 +206,8 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
 struct PairGrid {
     int jw_lo, n_pair_rows, chunks_pair, chunks_full;
 #ifdef OSSG_COORD_MAGIC_DIV
-    // experiment (not measured yet): ceil(2^40 / chunks) -- b / chunks == (b * magic) >> 40 for b * chunks < 2^40,
-    // three instructions instead of the ~25 of an integer division in every block's prologue
+    // ceil(2^40 / chunks) -- b / chunks == (b * magic) >> 40 for b * chunks < 2^40, three instructions instead of
+    // the ~25 of an integer division in every block's prologue (default since round 2, see the Makefile)
     unsigned long long magic_pair, magic_full;
 #endif
 };
@@ -865,6 +867,7 @@ static int check_params(const ossg_tripolar_params* p, ossg_tripolar_params& q)
     if (q.i0 < 1 || q.nx < 1 || q.i0 + q.nx - 1 > q.Nx || q.j0 < 1 || q.ny < 1 || q.j0 + q.ny - 1 > q.Ny)
         return set_error(OSSG_EWINDOW, "tile i0=%d nx=%d j0=%d ny=%d outside the %dx%d grid", q.i0, q.nx, q.j0, q.ny, q.Nx, q.Ny);
     if (!(q.radius > 0.0)) return set_error(OSSG_EINVAL, "radius must be positive");
+    if (q.flags & ~OSSG_LAMBDA1D_F32) return set_error(OSSG_EINVAL, "unknown flags 0x%x", q.flags);
     return 0;
 }
 
@@ -882,6 +885,7 @@ static size_t window_elems(const ossg_tripolar_params& q)
 static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* workspace)
 {
     a.g = GridDims{ q.Nx, q.Ny, q.Hx, q.Hy };
+    a.flags = q.flags;
     a.w = Window{ q.i0 - q.Hx, q.j0 - q.Hy, q.nx + 2 * q.Hx, q.ny + 2 * q.Hy };
     a.south = q.southernmost_latitude;
     a.north_poles_latitude = q.north_poles_latitude;
@@ -894,7 +898,7 @@ static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* works
 static int launch_tables(const BuildArgs& a, cudaStream_t s)
 {
     const int n = 2 * a.g.Nx + 2 * a.g.Ny + a.g.Hy + 1;
-    tables_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a.g, a.south, a.north_poles_latitude, a.radius, a.tables, a.stamp);
+    tables_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a.g, a.flags, a.south, a.north_poles_latitude, a.radius, a.tables, a.stamp);
     OSSG_LAUNCH_CHECK("tables_kernel");
     return 0;
 }

@@ -158,6 +158,7 @@ __device__ __forceinline__ Piece32 ld_piece32(const void* p)
 {
     Piece32 v;
     if (HINT == 1)      asm volatile("ld.global.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    else if (HINT == 3) asm volatile("ld.global.L2::64B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
     else if (HINT == 2) asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
     else                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
     return v;
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(ZB) fill_fused_kernel(const __grid_constant__ 
     const long long t = (long long)(blockIdx.x - nA) * ZB + threadIdx.x;
     const int form = fb.variant % 10, hint = (fb.variant / 10) % 10;
     const bool all_rows = nA == 0;
-    if (hint == 1) fused_part_b<1>(f, form, t, all_rows);
+    if (hint == 3) fused_part_b<3>(f, form, t, all_rows);
+    else if (hint == 1) fused_part_b<1>(f, form, t, all_rows);
     else if (hint == 2) fused_part_b<2>(f, form, t, all_rows);
     else fused_part_b<0>(f, form, t, all_rows);
 }

@@ -85,7 +85,8 @@ def tile_of(Nx: int, Ny: int, Rx: int, Ry: int, rx: int, ry: int):
 
 
 def DistributedTripolarGrid(arch: Distributed, FT=Float64, *, size, southernmost_latitude=-80, halo=(4, 4, 4),
-                            radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70, _tables=None):
+                            radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70, _tables=None,
+                            float32_longitudes: bool = False):
     Nx, Ny, Nz = (int(s) for s in size)
     Hx, Hy, Hz = (int(h) for h in halo)
     if Nx % 2 == 1:
@@ -96,7 +97,7 @@ def DistributedTripolarGrid(arch: Distributed, FT=Float64, *, size, southernmost
     if (arch.Ry > 1 and ny < Hy) or (arch.Rx > 1 and nx < Hx):      # a neighbour's halo is filled from INTERIOR rows / columns
         raise ValueError(f"tile {nx}x{ny} of rank {arch.local_rank} is smaller than the halo ({Hx}, {Hy})")
     params = make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius,
-                         tile=(i0, j0, nx, ny))
+                         tile=(i0, j0, nx, ny), flags=_lib.OSSG_LAMBDA1D_F32 if float32_longitudes else 0)
     _require_cuda()
     device = arch.torch_device()
     parents, tables = build_arrays_cached(params, FT, device, tables=_tables)

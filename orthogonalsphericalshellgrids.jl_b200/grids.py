@@ -238,12 +238,12 @@ def _elem_type(FT) -> int:
 
 
 def make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius,
-                tile=None) -> TripolarParams:
+                tile=None, flags: int = 0) -> TripolarParams:
     Nx, Ny = int(size[0]), int(size[1])
     i0, j0, nx, ny = tile if tile is not None else (1, 1, Nx, Ny)
     return TripolarParams(Nx, Ny, int(halo[0]), int(halo[1]), float(southernmost_latitude),
                           float(north_poles_latitude), float(first_pole_longitude), float(radius),
-                          int(i0), int(j0), int(nx), int(ny))
+                          int(i0), int(j0), int(nx), int(ny), int(flags), 0)
 
 
 def build_arrays_cached(params: TripolarParams, FT, device: torch.device, out: Optional[Sequence[torch.Tensor]] = None,
@@ -283,10 +283,16 @@ def build_arrays(params: TripolarParams, FT, device: torch.device, out: Optional
 
 
 def TripolarGrid(arch=None, FT=Float64, *, size, southernmost_latitude=-80, halo=(4, 4, 4),
-                 radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70, _tables=None):
+                 radius=R_Earth, z=(0, 1), north_poles_latitude=55, first_pole_longitude=70, _tables=None,
+                 float32_longitudes: bool = False):
     """Return an OrthogonalSphericalShellGrid tripolar grid on the sphere
     (src/tripolar_grid.jl:59-333).  `arch` defaults to GPU(); a Distributed architecture
-    dispatches to the distributed constructor (src/distributed_tripolar_grid.jl:24)."""
+    dispatches to the distributed constructor (src/distributed_tripolar_grid.jl:24).
+
+    float32_longitudes (not a reference keyword): the reference passes FT to generate_coordinate
+    (:89), so for FT = Float32 its 1-D longitudes may be Float32 values.  True applies that reading
+    (longitudes rounded once to Float32, OSSG_LAMBDA1D_F32); the default keeps them Float64 for every
+    FT.  DESIGN.md section 4 has the reasoning and what it changes."""
     from .distributed import Distributed, DistributedTripolarGrid   # late import: optional path
     if arch is None:
         arch = GPU()
@@ -294,12 +300,14 @@ def TripolarGrid(arch=None, FT=Float64, *, size, southernmost_latitude=-80, halo
         return DistributedTripolarGrid(arch, FT, size=size, southernmost_latitude=southernmost_latitude,
                                        halo=halo, radius=radius, z=z,
                                        north_poles_latitude=north_poles_latitude,
-                                       first_pole_longitude=first_pole_longitude, _tables=_tables)
+                                       first_pole_longitude=first_pole_longitude, _tables=_tables,
+                                       float32_longitudes=float32_longitudes)
     Nx, Ny, Nz = (int(s) for s in size)
     Hx, Hy, Hz = (int(h) for h in halo)
     if Nx % 2 == 1:          # src/tripolar_grid.jl:81-83
         raise ValueError("The number of cells in the longitude dimension should be even!")
-    params = make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius)
+    params = make_params(size, halo, southernmost_latitude, north_poles_latitude, first_pole_longitude, radius,
+                         flags=_lib.OSSG_LAMBDA1D_F32 if float32_longitudes else 0)
     _require_cuda()
     device = arch.torch_device() if isinstance(arch, GPU) else torch.device("cuda", torch.cuda.current_device())
     parents, tables = build_arrays_cached(params, FT, device, tables=_tables)

@@ -866,3 +866,24 @@ print("PASSED SILENTLY")
     env = dict(_os.environ, OSSG_PEER_TIMEOUT_MS="300")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
     assert "PASSED SILENTLY" not in r.stdout and r.returncode != 0, (r.returncode, r.stdout[-300:], r.stderr[-300:])
+
+
+def test_float32_longitude_reading_matches_the_oracle_option(ossg, oracle):
+    """OSSG_LAMBDA1D_F32 / float32_longitudes=True: the 1-D longitudes pre-rounded to Float32 (one reading of
+    generate_coordinate(FT, ...), src/tripolar_grid.jl:89); device and oracle agree bit for bit under either
+    reading, and the two readings differ (the option is not a no-op)."""
+    size, halo = (100, 60, 1), (4, 4, 4)           # 3.6 degree steps: not representable in Float32
+    try:
+        oracle.set_lambda_f32(True)
+        ref = oracle.build(orc.make_params(size, halo))
+    finally:
+        oracle.set_lambda_f32(False)
+    ref0 = oracle.build(orc.make_params(size, halo))
+    for FT, cast in ((ossg.Float64, np.float64), (ossg.Float32, np.float32)):
+        g = ossg.TripolarGrid(ossg.GPU(), FT, size=size, halo=halo, float32_longitudes=True)
+        got = to_np(g)
+        for n in orc.ALL_NAMES:
+            assert np.array_equal(got[n], ref[n].astype(cast), equal_nan=True), (FT, n)
+    assert not np.array_equal(ref["lam_cc"], ref0["lam_cc"])
+    inner = (slice(5, -5), slice(5, -5))
+    assert 0 < np.abs(ref["dx_cc"][inner] / ref0["dx_cc"][inner] - 1).max() < 1e-4

@@ -14,10 +14,10 @@ mkdir -p $OUT
 build() { # name flags...
   local name=$1; shift
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC "$@" -shared \
-       -o $OUT/libossg_$name.so ossg_api.cu ossg_tripolar.cu ossg_zipper.cu ossg_peer.cu ossg_util.cu -cudart shared
+       -o $OUT/libossg_$name.so ossg_api.cu ossg_tripolar.cu ossg_zipper.cu ossg_peer.cu ossg_nccl.cu -cudart shared -ldl
   echo "built $name"
 }
-build base
+build base            # (the plain forms: no atan range table, integer division in the block map)
 build atanrng -DOSSG_ATAN_RANGE_TABLE
 build magicdiv -DOSSG_COORD_MAGIC_DIV
 build coordx -DOSSG_ATAN_RANGE_TABLE -DOSSG_COORD_MAGIC_DIV

@@ -14,3 +14,5 @@ OSSG_PEER_TIMEOUT_MS=20000 timeout 600 compute-sanitizer --tool memcheck --error
 timeout 600 python bench.py > gpurun_out/r02a_bench.json 2> gpurun_out/r02a_bench.err
 tail -c 400 gpurun_out/r02a_bench.err
 cat gpurun_out/r02a_pytest.log | tail -8
+for f in build/variants/*.so; do OSSG_B200_LIB=$PWD/$f timeout 120 python tools/variant_time.py 2>&1 | tail -1; done > gpurun_out/r02a_variants.log
+cat gpurun_out/r02a_variants.log

@@ -13,7 +13,7 @@ p = make_params((Nx, Ny, 100), (H, H, H), -80.0, 55.0, 70.0, 6371.0e3)
 out = [torch.zeros((Ny + 2 * H, Nx + 2 * H), dtype=torch.float64, device=dev) for _ in range(20)]
 optr = _lib.ptr_array([t.data_ptr() for t in out])
 nb = L.ossg_tripolar_workspace_bytes(C.byref(p), _lib.OSSG_F64)
-ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+ws = torch.zeros(max(nb, 128), dtype=torch.uint8, device=dev)
 s = torch.cuda.current_stream(dev)
 prof = (C.c_float * 4)(); acc = [0.0] * 4; n = 20
 for it in range(n + 5):
