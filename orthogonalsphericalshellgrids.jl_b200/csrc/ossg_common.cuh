@@ -41,21 +41,33 @@ inline int cuda_fail(cudaError_t e, const char* what)
 // then bit-exact against the reference's CPU path for every input, NaN payloads included.
 // Branch-free on purpose (selects only): the fill kernels issue all their loads first and must stay
 // straight-line code for that; a first version with branches cost the zipper kernel 18 %.
-__device__ __forceinline__ double apply_sign(double v, double s)
+//   fold_unit : bc.condition = +-1 (every Zipper the reference creates); flip_hi = 0x80000000 for -1.
+//               High word only: one FP64 compare (that pipe is idle in the fill kernels), two logic ops, one select.
+//   apply_sign: any bc.condition (selects between the unit form and the oracle's (T)(s * c)).
+__device__ __forceinline__ double fold_unit(double v, unsigned flip_hi)
 {
-    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-    const bool nan = (u << 1) > 0xffe0000000000000ull;
-    const unsigned long long unit = nan ? (u | 0x0008000000000000ull) : (u ^ (s == -1.0 ? 0x8000000000000000ull : 0ull));
-    const double general = s * v;                       // any other bc.condition: the oracle's (T)(s * c)
-    return (s == 1.0 || s == -1.0) ? __longlong_as_double((long long)unit) : general;
+    const int hi = __double2hiint(v);
+    return __hiloint2double((v != v) ? (hi | 0x00080000) : (int)((unsigned)hi ^ flip_hi), __double2loint(v));
 }
-__device__ __forceinline__ float apply_sign(float v, double s)
+__device__ __forceinline__ float fold_unit(float v, unsigned flip_hi)
 {
-    const unsigned u = (unsigned)__float_as_int(v);
-    const bool nan = (u << 1) > 0xff000000u;
-    const unsigned unit = nan ? (u | 0x00400000u) : (u ^ (s == -1.0 ? 0x80000000u : 0u));
-    const float general = (float)(s * (double)v);
-    return (s == 1.0 || s == -1.0) ? __int_as_float((int)unit) : general;
+    const int u = __float_as_int(v);
+    return __int_as_float((v != v) ? (u | 0x00400000) : (int)((unsigned)u ^ flip_hi));
+}
+__device__ __forceinline__ bool sign_is_unit(double s) { return s == 1.0 || s == -1.0; }
+__device__ __forceinline__ unsigned sign_flip(double s) { return s == -1.0 ? 0x80000000u : 0u; }
+template <typename T>
+__device__ __forceinline__ T apply_sign(T v, double s)
+{
+    const T unit = fold_unit(v, sign_flip(s));
+    const T general = (T)(s * (double)v);
+    return sign_is_unit(s) ? unit : general;
+}
+// compile-time choice for the single-GPU fill kernels (issue-sensitive): UNIT is decided once per thread
+template <bool UNIT, typename T>
+__device__ __forceinline__ T fold_value(T v, double s, unsigned flip_hi)
+{
+    return UNIT ? fold_unit(v, flip_hi) : (T)(s * (double)v);
 }
 
 // Copy of one halo-width piece (Hx elements of a row).  The common case -- 4 doubles, both ends

@@ -24,15 +24,13 @@ __device__ __host__ inline int fold_rows(const ossg_field_desc& f) { return f.Hy
 // One thread serves one (i, level): it issues the loads of all Hy source rows (in chunks of 4)
 // before any store, so that every warp keeps 4 x 256 B in flight -- the fill is a pure
 // latency/bandwidth problem (zero flops).
-template <typename T>
-__device__ __forceinline__ void zipper_column(const ossg_field_desc& f, int i /*1..Nx*/, int kk)
+template <typename T, bool UNIT>
+__device__ __forceinline__ void zipper_column_impl(const ossg_field_desc& f, int i /*1..Nx*/, int kk, double s, int ip)
 {
     const int Nx = f.Nx, Ny = f.Ny, Hy = f.Hy;
     const size_t sx = (size_t)(Nx + 2 * f.Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
     T* c = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
-    double s = f.sign;
-    int ip = f.locx ? Nx - i + 2 : Nx - i + 1;                 // zipper_boundary_condition.jl:73,90,110,125
-    if (ip > Nx) { s = fabs(s); ip -= Nx; }                     // :74-75, :91-92
+    const unsigned flip = sign_flip(s);
     // halo row j = r + 1 (r = 0..Hy-1):  dst row Ny + j, src row Ny - j (y-Center) or Ny - j + 1 (y-Face)
     const T* src = c + (size_t)((f.locy ? Ny : Ny - 1) + Hy - 1) * sx + (ip + f.Hx - 1);   // r = 0, then -sx per row
     T* dst = c + (size_t)(Ny + Hy) * sx + (i + f.Hx - 1);                                   // r = 0, then +sx per row
@@ -44,13 +42,23 @@ __device__ __forceinline__ void zipper_column(const ossg_field_desc& f, int i /*
     for (; r + 4 <= Hy; r += 4) {
         const T v0 = src[-(ptrdiff_t)((r + 0) * sx)], v1 = src[-(ptrdiff_t)((r + 1) * sx)];
         const T v2 = src[-(ptrdiff_t)((r + 2) * sx)], v3 = src[-(ptrdiff_t)((r + 3) * sx)];
-        dst[(size_t)(r + 0) * sx] = apply_sign(v0, s);
-        dst[(size_t)(r + 1) * sx] = apply_sign(v1, s);
-        dst[(size_t)(r + 2) * sx] = apply_sign(v2, s);
-        dst[(size_t)(r + 3) * sx] = apply_sign(v3, s);
+        dst[(size_t)(r + 0) * sx] = fold_value<UNIT>(v0, s, flip);
+        dst[(size_t)(r + 1) * sx] = fold_value<UNIT>(v1, s, flip);
+        dst[(size_t)(r + 2) * sx] = fold_value<UNIT>(v2, s, flip);
+        dst[(size_t)(r + 3) * sx] = fold_value<UNIT>(v3, s, flip);
     }
-    for (; r < Hy; ++r) dst[(size_t)r * sx] = apply_sign(src[-(ptrdiff_t)(r * sx)], s);
-    if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + f.Hx - 1)] = apply_sign(vrow, s);
+    for (; r < Hy; ++r) dst[(size_t)r * sx] = fold_value<UNIT>(src[-(ptrdiff_t)(r * sx)], s, flip);
+    if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + f.Hx - 1)] = fold_value<UNIT>(vrow, s, flip);
+}
+
+template <typename T>
+__device__ __forceinline__ void zipper_column(const ossg_field_desc& f, int i /*1..Nx*/, int kk)
+{
+    double s = f.sign;
+    int ip = f.locx ? f.Nx - i + 2 : f.Nx - i + 1;             // zipper_boundary_condition.jl:73,90,110,125
+    if (ip > f.Nx) { s = fabs(s); ip -= f.Nx; }                 // :74-75, :91-92
+    if (sign_is_unit(s)) zipper_column_impl<T, true>(f, i, kk, s, ip);      // (uniform over the field up to the wrapped column)
+    else zipper_column_impl<T, false>(f, i, kk, s, ip);
 }
 
 __global__ void __launch_bounds__(ZB) zipper_kernel(const __grid_constant__ FieldBatch b)
@@ -99,15 +107,13 @@ __global__ void __launch_bounds__(ZB) periodic_x_kernel(const __grid_constant__ 
 //           rows, all rows of the z-halo levels): a plain periodic copy of Hx elements.
 // Requires Hx < Nx/2 (an edge column then has exactly one image and never is the self-mirrored
 // column Nx/2+1 of the (Face, Center) sign quirk); smaller grids use the two-launch form.
-template <typename T>
-__device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1..Nx*/, int kk)
+template <typename T, bool UNIT>
+__device__ __forceinline__ void fused_column_impl(const ossg_field_desc& f, int i /*1..Nx*/, int kk, double s, int ip)
 {
     const int Nx = f.Nx, Ny = f.Ny, Hy = f.Hy, Hx = f.Hx;
     const size_t sx = (size_t)(Nx + 2 * Hx), sxy = sx * (size_t)(Ny + 2 * Hy);
     T* c = static_cast<T*>(f.data) + (size_t)(f.k0 + kk) * sxy;
-    double s = f.sign;
-    int ip = f.locx ? Nx - i + 2 : Nx - i + 1;
-    if (ip > Nx) { s = fabs(s); ip -= Nx; }
+    const unsigned flip = sign_flip(s);
     const T* src = c + (size_t)((f.locy ? Ny : Ny - 1) + Hy - 1) * sx + (ip + Hx - 1);
     T* dst = c + (size_t)(Ny + Hy) * sx + (i + Hx - 1);
     T* rowNy = c + (size_t)(Ny + Hy - 1) * sx + (i + Hx - 1);
@@ -124,21 +130,31 @@ __device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1
         for (int u = 0; u < 4; ++u) v[u] = src[-(ptrdiff_t)((r + u) * sx)];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const T o = apply_sign(v[u], s);
+            const T o = fold_value<UNIT>(v[u], s, flip);
             dst[(size_t)(r + u) * sx] = o;
             if (has_img) dst[(ptrdiff_t)((r + u) * sx) + img] = o;
         }
     }
     for (; r < Hy; ++r) {
-        const T o = apply_sign(src[-(ptrdiff_t)(r * sx)], s);
+        const T o = fold_value<UNIT>(src[-(ptrdiff_t)(r * sx)], s, flip);
         dst[(size_t)r * sx] = o;
         if (has_img) dst[(ptrdiff_t)(r * sx) + img] = o;
     }
     if (f.locy == OSSG_CENTER) {
-        const T o = fix_row ? apply_sign(vrow, s) : vrow;
+        const T o = fix_row ? fold_value<UNIT>(vrow, s, flip) : vrow;      // (the periodic image of an untouched row Ny is a plain copy)
         if (fix_row) *rowNy = o;
         if (has_img) rowNy[img] = o;
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1..Nx*/, int kk)
+{
+    double s = f.sign;
+    int ip = f.locx ? f.Nx - i + 2 : f.Nx - i + 1;
+    if (ip > f.Nx) { s = fabs(s); ip -= f.Nx; }
+    if (sign_is_unit(s)) fused_column_impl<T, true>(f, i, kk, s, ip);
+    else fused_column_impl<T, false>(f, i, kk, s, ip);
 }
 
 // ---- part B.  A halo piece is Hx elements of a row; the common piece (4 doubles, 32-byte aligned) is
@@ -147,32 +163,30 @@ __device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1
 // contiguous -- the "seam"
 //        [ E-interior(r) | E-halo(r) | W-halo(r+1) | W-interior(r+1) ]        (4 x 32 B = 128 B)
 // with  W-halo(r) <- E-interior(r)  and  E-halo(r) <- W-interior(r).
+// Measured in round 2 on the 1/12 degree fields (profiles/r02_fill_dram.md): thread per (row, side),
+// thread per row, thread per two rows, thread per seam with a lane exchange, two launches instead of
+// one, L1::no_allocate, L2::128B, and cudaLimitMaxL2FetchGranularity = 32 / 128 all run within 2 % of
+// each other (91 ... 94 us for 4 fields, 99 us in two launches).  The L2 fetches 128 bytes around every
+// 32-byte piece by default (3 lines per 2 rows: the row pitch is an odd multiple of 64 bytes), 238 MB
+// of DRAM reads for 119 MB requested; the L2::64B prefetch-size qualifier brings that to 178 MB and
+// the time from 93 to 91 us.  Bytes are not what bounds this part: it issues ~3.7 M scattered DRAM
+// transactions, 34 KB apart, about 60 G/s -- the activation rate of the HBM3e stacks (tFAW), not their
+// bandwidth.  Kept: thread per row with the L2::64B loads (fewest bytes, fastest by 2 %).
 struct Piece32 { double a, b, c, d; };
 // every halo piece of the field is a 32-byte aligned run of 4 doubles (base, row pitch and Nx all multiples of 32 bytes)
 __host__ __device__ inline bool piece32_ok(const ossg_field_desc& f)
 {
     return f.elem_type == OSSG_F64 && f.Hx == 4 && f.Nx % 4 == 0 && (reinterpret_cast<uintptr_t>(f.data) & 31) == 0;
 }
-template <int HINT>
 __device__ __forceinline__ Piece32 ld_piece32(const void* p)
 {
     Piece32 v;
-    if (HINT == 1)      asm volatile("ld.global.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
-    else if (HINT == 3) asm volatile("ld.global.L2::64B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
-    else if (HINT == 2) asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
-    else                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    asm volatile("ld.global.L2::64B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_piece32(void* p, const Piece32& v)
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
-}
-__device__ __forceinline__ Piece32 shfl_piece(const Piece32& v, int delta /* +1: from lane-1, -1: from lane+1 */)
-{
-    Piece32 r;
-    if (delta > 0) { r.a = __shfl_up_sync(0xffffffffu, v.a, 1); r.b = __shfl_up_sync(0xffffffffu, v.b, 1); r.c = __shfl_up_sync(0xffffffffu, v.c, 1); r.d = __shfl_up_sync(0xffffffffu, v.d, 1); }
-    else { r.a = __shfl_down_sync(0xffffffffu, v.a, 1); r.b = __shfl_down_sync(0xffffffffu, v.b, 1); r.c = __shfl_down_sync(0xffffffffu, v.c, 1); r.d = __shfl_down_sync(0xffffffffu, v.d, 1); }
-    return r;
 }
 
 // rows whose periodic images part A writes: north-halo rows (and row Ny of y-Center fields) of the zipper levels
@@ -183,7 +197,7 @@ __device__ __forceinline__ bool part_a_row(const ossg_field_desc& f, long long r
     return lev >= f.k0 && lev < f.k0 + f.nk && jrow >= f.Ny + f.Hy - (f.locy == OSSG_CENTER ? 1 : 0);
 }
 
-// variant 0: one thread per (row, side), load before store
+// general form: one thread per (row, side), load before store
 template <typename T>
 __device__ __forceinline__ void fused_periodic_row(const ossg_field_desc& f, size_t row, int side)
 {
@@ -194,83 +208,11 @@ __device__ __forceinline__ void fused_periodic_row(const ossg_field_desc& f, siz
     copy_halo_piece(dst, src, Hx);
 }
 
-// variants 1, 2: one thread per ROWS consecutive rows, both sides; all loads before the stores
-template <int ROWS, int HINT>
-__device__ __forceinline__ void fused_periodic_rows32(const ossg_field_desc& f, long long row0, long long rows, bool all_rows)
-{
-    const size_t pitch = (size_t)(f.Nx + 2 * f.Hx) * 8;
-    char* c = static_cast<char*>(f.data) + (size_t)row0 * pitch;
-    Piece32 e[ROWS], w[ROWS];
-    bool on[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u) {
-        on[u] = row0 + u < rows && (all_rows || !part_a_row(f, row0 + u));
-        if (on[u]) { e[u] = ld_piece32<HINT>(c + u * pitch + (size_t)f.Nx * 8); w[u] = ld_piece32<HINT>(c + u * pitch + 32); }
-    }
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u)
-        if (on[u]) { st_piece32(c + u * pitch, e[u]); st_piece32(c + u * pitch + (size_t)f.Nx * 8 + 32, w[u]); }
-}
-
-// variant 3: one thread per seam t (between rows t-1 and t, t = 0..rows): it loads the two outer
-// pieces of its seam, trades them with its lane neighbours and stores the two inner pieces -- 64
-// contiguous bytes.  Every 128-byte seam is read once and written once by ONE thread.
-template <int HINT>
-__device__ __forceinline__ void fused_periodic_seam32(const ossg_field_desc& f, long long t, long long rows, bool all_rows)
-{
-    const size_t pitch = (size_t)(f.Nx + 2 * f.Hx) * 8;
-    char* base = static_cast<char*>(f.data);
-    const int lane = threadIdx.x & 31;
-    auto live = [&](long long r) { return r >= 0 && r < rows && (all_rows || !part_a_row(f, r)); };
-    const bool lo = live(t - 1), hi = live(t);              // row below / above the seam takes part
-    Piece32 e = {}, w = {};
-    if (lo) e = ld_piece32<HINT>(base + (size_t)(t - 1) * pitch + (size_t)f.Nx * 8);      // E-interior(t-1)
-    if (hi) w = ld_piece32<HINT>(base + (size_t)t * pitch + 32);                          // W-interior(t)
-    Piece32 w_lo = shfl_piece(w, +1);                         // W-interior(t-1), loaded by the thread of seam t-1
-    Piece32 e_hi = shfl_piece(e, -1);                         // E-interior(t),   loaded by the thread of seam t+1
-    if (lane == 0 && lo) w_lo = ld_piece32<HINT>(base + (size_t)(t - 1) * pitch + 32);
-    if (lane == 31 && hi) e_hi = ld_piece32<HINT>(base + (size_t)t * pitch + (size_t)f.Nx * 8);
-    if (lo) st_piece32(base + (size_t)(t - 1) * pitch + (size_t)f.Nx * 8 + 32, w_lo);     // E-halo(t-1)
-    if (hi) st_piece32(base + (size_t)t * pitch, e_hi);                                   // W-halo(t)
-}
-
 struct FusedBatch {
     FieldBatch b;
-    int blocksA[MAX_BATCH];          // part A blocks of field k: ceil(Nx / ZB) * nk  (0: part B covers every row)
+    int blocksA[MAX_BATCH];          // part A blocks of field k: ceil(Nx / ZB) * nk
     int chunksA[MAX_BATCH];          // ceil(Nx / ZB)
-    int variant;                     // part B form, see fill_variant()
 };
-
-// Part B form (experiment knob OSSG_FILL_VARIANT, read once; default = the measured best):
-//   0  thread per (row, side)            1  thread per row, both sides        2  thread per 2 rows
-//   3  thread per seam (lane exchange)   +10: loads carry an L2::128B prefetch hint   +20: L1::no_allocate
-//   +100: two launches (zipper_kernel, then part B over all rows) instead of one
-static int g_fill_variant_override = -1;          // EXPERIMENT HOOK (tools/fill_variants.py); removed once the default is chosen
-static int fill_variant()
-{
-    static const int v = env_int("OSSG_FILL_VARIANT", 0);
-    return g_fill_variant_override >= 0 ? g_fill_variant_override : v;
-}
-
-template <int HINT>
-__device__ __forceinline__ void fused_part_b(const ossg_field_desc& f, int form, long long t, bool all_rows)
-{
-    const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
-    const bool fast = piece32_ok(f);
-    if (form == 0 || !fast) {
-        if (t >= 2 * rows) return;
-        const long long row = t >> 1;
-        if (!all_rows && part_a_row(f, row)) return;
-        if (f.elem_type == OSSG_F64) fused_periodic_row<double>(f, (size_t)row, (int)(t & 1));
-        else fused_periodic_row<float>(f, (size_t)row, (int)(t & 1));
-    } else if (form == 1) {
-        if (t < rows) fused_periodic_rows32<1, HINT>(f, t, rows, all_rows);
-    } else if (form == 2) {
-        if (2 * t < rows) fused_periodic_rows32<2, HINT>(f, 2 * t, rows, all_rows);
-    } else {
-        if (t <= (rows | 31)) fused_periodic_seam32<HINT>(f, t, rows, all_rows);   // (whole warps: the lane exchange is warp-wide)
-    }
-}
 
 __global__ void __launch_bounds__(ZB) fill_fused_kernel(const __grid_constant__ FusedBatch fb)
 {
@@ -285,13 +227,21 @@ __global__ void __launch_bounds__(ZB) fill_fused_kernel(const __grid_constant__ 
         else fused_column<float>(f, i, kk);
         return;
     }
+    const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
     const long long t = (long long)(blockIdx.x - nA) * ZB + threadIdx.x;
-    const int form = fb.variant % 10, hint = (fb.variant / 10) % 10;
-    const bool all_rows = nA == 0;
-    if (hint == 3) fused_part_b<3>(f, form, t, all_rows);
-    else if (hint == 1) fused_part_b<1>(f, form, t, all_rows);
-    else if (hint == 2) fused_part_b<2>(f, form, t, all_rows);
-    else fused_part_b<0>(f, form, t, all_rows);
+    if (piece32_ok(f)) {                                              // thread per row: both loads, then both stores
+        if (t >= rows || part_a_row(f, t)) return;
+        char* c = static_cast<char*>(f.data) + (size_t)t * (size_t)(f.Nx + 2 * f.Hx) * 8;
+        const Piece32 e = ld_piece32(c + (size_t)f.Nx * 8), w = ld_piece32(c + 32);
+        st_piece32(c, e);
+        st_piece32(c + (size_t)f.Nx * 8 + 32, w);
+        return;
+    }
+    if (t >= 2 * rows) return;
+    const long long row = t >> 1;
+    if (part_a_row(f, row)) return;
+    if (f.elem_type == OSSG_F64) fused_periodic_row<double>(f, (size_t)row, (int)(t & 1));
+    else fused_periodic_row<float>(f, (size_t)row, (int)(t & 1));
 }
 
 // ------------------------------------------------------------------ (x,y)-partition fold: pack / unpack
@@ -393,28 +343,17 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
         if (fusable) {                       // zipper + periodic in one launch
             FusedBatch fb;
             fb.b = b;
-            fb.variant = fill_variant() % 100;
-            const bool two_launches = fill_variant() >= 100;
-            const int form = fb.variant % 10;
             long long gxf = 0;
-            int zx = 0, zy = 0;
             for (int k = 0; k < b.n; ++k) {
                 const ossg_field_desc& f = b.f[k];
                 fb.chunksA[k] = ceil_div(f.Nx, ZB);
-                fb.blocksA[k] = two_launches ? 0 : fb.chunksA[k] * f.nk;
-                zx = max(zx, fb.chunksA[k]); zy = max(zy, f.nk);
+                fb.blocksA[k] = fb.chunksA[k] * f.nk;
                 const long long rows = (long long)(f.Ny + 2 * f.Hy) * (f.Nz + 2 * f.Hz);
-                const bool fast = piece32_ok(f);
-                const long long threadsB = (form == 0 || !fast) ? 2 * rows : form == 1 ? rows : form == 2 ? (rows + 1) / 2 : (rows | 31) + 1;
+                const long long threadsB = piece32_ok(f) ? rows : 2 * rows;
                 const long long blocks = fb.blocksA[k] + (threadsB + ZB - 1) / ZB;
                 gxf = gxf > blocks ? gxf : blocks;
             }
             if (gxf > 0x7fffffffLL) return set_error(OSSG_EINVAL, "field too large for one launch");
-            if (two_launches) {
-                if (zy > 65535) return set_error(OSSG_EINVAL, "too many levels for one launch: %d", zy);
-                zipper_kernel<<<dim3(zx, zy, b.n), ZB, 0, s>>>(b);
-                OSSG_LAUNCH_CHECK("zipper_kernel");
-            }
             fill_fused_kernel<<<dim3((unsigned)gxf, b.n), ZB, 0, s>>>(fb);
             OSSG_LAUNCH_CHECK("fill_fused_kernel");
             continue;
@@ -441,8 +380,6 @@ static int launch_zipper_batch(const ossg_field_desc* fields, int n, bool with_p
 }  // namespace ossg
 
 using namespace ossg;
-
-extern "C" int ossg_experiment_fill_variant(int v) { ossg::g_fill_variant_override = v; return 0; }
 
 extern "C" int ossg_zipper_fill(const ossg_field_desc* f, void* stream)
 {

@@ -733,30 +733,26 @@ def test_zero_y_halo_still_overwrites_the_fold_row(ossg, oracle):
         assert _same_bits(dv.cpu().numpy(), want), (dims, loc)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 11, 13, 21, 23, 100, 101, 103])
-def test_fill_halo_regions_forms_are_bit_identical(ossg, oracle, variant):
-    """Every part-B form of the fused fill (csrc/ossg_zipper.cu fill_variant) against the oracle, on a
-    grid whose rows are 32-byte aligned (the 256-bit piece path) and on one whose rows are not."""
+def test_fill_halo_regions_piece_paths_are_bit_identical(ossg, oracle):
+    """The fused fill's periodic part: rows that are 32-byte aligned take the 256-bit piece path (one
+    thread per row, L2::64B loads), other layouts the general per-(row, side) path; both against the oracle,
+    four fields per launch."""
     L = ossg._lib.lib()
-    L.ossg_experiment_fill_variant(variant)
-    try:
-        for dims in ((60, 30, 3, 4, 4, 2), (62, 21, 5, 4, 3, 1), (34, 17, 2, 3, 9, 1)):
-            Nx, Ny, Nz, Hx, Hy, Hz = dims
-            shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
-            fields = []
-            for q, (locname, loc) in enumerate(LOCS.items()):
-                sign = -1 if loc[0] != loc[1] else 1
-                host = _poisoned_field(shape, Nx, Ny, Nz, Hx, Hy, Hz, np.float64, seed=31 + q)
-                dev = torch.as_tensor(host).cuda()
-                fields.append((host, dev, loc, sign, _desc(ossg, dev, dims, loc, sign)))
-            arr = (ossg._lib.FieldDesc * 4)(*[f[4] for f in fields])
-            ossg._lib.check(L.ossg_fill_halo_regions_batch(arr, 4, None))
-            torch.cuda.synchronize()
-            for host, dev, loc, sign, _ in fields:
-                want = oracle.fill_halo_regions(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
-                assert _same_bits(dev.cpu().numpy(), want), (variant, dims, loc)
-    finally:
-        L.ossg_experiment_fill_variant(-1)
+    for dims in ((60, 30, 3, 4, 4, 2), (62, 21, 5, 4, 3, 1), (34, 17, 2, 3, 9, 1), (64, 12, 2, 4, 2, 0)):
+        Nx, Ny, Nz, Hx, Hy, Hz = dims
+        shape = (Nz + 2 * Hz, Ny + 2 * Hy, Nx + 2 * Hx)
+        fields = []
+        for q, (locname, loc) in enumerate(LOCS.items()):
+            sign = -1 if loc[0] != loc[1] else 1
+            host = _poisoned_field(shape, Nx, Ny, Nz, Hx, Hy, Hz, np.float64, seed=31 + q)
+            dev = torch.as_tensor(host).cuda()
+            fields.append((host, dev, loc, sign, _desc(ossg, dev, dims, loc, sign)))
+        arr = (ossg._lib.FieldDesc * 4)(*[f[4] for f in fields])
+        ossg._lib.check(L.ossg_fill_halo_regions_batch(arr, 4, None))
+        torch.cuda.synchronize()
+        for host, dev, loc, sign, _ in fields:
+            want = oracle.fill_halo_regions(host.copy(), Nx, Ny, Nz, Hx, Hy, Hz, loc[0], loc[1], sign)
+            assert _same_bits(dev.cpu().numpy(), want), (dims, loc)
 
 
 def test_table_cache_in_the_workspace(ossg, oracle):
