@@ -253,7 +253,8 @@ class Ctx:
             saved = os.dup(1)
             os.dup2(2, 1)
             try:
-                dist.init_process_group("nccl", device_id=self.dev)
+                import datetime
+                dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=300))
                 dist.barrier()
                 torch.cuda.synchronize(self.dev)
             finally:
@@ -440,6 +441,8 @@ def parity_construction(ctx, partitions):
 
 
 def run_own(args):
+    # a partner that never shows up must end this run, not stall it for minutes (library default: 120 s)
+    os.environ.setdefault("OSSG_PEER_TIMEOUT_MS", "30000")
     ctx = Ctx(args)
     torch, dist, _lib, L = ctx.torch, ctx.dist, ctx._lib, ctx.L
     import ossg_b200 as ossg
@@ -541,7 +544,10 @@ def run_own(args):
 
     extra = {}
     if world == 1:
-        zipper = bench_zipper(L, _lib, torch, dev, stream, W, nx, ny)
+        zipper = bench_zipper(ctx, L, _lib, torch, dev, stream, W, nx, ny)
+        par = zipper.pop("parity", None) if isinstance(zipper, dict) else None
+        if par is not None:
+            parity["fill_halo_regions"] = par
         extra["configs"] = bench_small_configs(ctx)
     else:
         # every factorisation of N, timed like the headline (BASELINE config 4)
@@ -565,7 +571,11 @@ def run_own(args):
                     parity[key] = par
             except Exception as e:          # noqa: BLE001
                 zipper[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
-            torch.cuda.empty_cache()
+                parity[key] = {"mismatches": 1, "error": "section failed before its parity check"}
+            try:
+                torch.cuda.empty_cache()
+            except Exception:               # noqa: BLE001  (a dead context after a trapped kernel: the line below still goes out)
+                pass
     parity["mismatches"] = sum(int(v.get("mismatches", 0)) for v in parity.values() if isinstance(v, dict))
 
     if rank != 0:
@@ -651,25 +661,28 @@ def run_own(args):
 
 # FLUSHED configuration first (the headline of the zipper roofline), the repeat loop beside it; `traffic` = DRAM bytes per
 # launch from the committed ncu captures of the SAME loops (tools/prof_fill.py; profiles/r02_fill_dram.md)
-NCU_TRAFFIC_ZIPPER_FLUSH4 = None
-NCU_TRAFFIC_ZIPPER_LOOP8 = None
-NCU_TRAFFIC_FILL_FLUSH4 = None
+NCU_TRAFFIC_ZIPPER_FLUSH4 = 119344960       # dram__bytes_read + write per launch, mean of 4 captured launches (r02b)
+NCU_TRAFFIC_ZIPPER_LOOP8 = 237173888
+NCU_TRAFFIC_FILL_FLUSH4 = 320533504
 
 
 def zipper_roofline(zipper, hbm_peak, peak_src):
-    out = None
-    head = zipper.get("batch4_clean_flush") or zipper.get("batch4")
-    if head and "gbs" in head:
-        out = {"bound": "hbm", "kernel": "zipper_kernel", "achieved": head["gbs"], "peak": hbm_peak, "unit": "GB/s",
-               "frac": head["gbs"] / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": head["algorithmic_bytes"],
-               "traffic": NCU_TRAFFIC_ZIPPER_FLUSH4,
-               "measured_on": "batch4_clean_flush: c,u,v,zeta per launch, L2 flushed (256 MB write + 256 MB read) before every timed launch"}
-        for key, traffic in (("batch4", NCU_TRAFFIC_ZIPPER_FLUSH4), ("repeat100_zipper_batch8_larger_than_l2", NCU_TRAFFIC_ZIPPER_LOOP8),
-                             ("fill_halo_regions_batch4", NCU_TRAFFIC_FILL_FLUSH4)):
-            z = zipper.get(key)
-            if z and "gbs" in z:
-                out[key] = {"achieved": z["gbs"], "frac": z["gbs"] / hbm_peak, "algorithmic_bytes_per_launch": z["algorithmic_bytes"],
-                            "traffic": traffic}
+    """headline: c,u,v,zeta per launch with the L2 flushed by a 256 MB write before every timed launch (the
+    conservative number: the flush's dirty lines are written back during the timed kernel); beside it the same
+    after a clean flush, the 8-field repeat loop and the whole fill_halo_regions!"""
+    head = zipper.get("batch4")
+    if not head or "gbs" not in head:
+        return None
+    out = {"bound": "hbm", "kernel": "zipper_kernel", "achieved": head["gbs"], "peak": hbm_peak, "unit": "GB/s",
+           "frac": head["gbs"] / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": head["algorithmic_bytes"],
+           "traffic": NCU_TRAFFIC_ZIPPER_FLUSH4, "traffic_source": "profiles/r02_fill_dram.md (ncu dram__bytes of the same loops)",
+           "measured_on": "batch4: c,u,v,zeta per launch, L2 flushed (256 MB write) before every timed launch"}
+    for key, traffic in (("batch4_clean_flush", NCU_TRAFFIC_ZIPPER_FLUSH4), ("repeat100_zipper_batch8_larger_than_l2", NCU_TRAFFIC_ZIPPER_LOOP8),
+                         ("fill_halo_regions_batch4", NCU_TRAFFIC_FILL_FLUSH4)):
+        z = zipper.get(key)
+        if z and "gbs" in z:
+            out[key] = {"achieved": z["gbs"], "frac": z["gbs"] / hbm_peak, "algorithmic_bytes_per_launch": z["algorithmic_bytes"],
+                        "traffic": traffic, "dram_gbs": traffic / (z["ms"] * 1e-3) / 1e9, "dram_frac": traffic / (z["ms"] * 1e-3) / 1e9 / hbm_peak}
     return out
 
 
@@ -733,7 +746,17 @@ def bench_small_configs(ctx):
     return out
 
 
-def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
+class _RawField:
+    """adapter: a bare tensor + descriptor where FillReference expects a Field"""
+
+    def __init__(self, data, desc):
+        self.data, self._desc = data, desc
+
+    def descriptor(self):
+        return self._desc
+
+
+def bench_zipper(ctx, L, _lib, torch, dev, stream, W, nx, ny):
     """zipper halo-fill GB/s: c (C,C,+1), u (F,C,-1), v (C,F,-1), zeta (F,F,+1) on the workload grid,
     FP64, one batched launch per fill, L2 flushed between timed fills."""
     H, Nz = W["halo"], W["Nz"]
@@ -748,11 +771,29 @@ def bench_zipper(L, _lib, torch, dev, stream, W, nx, ny):
         for t, (loc, s) in zip(fields, specs)])
     for k in range(len(specs)):
         _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(descs[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
+    # ---- parity at full size first: ONE zipper fill, then (fresh fields) ONE fill_halo_regions! of c,u,v,zeta against the
+    # oracle's fill of the global field regenerated on the host (numpy hash), both boundary levels, whole parent window
+    res = {}
+    try:
+        ref = FillReference(ctx, 4)
+        raw = [_RawField(t, descs[k]) for k, t in enumerate(fields)]
+        par = {"what": "4320x2160 fields c,u,v,zeta, levels 1 and Nz, every element of the padded window (interior, fold rows, x halos, "
+                       "corners) against the oracle on the host-regenerated global field"}
+        for name, fn, full in (("zipper", L.ossg_zipper_fill_batch, False), ("fill_halo_regions", L.ossg_fill_halo_regions_batch, True)):
+            for k in range(len(specs)):
+                _lib.check_util(_lib.testutil().ossg_synth_field(C.byref(descs[k]), 0x5EED + k, 1, 1, stream.cuda_stream))
+            _lib.check(fn(descs, 4, stream.cuda_stream))
+            torch.cuda.synchronize(dev)
+            par[name] = {"mismatches": ref.mismatches(raw, (1, 1, nx, ny), full=full)}
+        ref.close()
+        par["mismatches"] = sum(v["mismatches"] for v in par.values() if isinstance(v, dict))
+        res["parity"] = par
+    except Exception as e:          # noqa: BLE001  (the timing below does not depend on it; a failure is reported, not hidden)
+        res["parity"] = {"error": f"{type(e).__name__}: {e}"[:300], "mismatches": 1}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     algo = 0
     for (loc, _) in specs:
         algo += 2 * H * nx * Nz * 8 + (nx * Nz * 8 if loc[1] == 0 else 0)
-    res = {}
     # periodic west/east fill over the whole (y, z) parent extent: read + write of 2 Hx elements per row
     rows = (ny + 2 * H) * (Nz + 2 * H)
     algo_full = algo + len(specs) * rows * 2 * (2 * H) * 8
@@ -883,13 +924,14 @@ class FillReference:
         import numpy as np
         W = WORKLOAD
         self.ctx, self.ks = ctx, [1, W["Nz"]]
-        d = f"/dev/shm/ossg_fill_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        d = f"/dev/shm/ossg_fill_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if ctx.world > 1 else os.getpid()}"
         if ctx.rank == 0:
             os.makedirs(d, exist_ok=True)
             for k in range(nfields):
                 np.save(os.path.join(d, f"f{k}.npy"), host_synth_levels(0x5EED + k, W["Nx"], W["Ny"], W["halo"], self.ks))
         box = [d]
-        ctx.dist.broadcast_object_list(box, src=0)
+        if ctx.world > 1:
+            ctx.dist.broadcast_object_list(box, src=0)
         self.dir = box[0]
         ctx.barrier()
         self.base = [np.load(os.path.join(self.dir, f"f{k}.npy"), mmap_mode="r") for k in range(nfields)]

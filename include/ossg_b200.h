@@ -277,7 +277,8 @@ typedef struct ossg_peer_fold {
                                                default 120 s; the kernel then TRAPS): 2*OSSG_MAX_PEERS+1
                                                uint64, zero-initialised once, never reset            */
     void*   flags_peer[OSSG_MAX_PEERS];     /* the peers' flag blocks, peer-mapped ([me] unused)  */
-    uint64_t epoch;                         /* 1, 2, 3, ... one per call, the same on all ranks  */
+    uint64_t epoch;                         /* 1, 2, 3, ... one per call ON THIS FLAG BLOCK, consecutive, the same
+                                               on all ranks (completion is counted in arrivals per epoch)          */
     int32_t push;                           /* 0: each rank loads its sources from the owners;
                                                1: each rank stores its rows into the destinations'
                                                halos (posted NVLink writes);
@@ -315,7 +316,8 @@ typedef struct ossg_peer_halo {
     int32_t phase;                          /* 0: south/north rows, 1: west/east columns,
                                                2: unpack of the staged west/east columns (local)  */
     int32_t reserved;
-    void*   flags_local;                    /* flag block of THIS phase (2*OSSG_MAX_PEERS+1 uint64) */
+    void*   flags_local;                    /* flag block of THIS phase (2*OSSG_MAX_PEERS+1 uint64); every phase
+                                               has its own block and its own consecutive epochs 1, 2, 3, ...        */
     void*   flags_peer[OSSG_MAX_PEERS];     /* the same block on rank r, peer-mapped              */
     uint64_t epoch;
     /* Optional staging of phase 1: a halo column is a 32-byte piece per row, the least efficient

@@ -428,7 +428,10 @@ struct TileSmem {
 // Thread (tx, ty) copies patch point (tx, ty) of all four patches (one offset computation, the
 // staggering shifts are constants); the first QY + TX threads then copy column TX and row TY.
 // Ends with the wait for the thread's own copies; the caller synchronises the block.
-__device__ __forceinline__ void tile_stage_cp_async(const BuildArgs& a, const Window& w, int It0, int Jt0, int tid, const TileSmem<false>& S)
+// CHECK = false: the whole (TX+1) x (TY+1) patch of every staggering lies inside the window (true for every tile
+// that is not cut by the right / top edge of the fast rectangle, which itself stays one cell inside the window).
+template <bool CHECK>
+__device__ __forceinline__ void tile_stage_points(const BuildArgs& a, const Window& w, int It0, int Jt0, int tid, const TileSmem<false>& S)
 {
     constexpr int QX = TileGeom<false>::QX, PS = TileGeom<false>::PS;
     auto stage_point = [&](int pi, int pj) {
@@ -439,7 +442,7 @@ __device__ __forceinline__ void tile_stage_cp_async(const BuildArgs& a, const Wi
         for (int loc = 0; loc < 4; ++loc) {
             const int di = patch_di(loc), dj = patch_dj(loc);
             const int i2 = iw + di, j2 = jw + dj;
-            if (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny) {
+            if (!CHECK || (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny)) {
                 const long long o2 = o + (long long)dj * w.wnx + di;
                 cp_async_8(&S.lam[loc * PS + p], a.coords64[loc] + o2);
                 cp_async_8(&S.phr[loc * PS + p], a.coords64[4 + loc] + o2);
@@ -452,6 +455,13 @@ __device__ __forceinline__ void tile_stage_cp_async(const BuildArgs& a, const Wi
     stage_point(threadIdx.x, threadIdx.y);
     if (tid < QY) stage_point(TX, tid);
     else if (tid < QY + TX) stage_point(tid - QY, TY);
+}
+
+__device__ __forceinline__ void tile_stage_cp_async(const BuildArgs& a, const Window& w, int It0, int Jt0, int tid, const TileSmem<false>& S)
+{
+    const bool inside = It0 - 1 >= w.I0 && It0 + TX < w.I0 + w.wnx && Jt0 - 1 >= w.J0 && Jt0 + TY < w.J0 + w.wny;   // (block-uniform)
+    if (inside) tile_stage_points<false>(a, w, It0, Jt0, tid, S);
+    else tile_stage_points<true>(a, w, It0, Jt0, tid, S);
     cp_async_wait_all();
 }
 

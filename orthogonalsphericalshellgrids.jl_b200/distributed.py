@@ -460,7 +460,10 @@ class PeerHalo:
         self.fold = PeerFold(fields, group=group)
         L = _lib.lib()
         dev = fields[0].data.device
-        self.flags = [torch.zeros(2 * _lib.OSSG_MAX_PEERS + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+        # one flag block and one epoch counter per phase: the epochs a flag block sees must be consecutive (1, 2, 3, ...),
+        # because "rank r has finished exchange e" is an arrival COUNT (e x arrivals per kernel), not a stored epoch
+        self.flags = [torch.zeros(2 * _lib.OSSG_MAX_PEERS + 1, dtype=torch.int64, device=dev) for _ in range(3)]
+        self.epochs = [0, 0, 0]
         torch.cuda.synchronize(dev)
 
         def export(ptr):
@@ -500,9 +503,9 @@ class PeerHalo:
             hd = _lib.PeerHaloDesc()
             hd.me, hd.nranks, hd.phase = me, world, phase
             hd.north, hd.south, hd.east, hd.west = nb["north"], nb["south"], nb["east"], nb["west"]
-            hd.flags_local = self.flags[min(phase, 1)].data_ptr()
+            hd.flags_local = self.flags[phase].data_ptr()
             for r in set(v for v in nb.values() if v >= 0 and v != me):
-                hd.flags_peer[r] = open_(*gathered[r]["flags"][min(phase, 1)])
+                hd.flags_peer[r] = open_(*gathered[r]["flags"][phase])
             self.descs.append(hd)
         # per batch: where this rank pushes (the neighbours' buffers) and what it unpacks (its own)
         self.stage_ptrs = []
@@ -543,8 +546,8 @@ class PeerHalo:
         for phase in (0, 1, 2) if self.staged else (0, 1):
             for b, (arr, n) in enumerate(self._launches):
                 hd = self.descs[phase]
-                self.epoch += 1
-                hd.epoch = self.epoch
+                self.epochs[phase] += 1
+                hd.epoch = self.epochs[phase]
                 if self.staged and phase > 0:
                     sp = self.stage_ptrs[b]
                     hd.stage_to_east, hd.stage_to_west = sp["to_east"], sp["to_west"]
