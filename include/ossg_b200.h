@@ -247,9 +247,9 @@ int ossg_nccl_comm_destroy(void* comm);
  * the field arrays of the other top-row ranks (CUDA IPC, ossg_ipc_export / ossg_ipc_open) and its
  * zipper kernel loads the source rows straight from the owner (the mirror rank; for x-Face fields
  * also one column of its neighbour) while writing its own north halo -- each element crosses
- * NVLink once.  Ranks order themselves with release/acquire flags in IPC-mapped device memory (an
- * "arrived" epoch at kernel start; at kernel end every block signals its partners and block 0 waits
- * for all partners' blocks); the host never synchronises and no NCCL call is on this path.  A rank
+ * NVLink once.  Ranks order themselves with release/acquire epoch flags in IPC-mapped device memory (an
+ * "arrived" flag at kernel start, a "finished" flag written by the last block at kernel end, which then
+ * waits for the partners' flags); the host never synchronises and no NCCL call is on this path.  A rank
  * that never makes the matching call is a programming error: the waiting kernels trap after
  * OSSG_PEER_TIMEOUT_MS and the next CUDA call of the process fails.  Same result as ossg_zipper_fill on the global
  * field (src/zipper_boundary_condition.jl:70-155), bit for bit.                                 */
@@ -270,15 +270,14 @@ typedef struct ossg_peer_fold {
     int32_t me, nranks;                     /* this rank's x-index in the top row, Rx (<= 8)     */
     int32_t i0[OSSG_MAX_PEERS];             /* global first interior column of top-row rank r    */
     int32_t nx[OSSG_MAX_PEERS];             /* its width                                         */
-    void*   flags_local;                    /* this rank's flag block: ready[OSSG_MAX_PEERS] epochs,
-                                               done[OSSG_MAX_PEERS] arrival counts (uint64), then one
-                                               uint64 whose upper half is the error word (set to 1 when
+    void*   flags_local;                    /* this rank's flag block: ready[OSSG_MAX_PEERS] and
+                                               done[OSSG_MAX_PEERS] epochs (uint64), then one uint64: lower
+                                               half a block counter, upper half the error word (set to 1 when
                                                a partner did not show up within OSSG_PEER_TIMEOUT_MS,
                                                default 120 s; the kernel then TRAPS): 2*OSSG_MAX_PEERS+1
                                                uint64, zero-initialised once, never reset            */
     void*   flags_peer[OSSG_MAX_PEERS];     /* the peers' flag blocks, peer-mapped ([me] unused)  */
-    uint64_t epoch;                         /* 1, 2, 3, ... one per call ON THIS FLAG BLOCK, consecutive, the same
-                                               on all ranks (completion is counted in arrivals per epoch)          */
+    uint64_t epoch;                         /* 1, 2, 3, ... growing with every call on this flag block, the same on all ranks */
     int32_t push;                           /* 0: each rank loads its sources from the owners;
                                                1: each rank stores its rows into the destinations'
                                                halos (posted NVLink writes);
@@ -316,8 +315,7 @@ typedef struct ossg_peer_halo {
     int32_t phase;                          /* 0: south/north rows, 1: west/east columns,
                                                2: unpack of the staged west/east columns (local)  */
     int32_t reserved;
-    void*   flags_local;                    /* flag block of THIS phase (2*OSSG_MAX_PEERS+1 uint64); every phase
-                                               has its own block and its own consecutive epochs 1, 2, 3, ...        */
+    void*   flags_local;                    /* flag block of THIS phase (2*OSSG_MAX_PEERS+1 uint64)              */
     void*   flags_peer[OSSG_MAX_PEERS];     /* the same block on rank r, peer-mapped              */
     uint64_t epoch;
     /* Optional staging of phase 1: a halo column is a 32-byte piece per row, the least efficient

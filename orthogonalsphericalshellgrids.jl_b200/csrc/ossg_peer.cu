@@ -11,23 +11,18 @@
 // launch, every element crosses NVLink once and is written once, no staging buffer.
 //
 // Ordering between ranks (no host synchronisation, no NCCL call on this path).  Every rank owns a flag
-// block in device memory that its partners map through CUDA IPC: ready[r] (an epoch) and done[r] (an
-// arrival count), r = partner rank.
-//   start: block 0 stores epoch -> ready[me] on every partner (st.release.sys).  Every warp prefetches
-//          the local rows of its first work item, then waits until ready[r] >= epoch for all partners r
-//          (ld.acquire.sys on LOCAL memory).  A rank's kernel is stream-ordered after the kernels that
-//          produced its interior and consumed its halo, so "kernel started" == "interior ready, halo free".
-//   end:   every block, once its stores (or peer loads) are done, fences at system scope and adds to
-//          done[me] on every partner (red.release.sys.add).  The arrivals of one kernel always sum to
-//          PEER_ARRIVALS (block 0 adds the remainder), so "rank r has finished exchange e" is
-//          done[r] >= e * PEER_ARRIVALS with no per-exchange state.  Only block 0 waits for that, from
-//          all partners, before it exits: work queued behind the kernel then sees a complete halo (push)
-//          and cannot overwrite rows a partner still reads (pull).  No block counter, no local barrier
-//          between the blocks: the fences of different blocks overlap.
-// Flags only grow, nothing is ever reset.  A partner that never shows up (a rank that did not make the
-// matching call) is a programming error: after OSSG_PEER_TIMEOUT_MS (default 120 s, 0 = wait forever)
-// the waiting kernel raises the error word of its flag block and TRAPS -- the next CUDA call of this
-// process fails loudly instead of continuing on stale halos.
+// block in device memory that its partners map through CUDA IPC: ready[r] and done[r] (epochs), r = partner rank.
+//   start: block 0 stores epoch -> ready[me] on every partner (st.release.sys; no fence in front of it: the
+//          rank's earlier kernels are complete by stream order).  Every warp prefetches the local rows of its
+//          block's first work item, then waits until ready[r] >= epoch for all partners r (ld.acquire.sys on
+//          LOCAL memory).  "Kernel started" == "interior ready, halo free to be overwritten".
+//   end:   the last block to finish (local arrival counter) fences at system scope, stores epoch -> done[me] on
+//          every partner and waits for done[r] >= epoch from all of them before it exits: work queued behind
+//          the kernel then sees a complete halo (push) and cannot overwrite rows a partner still reads (pull).
+// Epochs only grow, nothing is ever reset.  A partner that never shows up (a rank that did not make the
+// matching call) is a programming error: after OSSG_PEER_TIMEOUT_MS (default 120 s, 0 = wait forever) the
+// waiting kernel raises the error word of its flag block and TRAPS -- the next CUDA call of this process
+// fails loudly instead of continuing on stale halos.
 #include <mutex>
 #include <vector>
 #include <cstring>
@@ -52,18 +47,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-constexpr unsigned long long PEER_ARRIVALS = 1ull << 20;     // arrivals per kernel and partner (more than any grid has blocks)
-
 // Wait until *flag >= target.  A missing partner must not hang the GPU for ever and must not pass
 // silently either: on timeout the error word is raised (for post-mortem inspection) and the kernel traps.
 __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long target, unsigned int* error_word,
@@ -104,17 +93,30 @@ struct PeerSync {
         if (is_partner(lane)) wait_flag(mine + lane, epoch, error_word(), timeout_ns);
         __syncwarp();
     }
-    // end of the block's work: signal every partner; block 0 then waits for every partner's kernel
+    // end of the kernel: the LAST block to finish (a local arrival counter) fences at system scope, tells every
+    // partner "rank me has finished exchange `epoch`" and waits for the same from all of them before it exits.
+    // (Measured alternative, dropped: every block signalling its partners itself with red.release.sys.add -- 592
+    // remote atomics on one address serialise at the partner's L2 and cost 7-13 us per exchange on 2 GPUs.)
     __device__ __forceinline__ void finish() const
     {
-        __syncthreads();                                              // the block's stores / peer loads are issued ...
+        __shared__ int s_last;
+        __syncthreads();                                              // the block's stores / peer loads are issued
+        if (threadIdx.x == 0) {
+            unsigned int* counter = reinterpret_cast<unsigned int*>(mine + 2 * OSSG_MAX_PEERS);
+            __threadfence();                                          // release this block's stores ...
+            s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+            if (s_last) {
+                __threadfence();                                      // ... and acquire everybody else's
+                atomicExch(counter, 0u);                              // ready for the next launch (stream-ordered)
+            }
+        }
+        __syncthreads();
         const int t = threadIdx.x;
-        if (t < 32) {
-            __threadfence_system();                                   // ... and performed, as far as any observer of the signal is concerned
+        if (s_last && t < 32) {
+            __threadfence_system();
             if (is_partner(t)) {
-                const unsigned long long n = blockIdx.x == 0 ? PEER_ARRIVALS - (gridDim.x - 1) : 1ull;
-                red_release_sys_add(static_cast<unsigned long long*>(peer[t]) + OSSG_MAX_PEERS + me, n);
-                if (blockIdx.x == 0) wait_flag(mine + OSSG_MAX_PEERS + t, epoch * PEER_ARRIVALS, error_word(), timeout_ns);
+                st_release_sys(static_cast<unsigned long long*>(peer[t]) + OSSG_MAX_PEERS + me, epoch);
+                wait_flag(mine + OSSG_MAX_PEERS + t, epoch, error_word(), timeout_ns);
             }
         }
     }
