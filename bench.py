@@ -245,7 +245,7 @@ class Ctx:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
-        pin_to_gpu_numa_node(self.local_rank)
+        self.numa_node = pin_to_gpu_numa_node(self.local_rank)
         if self.world > 1:
             # NCCL prints its version banner on stdout when the first communicator is created; stdout must
             # carry the one JSON line only, so fd 1 points at stderr until that has happened
@@ -640,6 +640,7 @@ def run_own(args):
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
                 "what": "ossg_tripolar_build + ONE copy of the contiguous 20-array block to a pinned host buffer on the GPU's NUMA node "
                         "(TripolarGrid(CPU()) equivalent)",
+                "numa_node_of_rank0": ctx.numa_node, "host_cpus_of_rank0": len(os.sched_getaffinity(0)),
                 "public_constructor_wall_ms": public_ms,
                 "public_constructor_what": "wall clock of ossg.TripolarGrid(GPU(), size=...) per call, allocation of the 20 arrays and "
                                            "the workspace included, device synchronised"},

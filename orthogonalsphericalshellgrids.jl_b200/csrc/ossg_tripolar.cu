@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 #include "ossg_common.cuh"
 #include "ossg_tripolar_core.cuh"
@@ -80,6 +81,9 @@ __host__ __device__ inline TableKeys table_keys(const GridDims& g, int flags, do
 __global__ void __launch_bounds__(128) tables_kernel(GridDims g, int flags, double south, double north_poles_latitude,
                                                      double radius, double* __restrict__ base, unsigned long long* stamp)
 {
+    // programmatic dependent launch: the coordinate kernel behind this one may be scheduled right away; it
+    // waits (cudaGridDependencySynchronize) for this grid to finish before it reads a table entry
+    cudaTriggerProgrammaticLaunchCompletion();
     const TableKeys key = table_keys(g, flags, south, north_poles_latitude, radius);
     bool xy_ok = true, ll_ok = true;
 #pragma unroll
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ Bui
 {
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
     const int jw = blockIdx.y;
+    cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
     if (iw >= a.w.wnx) return;
     const int I = a.w.I0 + iw, J = a.w.J0 + jw;
     const GridDims g = a.g;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
     if (threadIdx.x < 30) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
 #endif
     __syncthreads();
+    cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
     const int t = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
     const int Nx = g.Nx, Hx = g.Hx;
@@ -913,6 +919,21 @@ static int launch_tables(const BuildArgs& a, cudaStream_t s)
     return 0;
 }
 
+// Launch with programmatic stream serialisation: the kernel may start while its predecessor in the stream (the
+// table kernel, which triggers its dependents at once) is still running; it synchronises on that grid itself.
+// The table kernel is a stamp check in the steady state, so this removes one full kernel boundary per build.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename FT>
 static int launch_coords(const BuildArgs& a, cudaStream_t s)
 {
@@ -931,10 +952,10 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
         pg.magic_pair = ((1ull << 40) + pg.chunks_pair - 1) / pg.chunks_pair;     // (nb < 2^31 and chunks < 2^9 keep b * chunks below 2^40)
         pg.magic_full = ((1ull << 40) + pg.chunks_full - 1) / pg.chunks_full;
 #endif
-        coords_pair_kernel<FT><<<(unsigned)nb, block, 0, s>>>(a, pg);
+        OSSG_CUDA_TRY(launch_pdl(coords_pair_kernel<FT>, dim3((unsigned)nb), block, s, a, pg));
         OSSG_LAUNCH_CHECK("coords_pair_kernel");
     } else {
-        coords_kernel<FT><<<grid, block, 0, s>>>(a);
+        OSSG_CUDA_TRY(launch_pdl(coords_kernel<FT>, grid, block, s, a));
         OSSG_LAUNCH_CHECK("coords_kernel");
     }
     return 0;
