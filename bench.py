@@ -32,16 +32,17 @@ METRIC = "grid cells/s for coords+metrics (FP64)"
 UNIT = "cells/s"
 
 # FP64 pipe work per launch, counted by ncu on the 1/12 degree workload (SASS opcode mix of the
-# committed capture profiles/r01i_*_opcodes.md: DFMA + DMUL + DADD + DSETP thread-instructions):
-#   metrics_tile_kernel : 915.7 per tile cell (4320 x 2158 cells)
-#   coords_pair_kernel  : 194.9 per padded element (4328 x 2168 elements)
+# committed capture profiles/r02d_*_opcodes.md, taken at the round-2 kernels: DFMA + DMUL + DADD + DSETP
+# thread-instructions):
+#   metrics_tile_kernel : 915.7 per tile cell (4320 x 2158 cells)        266.76 M warp-instructions
+#   coords_pair_kernel  : 194.9 per padded element (4328 x 2168 elements)  57.16 M warp-instructions
 # and the DRAM traffic of one metrics_tile_kernel launch from the same capture
-# (dram__bytes_read.sum + dram__bytes_write.sum = 601.5 MB + 849.7 MB; algorithmic 1491.6 MB).
+# (dram__bytes_read.sum + dram__bytes_write.sum = 601.1 MB + 850.3 MB; algorithmic 1491.6 MB).
 # These are properties of the code, not of the timing; refresh them whenever the kernels change.
 FP64_INST_PER_CELL_TILE = 915.7
 FP64_INST_PER_ELEM_COORDS = 194.9
-NCU_TRAFFIC_TILE_BYTES = 601518592 + 849665280
-PROFILE_TAG = "r01i"
+NCU_TRAFFIC_TILE_BYTES = 601125888 + 850315264
+PROFILE_TAG = "r02d"
 
 
 def partition_for(n):

@@ -41,15 +41,15 @@ extern "C" const char* ossg_last_error(void) { return ossg::last_error_buffer();
 
 extern "C" int ossg_device_ok(void)
 {
-    int dev = -1;
+    int dev = -1, major = 0, minor = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return ossg::cuda_fail(e, "cudaGetDevice");
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) return ossg::cuda_fail(e, "cudaGetDeviceProperties");
-    if (prop.major != 10)
-        return ossg::set_error(-1, "device %d (%s) has compute capability %d.%d; this library is built for sm_100a only",
-                               dev, prop.name, prop.major, prop.minor);
+    // (two attribute queries, microseconds; cudaGetDeviceProperties takes milliseconds and sat in every constructor call)
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (e != cudaSuccess) return ossg::cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10)
+        return ossg::set_error(-1, "device %d has compute capability %d.%d; this library is built for sm_100a only", dev, major, minor);
     return 0;
 }
 #endif  // OSSG_TESTUTIL_BUILD
