@@ -200,6 +200,29 @@ def cpu_fill_rates():
         out[name] = {"ms": dt * 1e3, "algorithmic_bytes": b, "gbs": b / dt / 1e9}
     out.update({"cores": 1, "kind": "port",
                 "sample": f"{Nx}x{Ny}x{Nz} FP64 fields c,u,v,zeta (1/4 degree), CPU restatement of reference v0.2.1"})
+    # the same on the 1/12 degree horizontal size with the four fields filled concurrently (one host thread per field;
+    # the fill is a per-field loop in the reference too): a bounded sample of the levels, the whole fields are 8.1 GB each
+    import threading
+    Nx, Ny, Nz = WORKLOAD["Nx"], WORKLOAD["Ny"], 10
+    fields = [np.full((Nz + 2 * H, Ny + 2 * H, Nx + 2 * H), 0.5 + k) for k in range(len(specs))]
+    algo = sum(2 * H * Nx * Nz * 8 + (Nx * Nz * 8 if loc[1] == 0 else 0) for loc, _ in specs)
+    algo_full = algo + len(specs) * (Ny + 2 * H) * (Nz + 2 * H) * 2 * (2 * H) * 8
+    par = {}
+    for name, fn, b in (("zipper_batch4", o.zipper, algo), ("fill_halo_regions_batch4", o.fill_halo_regions, algo_full)):
+        def work(c, loc, sg):
+            fn(c, Nx, Ny, Nz, H, H, H, loc[0], loc[1], sg)
+        reps = 3
+        for it in range(reps + 1):
+            if it == 1:
+                t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(c, loc, sg)) for c, (loc, sg) in zip(fields, specs)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+        dt = (time.perf_counter() - t0) / reps
+        par[name] = {"ms": dt * 1e3, "algorithmic_bytes": b, "gbs": b / dt / 1e9}
+    par.update({"cores": len(specs), "kind": "port",
+                "sample": f"{Nx}x{Ny} (1/12 degree) x {Nz} of the 100 levels, FP64 fields c,u,v,zeta filled concurrently, one host thread per field"})
+    out["four_threads_twelfth_degree"] = par
     return out
 
 
@@ -307,14 +330,14 @@ def pin_to_gpu_numa_node(index):
     best effort, silent when sysfs does not say"""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-        if bus is None:
+        pr = torch.cuda.get_device_properties(index)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
             q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
                                capture_output=True, text=True, timeout=10).stdout.strip()
             bus = q[-12:].lower() if q else None
         if not bus:
-            return None
-        if isinstance(bus, int):
             return None
         node = int(open(f"/sys/bus/pci/devices/{str(bus).lower()}/numa_node").read())
         if node < 0:
