@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ Bui
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
     const int jw = blockIdx.y;
     cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
+    cudaTriggerProgrammaticLaunchCompletion();                // the tile kernel behind may take the slots this grid's tail frees
     if (iw >= a.w.wnx) return;
     const int I = a.w.I0 + iw, J = a.w.J0 + jw;
     const GridDims g = a.g;
@@ -233,13 +234,16 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
 #else
         const unsigned long long mp = 0, mf = 0;
 #endif
-        if (b < nb_pair) {
-            const int r = magic_div(b, pg.chunks_pair, mp);
+        // the rows outside 1..Ny-1 (halo rows of the fold and of the south: one general evaluation per element, the
+        // longest threads of the grid) take the FIRST blocks, so that they run next to the pair rows instead of after them
+        const int nb_full = (int)gridDim.x - nb_pair;
+        if (b >= nb_full) {
+            const int r = magic_div(b - nb_full, pg.chunks_pair, mp);
             jw = pg.jw_lo + r;
-            chunk = b - r * pg.chunks_pair;
+            chunk = (b - nb_full) - r * pg.chunks_pair;
         } else {
-            const int r = magic_div(b - nb_pair, pg.chunks_full, mf);
-            chunk = (b - nb_pair) - r * pg.chunks_full;
+            const int r = magic_div(b, pg.chunks_full, mf);
+            chunk = b - r * pg.chunks_full;
             jw = r < pg.jw_lo ? r : r + pg.n_pair_rows;
         }
     }
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
 #endif
     __syncthreads();
     cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
+    cudaTriggerProgrammaticLaunchCompletion();                // the tile kernel behind may take the slots this grid's tail frees
     const int t = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
     const int Nx = g.Nx, Hx = g.Hx;
@@ -283,7 +288,11 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
             // point that leaves the preconditions sets `bad`; the thread then redoes its four points
             // through the general functions and overwrites the speculative stores.
             bool bad = false;
+#if defined(OSSG_COORD_UNROLL)
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int k0 = 0; k0 < 4; k0 += OSSG_COORD_ILP) {
 #pragma unroll
                 for (int kk = 0; kk < OSSG_COORD_ILP; ++kk) {           // k = 0: FC, 1: FF, 2: CC, 3: CF
@@ -344,6 +353,9 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
 // repeat its trigonometry.
 #ifndef OSSG_USE_TMA
 #define OSSG_USE_TMA 0
+#endif
+#ifndef OSSG_FRAME_DEFAULT
+#define OSSG_FRAME_DEFAULT 2          /* measured best on the whole grid and on the slabs of 2..8 ranks (profiles/r02g_slabs.txt) */
 #endif
 #ifndef OSSG_TX
 #define OSSG_TX 32
@@ -423,11 +435,10 @@ struct TileSmem {
     double* lam;      // [4][PS]  lambda (degrees)
     double* phr;      // [4][PS]  phi (degrees) during staging, then deg2rad(phi)/2
     double* cosp;     // [4][PS]  cos(deg2rad(phi))
-    double* ux;       // [2][PS]  unit vectors: slot 0 = CC, slot 1 = FF
-    double* uy;
-    double* uz;
+    double2* uxy;     // [2][PS]  unit vectors, (x, y) as one 16-byte element (one LDS.128 / STS.128): slot 0 = CC, slot 1 = FF
+    double* uz;       // [2][PS]
     __device__ __forceinline__ explicit TileSmem(double* smem)
-        : lam(smem), phr(smem + 4 * PS), cosp(smem + 8 * PS), ux(smem + 12 * PS), uy(smem + 14 * PS), uz(smem + 16 * PS) {}
+        : lam(smem), phr(smem + 4 * PS), cosp(smem + 8 * PS), uxy(reinterpret_cast<double2*>(smem + 12 * PS)), uz(smem + 16 * PS) {}
 };
 
 // ---- stage the four coordinate patches: global -> shared, asynchronously (LDGSTS), no registers.
@@ -495,8 +506,7 @@ __device__ __forceinline__ void tile_point_stage(const TileSmem<TMA>& S, int tid
             Vec3 v = lat_lon_to_cartesian_spec(lat, lon, bad);
             if (bad) v = lat_lon_to_cartesian_ool(lat, lon);
             const int us = u < QPTS ? u : u - QPTS + PS;
-            S.ux[us] = v.x;
-            S.uy[us] = v.y;
+            S.uxy[us] = make_double2(v.x, v.y);
             S.uz[us] = v.z;
             const double phr = lat * D2R;
             S.phr[t] = 0.5 * phr;                     // the haversines want deg2rad(phi)/2
@@ -525,43 +535,45 @@ __device__ __forceinline__ void tile_point_stage(const TileSmem<TMA>& S, int tid
 // overwritten by the same thread.
 //   o        element offset of the cell in the window arrays
 //   shC/shF  TMA staging only: a patch whose first column is odd sits one column to the right in its box
+__device__ __forceinline__ Vec3 unit_vector(double2 xy, double z) { return Vec3{ xy.x, xy.y, z }; }
+
 template <typename FT, bool TMA>
 __device__ __forceinline__ void tile_cell_stage(const BuildArgs& a, const TileSmem<TMA>& S, int tx, int ty, size_t o, int shC, int shF)
 {
     constexpr int QX = TileGeom<TMA>::QX, PS = TileGeom<TMA>::PS;
     double* const s_lam = S.lam; double* const s_phr = S.phr; double* const s_cos = S.cosp;
-    double* const s_ux = S.ux; double* const s_uy = S.uy; double* const s_uz = S.uz;
+    const double2* const s_uxy = S.uxy; double* const s_uz = S.uz;
     const double R = a.radius;
     // patch index of this cell's own point per staggering (index = loc)
     const int own_cc = (ty + 1) * QX + tx + 1 + shC, own_fc = (ty + 1) * QX + tx + shF;
     const int own_cf = ty * QX + tx + 1 + shC, own_ff = ty * QX + tx + shF;
 
     const double R2 = 2 * R, RR = R * R;
-    bool bad = false;
+    SpecRange rg;
 #define PT(L, p) s_lam[(L) * PS + (p)], s_phr[(L) * PS + (p)], s_cos[(L) * PS + (p)]
     {
-        const double dx_fc = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - 1), R2, bad);        // utils.jl:14
-        const double dy_fc = haversine_spec(PT(FF, own_ff + QX), PT(FF, own_ff), R2, bad);       // :19
+        const double dx_fc = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - 1), R2, rg);        // utils.jl:14
+        const double dy_fc = haversine_spec(PT(FF, own_ff + QX), PT(FF, own_ff), R2, rg);       // :19
         store_metric<FT>(a, DX_FC, o, dx_fc);
         store_metric<FT>(a, DY_FC, o, dy_fc);
         store_metric<FT>(a, AZ_FC, o, dy_fc * dx_fc);                                            // :34
-        const double dy_cf = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - QX), R2, bad);       // :20
-        const double dx_cf = haversine_spec(PT(FF, own_ff + 1), PT(FF, own_ff), R2, bad);        // :15
+        const double dy_cf = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - QX), R2, rg);       // :20
+        const double dx_cf = haversine_spec(PT(FF, own_ff + 1), PT(FF, own_ff), R2, rg);        // :15
         store_metric<FT>(a, DY_CF, o, dy_cf);
         store_metric<FT>(a, DX_CF, o, dx_cf);
         store_metric<FT>(a, AZ_CF, o, dy_cf * dx_cf);                                            // :35
-        store_metric<FT>(a, DY_FF, o, haversine_spec(PT(FC, own_fc), PT(FC, own_fc - QX), R2, bad));   // :21
-        store_metric<FT>(a, DY_CC, o, haversine_spec(PT(CF, own_cf + QX), PT(CF, own_cf), R2, bad));   // :18
-        store_metric<FT>(a, DX_FF, o, haversine_spec(PT(CF, own_cf), PT(CF, own_cf - 1), R2, bad));    // :16
-        store_metric<FT>(a, DX_CC, o, haversine_spec(PT(FC, own_fc + 1), PT(FC, own_fc), R2, bad));    // :13
+        store_metric<FT>(a, DY_FF, o, haversine_spec(PT(FC, own_fc), PT(FC, own_fc - QX), R2, rg));   // :21
+        store_metric<FT>(a, DY_CC, o, haversine_spec(PT(CF, own_cf + QX), PT(CF, own_cf), R2, rg));   // :18
+        store_metric<FT>(a, DX_FF, o, haversine_spec(PT(CF, own_cf), PT(CF, own_cf - 1), R2, rg));    // :16
+        store_metric<FT>(a, DX_CC, o, haversine_spec(PT(FC, own_fc + 1), PT(FC, own_fc), R2, rg));    // :13
     }
-#define UV(q, p) Vec3{ s_ux[(q) * PS + (p)], s_uy[(q) * PS + (p)], s_uz[(q) * PS + (p)] }
+#define UV(q, p) unit_vector(s_uxy[(q) * PS + (p)], s_uz[(q) * PS + (p)])
     {   // az_ff from CC[i-1,j-1], CC[i,j-1], CC[i,j], CC[i-1,j] (:38-43); az_cc from FF[i,j], FF[i+1,j], FF[i+1,j+1], FF[i,j+1] (:23-28)
         const int b0 = own_cc - QX - 1, b1 = own_ff;
-        store_metric<FT>(a, AZ_FF, o, spherical_area_quadrilateral_spec(UV(0, b0), UV(0, b0 + 1), UV(0, b0 + QX + 1), UV(0, b0 + QX), bad) * RR);
-        store_metric<FT>(a, AZ_CC, o, spherical_area_quadrilateral_spec(UV(1, b1), UV(1, b1 + 1), UV(1, b1 + QX + 1), UV(1, b1 + QX), bad) * RR);
+        store_metric<FT>(a, AZ_FF, o, spherical_area_quadrilateral_spec(UV(0, b0), UV(0, b0 + 1), UV(0, b0 + QX + 1), UV(0, b0 + QX), rg) * RR);
+        store_metric<FT>(a, AZ_CC, o, spherical_area_quadrilateral_spec(UV(1, b1), UV(1, b1 + 1), UV(1, b1 + QX + 1), UV(1, b1 + QX), rg) * RR);
     }
-    if (!bad) return;
+    if (!rg.violated()) return;
 
     // ---- general path (rare): rolled, out-of-line functions
     //   it 0: dx_fc = hav(CC[i,j], CC[i-1,j])   dy_fc = hav(FF[i,j+1], FF[i,j])   az_fc = dy_fc * dx_fc
@@ -594,10 +606,123 @@ __device__ __forceinline__ void tile_cell_stage(const BuildArgs& a, const TileSm
 #undef UV
 }
 
-template <typename FT, bool TMA>
-__global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
-                                                             const __grid_constant__ TileMaps tm)
+// ------------------------------------------------------------------ K2f (frame)
+// Coordinate accessor of the frame kernel: read the window's coordinate arrays where the point lies
+// inside the window, otherwise evaluate the coordinate at its source from the tables (the two
+// give the same bits; the second is needed on the ring of a tile window, whose stencil leaves it).
+struct FrameAcc {
+    const double* const* c; Window w; Tables tb; GridDims g; double fpl;
+    __device__ void operator()(int loc, int I, int J, double& lam, double& phi) const
+    {
+        const int iw = I - w.I0, jw = J - w.J0;
+        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
+            const size_t o = (size_t)jw * w.wnx + iw;
+            lam = __ldg(c[loc] + o);
+            phi = __ldg(c[4 + loc] + o);
+        } else {
+            coord_at(tb, g, fpl, loc, I, J, lam, phi);
+        }
+    }
+};
+
+// frame = window minus fast rectangle, enumerated as four rectangles
+struct Frame {
+    int jlo, jhi, ilo, ihi;     // fast rectangle in WINDOW coordinates: [ilo, ihi) x [jlo, jhi)
+    long long n_south, n_north, n_west, n_east;
+};
+
+__host__ __device__ inline Frame make_frame(const Window& w, const FastRect& fr)
 {
+    Frame f;
+    if (fr.nx <= 0 || fr.ny <= 0) { f.ilo = f.ihi = 0; f.jlo = f.jhi = w.wny; }
+    else { f.ilo = fr.I0 - w.I0; f.ihi = f.ilo + fr.nx; f.jlo = fr.J0 - w.J0; f.jhi = f.jlo + fr.ny; }
+    f.n_south = (long long)f.jlo * w.wnx;
+    f.n_north = (long long)(w.wny - f.jhi) * w.wnx;
+    f.n_west = (long long)(f.jhi - f.jlo) * f.ilo;
+    f.n_east = (long long)(f.jhi - f.jlo) * (w.wnx - f.ihi);
+    return f;
+}
+
+// One thread per (frame element, metric), metric-major: a warp serves 32 consecutive elements of
+// ONE metric, evaluates it at its class's M2 source and stores it coalesced.  (The former
+// one-thread-per-element form evaluated up to four sources and twelve metrics in sequence: a 40 us
+// latency chain holding 128 registers next to the tile kernel.)  t = mtr * n + element.
+template <typename FT>
+__device__ __noinline__ void frame_element(const BuildArgs& a, const Frame& f, long long t)
+{
+    const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
+    const int mtr = (int)(t / n);
+    t -= (long long)mtr * n;
+    const Window w = a.w;
+    int iw, jw;
+    if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
+    else if ((t -= f.n_south) < f.n_north) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); jw += f.jhi; }
+    else if ((t -= f.n_north) < f.n_west) { jw = (int)(t / f.ilo); iw = (int)(t - (long long)jw * f.ilo); jw += f.jlo; }
+    else {
+        t -= f.n_west;
+        const int ne = w.wnx - f.ihi;
+        jw = (int)(t / ne); iw = (int)(t - (long long)jw * ne) + f.ihi; jw += f.jlo;
+    }
+    const GridDims g = a.g;
+    const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
+    const int I = w.I0 + iw, J = w.J0 + jw;
+    const int loc = metric_loc(mtr);
+    double v;
+    if (J <= 1) {                                            // M3: lat-lon continuation rows
+        const double* row = tb.ll + (size_t)(J + g.Hy - 1) * LL_NCOL;
+        const int col = mtr == DX_CC ? LL_DX_CC : mtr == DX_FC ? LL_DX_FC : mtr == DX_CF ? LL_DX_CF : mtr == DX_FF ? LL_DX_FF
+                      : mtr == AZ_CC ? LL_AZ_CC : mtr == AZ_FC ? LL_AZ_FC : mtr == AZ_CF ? LL_AZ_CF : mtr == AZ_FF ? LL_AZ_FF : LL_DY;
+        v = row[col];
+    } else {                                                 // M1 at the class's M2 source
+        int si, sj; bool wrapped;
+        halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, si, sj, wrapped);
+        const FrameAcc acc{ a.coords64, w, tb, g, a.first_pole_longitude };
+        v = metric_one(acc, mtr, si, sj, a.radius);
+    }
+    static_cast<FT*>(a.metrics_out[mtr])[(size_t)jw * w.wnx + iw] = (FT)v;
+}
+
+// The frame on its own grid (see launch_metrics for when).
+template <typename FT>
+__global__ void __launch_bounds__(128) metrics_frame_kernel(const __grid_constant__ BuildArgs a, const Frame f, const int sync_first)
+{
+    // sync_first = 0 (launched with programmatic serialisation behind the TILE kernel, every block of which has waited
+    // for the coordinates before it let this grid go): compute at once, next to the tile kernel's last wave, and wait for
+    // that grid LAST -- this grid must not complete before it, the stream's next operation depends on both.
+    if (sync_first) cudaGridDependencySynchronize();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < N_METRIC * (f.n_south + f.n_north + f.n_west + f.n_east)) frame_element<FT>(a, f, t);
+    cudaGridDependencySynchronize();
+}
+
+// RIDE: the halo frame (M2/M3, 0.55 % of the elements, one long latency chain per element) rides in this grid:
+// block columns >= `tile_cols` of the first `frame.rows` block rows are frame blocks, so they are scheduled
+// interleaved with the tile blocks (their latency hides behind the tiles' arithmetic, as on a second stream) at the
+// cost of neither a launch nor an event pair.  RIDE = false: the frame runs on its own grid (launch_metrics).
+struct FrameRide { Frame frame; int tile_cols, cols, rows; };
+
+template <typename FT, bool TMA, bool RIDE>
+__global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __grid_constant__ BuildArgs a, const FastRect fr,
+                                                             const __grid_constant__ TileMaps tm, const __grid_constant__ FrameRide ride)
+{
+    // Launched with programmatic stream serialisation behind the coordinate kernel: the block may be resident while
+    // that grid drains, and waits here for its completion (and flush) before it reads a coordinate.  Once every block
+    // has passed this point a frame kernel launched behind this grid may start (it needs the coordinates only).
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if constexpr (RIDE) {
+        if ((int)blockIdx.x >= ride.tile_cols) {
+            if ((int)blockIdx.y < ride.rows) {
+                const long long t = ((long long)blockIdx.y * ride.cols + ((int)blockIdx.x - ride.tile_cols)) * NT + threadIdx.y * TX + threadIdx.x;
+                const Frame& f = ride.frame;
+                if (t < N_METRIC * (f.n_south + f.n_north + f.n_west + f.n_east)) frame_element<FT>(a, f, t);
+            }
+            return;
+        }
+    }
+    // block rows from the north: the rows next to the poles (cells that leave the speculative path) are the slowest
+    // tiles, scheduled first they run next to ordinary tiles instead of forming the grid's tail
+    const int by = (int)(gridDim.y - 1 - blockIdx.y);
     constexpr int QPTS = TileGeom<TMA>::QPTS, PS = TileGeom<TMA>::PS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(TMA ? (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127
@@ -605,7 +730,7 @@ __global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __gri
     const TileSmem<TMA> S(smem);
 
     const int tid = threadIdx.y * TX + threadIdx.x;
-    const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + blockIdx.y * TY;   // global index of tile cell (0,0)
+    const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + by * TY;   // global index of tile cell (0,0)
     const Window w = a.w;
 
     if constexpr (TMA) {
@@ -636,7 +761,7 @@ __global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __gri
     tile_point_stage<TMA>(S, tid);
     __syncthreads();
 
-    const int ci = blockIdx.x * TX + threadIdx.x, cj = blockIdx.y * TY + threadIdx.y;
+    const int ci = blockIdx.x * TX + threadIdx.x, cj = by * TY + threadIdx.y;
     if (ci >= fr.nx || cj >= fr.ny) return;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
@@ -699,7 +824,7 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
         const unsigned other = (unsigned)(member ^ 1);
         double* const r_phr = cluster.map_shared_rank(S.phr, other);
         double* const r_cos = cluster.map_shared_rank(S.cosp, other);
-        double* const r_ux = cluster.map_shared_rank(S.ux, other);
+        double2* const r_uxy = cluster.map_shared_rank(S.uxy, other);
         double* const r_uz = cluster.map_shared_rank(S.uz, other);
         int* const r_flag = cluster.map_shared_rank(&s_flag, other);
         // task u -> patch point: x-Center patch first (nC columns per row), then the x-Face patch
@@ -727,12 +852,12 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
                 m::sincosd_lat_spec(lat, sn, cs, bad);
                 const double cphi = m::cos_rad_inl(lat * D2R);
                 S.uz[us] = sn;
-                S.ux[us] = cs;                                // (cosd(phi) until the longitude part multiplies it)
+                S.uxy[us].x = cs;                             // (cosd(phi) until the longitude part multiplies it)
                 S.cosp[t] = cphi;
                 if (bad) s_flag = 1;
                 if (shared) {
                     const int tr = (face ? FF : CC) * PS + idxr, ur = (face ? PS : 0) + idxr;
-                    if (!bad && f64_bits(r_phr[tr]) == f64_bits(lat)) { r_uz[ur] = sn; r_ux[ur] = cs; r_cos[tr] = cphi; }
+                    if (!bad && f64_bits(r_phr[tr]) == f64_bits(lat)) { r_uz[ur] = sn; r_uxy[ur].x = cs; r_cos[tr] = cphi; }
                     else *r_flag = 1;
                 }
             }
@@ -768,9 +893,8 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
         bool bad = false;
         double sl, cl;
         m::sincosd_lon_spec(S.lam[t], sl, cl, bad);
-        const double cs = S.ux[us];
-        S.ux[us] = cl * cs;
-        S.uy[us] = sl * cs;
+        const double cs = S.uxy[us].x;
+        S.uxy[us] = make_double2(cl * cs, sl * cs);
         S.phr[t] = 0.5 * (S.phr[t] * D2R);                    // the haversines want deg2rad(phi)/2
         S.phr[t2] = 0.5 * (S.phr[t2] * D2R);
         if (bad) s_flag = 1;
@@ -787,84 +911,6 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
     if (tx >= nt || blockIdx.y * TY + ty >= fr.ny) return;
     const size_t o = (size_t)(Jt0 + ty - w.J0) * w.wnx + (It0 + tx - w.I0);
     tile_cell_stage<FT, false>(a, S, tx, ty, o, 0, 0);
-}
-
-// ------------------------------------------------------------------ K2f (frame)
-// Coordinate accessor of the frame kernel: read the window's coordinate arrays where the point lies
-// inside the window, otherwise evaluate the coordinate at its source from the tables (the two
-// give the same bits; the second is needed on the ring of a tile window, whose stencil leaves it).
-struct FrameAcc {
-    const double* const* c; Window w; Tables tb; GridDims g; double fpl;
-    __device__ void operator()(int loc, int I, int J, double& lam, double& phi) const
-    {
-        const int iw = I - w.I0, jw = J - w.J0;
-        if (iw >= 0 && iw < w.wnx && jw >= 0 && jw < w.wny) {
-            const size_t o = (size_t)jw * w.wnx + iw;
-            lam = __ldg(c[loc] + o);
-            phi = __ldg(c[4 + loc] + o);
-        } else {
-            coord_at(tb, g, fpl, loc, I, J, lam, phi);
-        }
-    }
-};
-
-// frame = window minus fast rectangle, enumerated as four rectangles
-struct Frame {
-    int jlo, jhi, ilo, ihi;     // fast rectangle in WINDOW coordinates: [ilo, ihi) x [jlo, jhi)
-    long long n_south, n_north, n_west, n_east;
-};
-
-__host__ __device__ inline Frame make_frame(const Window& w, const FastRect& fr)
-{
-    Frame f;
-    if (fr.nx <= 0 || fr.ny <= 0) { f.ilo = f.ihi = 0; f.jlo = f.jhi = w.wny; }
-    else { f.ilo = fr.I0 - w.I0; f.ihi = f.ilo + fr.nx; f.jlo = fr.J0 - w.J0; f.jhi = f.jlo + fr.ny; }
-    f.n_south = (long long)f.jlo * w.wnx;
-    f.n_north = (long long)(w.wny - f.jhi) * w.wnx;
-    f.n_west = (long long)(f.jhi - f.jlo) * f.ilo;
-    f.n_east = (long long)(f.jhi - f.jlo) * (w.wnx - f.ihi);
-    return f;
-}
-
-// One thread per (frame element, metric), metric-major: a warp serves 32 consecutive elements of
-// ONE metric, evaluates it at its class's M2 source and stores it coalesced.  (The former
-// one-thread-per-element form evaluated up to four sources and twelve metrics in sequence: a 40 us
-// latency chain holding 128 registers next to the tile kernel.)
-template <typename FT>
-__global__ void __launch_bounds__(128) metrics_frame_kernel(BuildArgs a, Frame f)
-{
-    const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N_METRIC * n) return;
-    const int mtr = (int)(t / n);
-    t -= (long long)mtr * n;
-    const Window w = a.w;
-    int iw, jw;
-    if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
-    else if ((t -= f.n_south) < f.n_north) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); jw += f.jhi; }
-    else if ((t -= f.n_north) < f.n_west) { jw = (int)(t / f.ilo); iw = (int)(t - (long long)jw * f.ilo); jw += f.jlo; }
-    else {
-        t -= f.n_west;
-        const int ne = w.wnx - f.ihi;
-        jw = (int)(t / ne); iw = (int)(t - (long long)jw * ne) + f.ihi; jw += f.jlo;
-    }
-    const GridDims g = a.g;
-    const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
-    const int I = w.I0 + iw, J = w.J0 + jw;
-    const int loc = metric_loc(mtr);
-    double v;
-    if (J <= 1) {                                            // M3: lat-lon continuation rows
-        const double* row = tb.ll + (size_t)(J + g.Hy - 1) * LL_NCOL;
-        const int col = mtr == DX_CC ? LL_DX_CC : mtr == DX_FC ? LL_DX_FC : mtr == DX_CF ? LL_DX_CF : mtr == DX_FF ? LL_DX_FF
-                      : mtr == AZ_CC ? LL_AZ_CC : mtr == AZ_FC ? LL_AZ_FC : mtr == AZ_CF ? LL_AZ_CF : mtr == AZ_FF ? LL_AZ_FF : LL_DY;
-        v = row[col];
-    } else {                                                 // M1 at the class's M2 source
-        int si, sj; bool wrapped;
-        halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, si, sj, wrapped);
-        const FrameAcc acc{ a.coords64, w, tb, g, a.first_pole_longitude };
-        v = metric_one(acc, mtr, si, sj, a.radius);
-    }
-    static_cast<FT*>(a.metrics_out[mtr])[(size_t)jw * w.wnx + iw] = (FT)v;
 }
 
 // ------------------------------------------------------------------ host side
@@ -923,15 +969,20 @@ static int launch_tables(const BuildArgs& a, cudaStream_t s)
 // table kernel, which triggers its dependents at once) is still running; it synchronises on that grid itself.
 // The table kernel is a stamp check in the steady state, so this removes one full kernel boundary per build.
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args)
+static cudaError_t launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, bool programmatic, cudaStream_t s, Args&&... args)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = programmatic ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args)
+{
+    return launch_pdl_smem(kernel, grid, block, 0, true, s, std::forward<Args>(args)...);
 }
 
 template <typename FT>
@@ -988,10 +1039,10 @@ static int fork_join(ForkJoin** out)                       // call with g_fork_m
 }
 
 // the tile kernels ask for more than 48 KB of dynamic shared memory: opt in once per device
-static int tile_attributes(int which /*0: double, 1: float*/, int kernel /*0: cp.async, 1: TMA, 2: pairs*/, const void* fn, size_t bytes)
+static int tile_attributes(int which /*0: double, 1: float*/, int kernel /*0: cp.async, 1: TMA, 2: pairs, 3: cp.async + frame*/, const void* fn, size_t bytes)
 {
     static std::mutex mu;
-    static unsigned long long done[2][3] = {};
+    static unsigned long long done[2][4] = {};
     int dev = 0;
     OSSG_CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
@@ -1013,6 +1064,23 @@ static int tile_form()
         return 0;
     }();
     return form;
+}
+
+// Where the halo frame runs, from the environment once per process (OSSG_FRAME = fork | tail | ride):
+//   0 fork  its own grid on a side stream next to the tile kernel (event pair around it)
+//   1 tail  its own grid behind the tile kernel with programmatic serialisation: it starts when the tile kernel's last
+//           wave is resident and fills the slots that wave leaves
+//   2 ride  inside the tile kernel's grid (extra block columns, metrics_tile_kernel<.., RIDE = true>)
+static int frame_mode()
+{
+    static const int mode = [] {
+        const char* e = getenv("OSSG_FRAME");
+        if (e && strcmp(e, "fork") == 0) return 0;
+        if (e && strcmp(e, "tail") == 0) return 1;
+        if (e && strcmp(e, "ride") == 0) return 2;
+        return OSSG_FRAME_DEFAULT;
+    }();
+    return mode;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -1069,18 +1137,27 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
     const Frame f = make_frame(w, fr);
     const long long nframe = f.n_south + f.n_north + f.n_west + f.n_east;
 
-    // frame kernel: forked onto the side stream when there is a tile kernel to overlap with (the
-    // profiled build keeps the two in sequence so that their times can be told apart)
-    const bool fork = have_tile && nframe > 0 && !between;
+    // table kernel -> coordinate kernel -> tile kernel, each launched with programmatic stream serialisation behind the
+    // one it depends on; the frame as frame_mode() says.  The profiled build records events between the kernels,
+    // which serialises them fully, and keeps the frame on its own grid behind the tile kernel so that the kernel
+    // times can be told apart.
+    const bool chain = !between;
+    const int form = tile_form();
+    const bool want_tma = form == 1;
+    const bool want_pairs = form == 2 && fr.I0 == 1 && fr.nx == a.g.Nx && a.g.Nx % 4 == 0;
+    int mode = (chain && have_tile && nframe > 0) ? frame_mode() : 1;
+    if (mode == 2 && (want_pairs || want_tma)) mode = 1;
+    if (mode == 1 && want_pairs) mode = 0;               // (the pair kernel does not trigger its dependents early)
+    const long long nfb128 = ceil_div((long long)N_METRIC * nframe, 128);
     std::unique_lock<std::mutex> fork_lock(g_fork_mu, std::defer_lock);
     ForkJoin* fj = nullptr;
-    if (fork) {
+    if (mode == 0) {
         fork_lock.lock();
         int rc = fork_join(&fj);
         if (rc) return rc;
         OSSG_CUDA_TRY(cudaEventRecord(fj->fork, s));
         OSSG_CUDA_TRY(cudaStreamWaitEvent(fj->side, fj->fork, 0));
-        metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, fj->side>>>(a, f);
+        metrics_frame_kernel<FT><<<(unsigned)nfb128, 128, 0, fj->side>>>(a, f, 1);
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
         OSSG_CUDA_TRY(cudaEventRecord(fj->join, fj->side));
     }
@@ -1088,15 +1165,14 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
         const int which = sizeof(FT) == 4;
         dim3 block(TX, TY), grid(ceil_div(fr.nx, TX), ceil_div(fr.ny, TY));
         TileMaps tm;
+        FrameRide ride;
+        memset(&ride, 0, sizeof(ride));
         // Staging of the coordinate patches: cp.async by default.  The TMA form (eight 2-D box loads
         // issued by one thread) is complete and parity-tested but measured 3 % slower on the 1/12
         // degree grid (0.650 vs 0.631 ms: 3 % more patch points because of the 16-byte box
         // alignment, and the patch arrives later than 256 threads' own loads); the mirror-pair
         // variant (clusters of two CTAs sharing the latitude part of the point stage) measured 17 %
         // slower (0.724 vs 0.621 ms).  Both stay opt-in, see tile_form().
-        const int form = tile_form();
-        const bool want_tma = form == 1;
-        const bool want_pairs = form == 2 && fr.I0 == 1 && fr.nx == a.g.Nx && a.g.Nx % 4 == 0;
         int rc = 0;
         if (want_pairs) {
             if ((rc = tile_attributes(which, 2, (const void*)metrics_tile_pair_kernel<FT>, TileGeom<false>::SMEM_BYTES))) return rc;
@@ -1104,20 +1180,33 @@ static int launch_metrics(const BuildArgs& a, bool whole_grid, cudaStream_t s, c
             dim3 pgrid(4 * nts, ceil_div(fr.ny, TY));            // 2 quarters of A tiles x nts pairs x 2 members
             metrics_tile_pair_kernel<FT><<<pgrid, block, TileGeom<false>::SMEM_BYTES, s>>>(a, fr);
         } else if (want_tma && make_tile_maps(a, tm)) {
-            if ((rc = tile_attributes(which, 1, (const void*)metrics_tile_kernel<FT, true>, TileGeom<true>::SMEM_BYTES))) return rc;
-            metrics_tile_kernel<FT, true><<<grid, block, TileGeom<true>::SMEM_BYTES, s>>>(a, fr, tm);
-        } else {
-            if ((rc = tile_attributes(which, 0, (const void*)metrics_tile_kernel<FT, false>, TileGeom<false>::SMEM_BYTES))) return rc;
+            if ((rc = tile_attributes(which, 1, (const void*)metrics_tile_kernel<FT, true, false>, TileGeom<true>::SMEM_BYTES))) return rc;
+            OSSG_CUDA_TRY(launch_pdl_smem(metrics_tile_kernel<FT, true, false>, grid, block, TileGeom<true>::SMEM_BYTES, chain, s, a, fr, tm, ride));
+        } else if (mode == 2) {
+            // frame blocks in the first 3/4 of the block rows only: a frame block is one ~25 us latency chain, in the
+            // last rows it would outlast the tile blocks next to it
+            const long long nfb = ceil_div((long long)N_METRIC * nframe, (long long)NT);
+            ride.frame = f;
+            ride.tile_cols = (int)grid.x;
+            ride.rows = max(1, (int)(grid.y * 3 / 4));
+            ride.cols = (int)ceil_div(nfb, (long long)ride.rows);
+            grid.x += ride.cols;
+            if ((rc = tile_attributes(which, 3, (const void*)metrics_tile_kernel<FT, false, true>, TileGeom<false>::SMEM_BYTES))) return rc;
             memset(&tm, 0, sizeof(tm));
-            metrics_tile_kernel<FT, false><<<grid, block, TileGeom<false>::SMEM_BYTES, s>>>(a, fr, tm);
+            OSSG_CUDA_TRY(launch_pdl_smem(metrics_tile_kernel<FT, false, true>, grid, block, TileGeom<false>::SMEM_BYTES, chain, s, a, fr, tm, ride));
+        } else {
+            if ((rc = tile_attributes(which, 0, (const void*)metrics_tile_kernel<FT, false, false>, TileGeom<false>::SMEM_BYTES))) return rc;
+            memset(&tm, 0, sizeof(tm));
+            OSSG_CUDA_TRY(launch_pdl_smem(metrics_tile_kernel<FT, false, false>, grid, block, TileGeom<false>::SMEM_BYTES, chain, s, a, fr, tm, ride));
         }
         OSSG_LAUNCH_CHECK("metrics_tile_kernel");
     }
     if (between) OSSG_CUDA_TRY(cudaEventRecord(between, s));
-    if (fork) {
+    if (mode == 0) {
         OSSG_CUDA_TRY(cudaStreamWaitEvent(s, fj->join, 0));
-    } else if (nframe > 0) {
-        metrics_frame_kernel<FT><<<ceil_div((long long)N_METRIC * nframe, 128), 128, 0, s>>>(a, f);
+    } else if (mode == 1 && nframe > 0) {
+        // behind the tile kernel (which lets it go early) the wait comes last; behind the coordinate kernel itself first
+        OSSG_CUDA_TRY(launch_pdl_smem(metrics_frame_kernel<FT>, dim3((unsigned)nfb128), dim3(128), 0, chain, s, a, f, have_tile && !want_pairs ? 0 : 1));
         OSSG_LAUNCH_CHECK("metrics_frame_kernel");
     }
     return 0;

@@ -294,18 +294,69 @@ OSSG_HD double haversine_hot(double lam_x, double hphi1, double c1, double lam_y
     return haversine_tail_ool(hdphi, hdlam, c1, c2, radius);
 }
 
+// Preconditions of the speculative forms below, accumulated over a whole cell.  An FP64 comparison costs the issue
+// slot twice (half-rate pipe), so the range tests run on the HIGH WORDS with integer max / min (one VIMNMX3 per two
+// values) and are judged once per cell:
+//   squares z of the haversine half-differences: unsigned max; z < 2^-12  <=>  hi(z) < 0x3F300000 for z >= 0, which
+//     implies |x| < 2^-6 = HAV_HOT (|x| >= 2^-6 squares to at least 2^-12 exactly); a NaN or infinite z has a high
+//     word of at least 0x7FF00000 under either sign;
+//   haversine radicands a: signed min; a >= 2^-970 (sqrt_nb), a negative radicand has a negative high word;
+//   triangle numerators n = |.| : unsigned min (div_nb); tangents t: unsigned max, hi(t) < hi(ATAN_SHORT) implies
+//     0 <= t < ATAN_SHORT, a negative or NaN tangent (never a real cell) compares high and takes the general path.
+// -DOSSG_RANGE_FP_TESTS keeps the round-1 form (FP64 comparisons ORed into a flag).
+struct SpecRange {
+#if defined(OSSG_RANGE_FP_TESTS)
+    bool bad = false;
+    OSSG_HD void haversine(double hdphi, double hdlam, double, double, double a)
+    {
+        bad |= !((fabs(hdphi) < 0x1p-6) & (fabs(hdlam) < 0x1p-6)) | (m::hi_abs(a) < m::SQRT_NB_MIN_HI);
+    }
+    OSSG_HD void triangles(double n0, double n1, double n2, double n3, double t0, double t1, double t2, double t3)
+    {
+        bad |= (m::hi_abs(n0) < m::DIV_NB_MIN_HI) | (m::hi_abs(n1) < m::DIV_NB_MIN_HI) |
+               (m::hi_abs(n2) < m::DIV_NB_MIN_HI) | (m::hi_abs(n3) < m::DIV_NB_MIN_HI);
+        // (a tiny or non-finite denominator makes |t| huge or NaN and fails this test as well)
+        bad |= !((fabs(t0) < m::ATAN_SHORT) & (fabs(t1) < m::ATAN_SHORT) & (fabs(t2) < m::ATAN_SHORT) & (fabs(t3) < m::ATAN_SHORT));
+    }
+    OSSG_HD void flag(bool b) { bad |= b; }
+    OSSG_HD bool violated() const { return bad; }
+#else
+    unsigned zmax = 0u, tmax = 0u, nmin = 0xffffffffu;
+    int amin = 0x7fffffff;
+    OSSG_HD static unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
+    OSSG_HD static unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
+    OSSG_HD void haversine(double, double, double z1, double z2, double a)
+    {
+        zmax = umax(zmax, umax(m::hi_bits(z1), m::hi_bits(z2)));
+        const int ah = (int)m::hi_bits(a);
+        amin = ah < amin ? ah : amin;
+    }
+    OSSG_HD void triangles(double n0, double n1, double n2, double n3, double t0, double t1, double t2, double t3)
+    {
+        nmin = umin(umin(nmin, m::hi_bits(n0)), umin(m::hi_bits(n1), umin(m::hi_bits(n2), m::hi_bits(n3))));   // n = |.|: no sign bit
+        tmax = umax(umax(tmax, m::hi_bits(t0)), umax(m::hi_bits(t1), umax(m::hi_bits(t2), m::hi_bits(t3))));
+    }
+    OSSG_HD void flag(bool b) { zmax = b ? 0xffffffffu : zmax; }
+    OSSG_HD bool violated() const
+    {
+        return (zmax >= 0x3F300000u) | (amin < (int)m::SQRT_NB_MIN_HI) | (nmin < m::DIV_NB_MIN_HI) | (tmax >= ATAN_SHORT_HI);
+    }
+    static constexpr unsigned ATAN_SHORT_HI = 0x3F1A36E2u;     // high word of ATAN_SHORT = 1e-4 (0x3F1A36E2EB1C432D)
+#endif
+};
+
 // Speculative form for straight-line code: always evaluates the hot sequence (with the branch-free
-// sqrt) and ORs into `bad` whether its preconditions failed; the caller recomputes the cell through
-// the general functions when anything was bad.  Same bits as haversine_pre whenever !bad.
+// sqrt) and records in `rg` whether its preconditions failed; the caller recomputes the cell through
+// the general functions when anything was violated.  Same bits as haversine_pre otherwise.
 OSSG_HD double haversine_spec(double lam_x, double hphi1, double c1, double lam_y, double hphi2, double c2,
-                              double radius2, bool& bad)
+                              double radius2, SpecRange& rg)
 {
     const double hdphi = hphi2 - hphi1;
     const double hdlam = (lam_y - lam_x) * HALF_D2R;
     const double s1 = m::sin_small(hdphi);
     const double s2 = m::sin_small(hdlam);
     const double a = s1 * s1 + c1 * c2 * (s2 * s2);
-    bad |= !((fabs(hdphi) < HAV_HOT) & (fabs(hdlam) < HAV_HOT)) | (m::hi_abs(a) < m::SQRT_NB_MIN_HI);
+    rg.haversine(hdphi, hdlam, hdphi * hdphi, hdlam * hdlam, a);      // (the squares are sin_small's own z)
     return radius2 * m::asin_small(m::sqrt_nb(a));        // radius2 = 2 R: == 2 (R asin), doubling is exact
 }
 
@@ -382,7 +433,7 @@ OSSG_HD double spherical_area_quadrilateral_hot(const Vec3& a, const Vec3& b, co
 }
 
 // Speculative form (see haversine_spec): branch-free divisions and short atans.
-OSSG_HD double spherical_area_quadrilateral_spec(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d, bool& bad)
+OSSG_HD double spherical_area_quadrilateral_spec(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& d, SpecRange& rg)
 {
     const double ab = dot3(a, b), ac = dot3(a, c), ad = dot3(a, d);
     const double bc = dot3(b, c), bd = dot3(b, d), cd = dot3(c, d);
@@ -392,10 +443,7 @@ OSSG_HD double spherical_area_quadrilateral_spec(const Vec3& a, const Vec3& b, c
     const double t_abd = m::div_nb(n_abd, 1 + ab + bd + ad);
     const double t_acd = m::div_nb(n_acd, 1 + ac + cd + ad);
     const double t_bcd = m::div_nb(n_bcd, 1 + bc + cd + bd);
-    bad |= (m::hi_abs(n_abc) < m::DIV_NB_MIN_HI) | (m::hi_abs(n_abd) < m::DIV_NB_MIN_HI) |
-           (m::hi_abs(n_acd) < m::DIV_NB_MIN_HI) | (m::hi_abs(n_bcd) < m::DIV_NB_MIN_HI);
-    // (a tiny or non-finite denominator makes |t| huge or NaN and fails this test as well)
-    bad |= !((fabs(t_abc) < m::ATAN_SHORT) & (fabs(t_abd) < m::ATAN_SHORT) & (fabs(t_acd) < m::ATAN_SHORT) & (fabs(t_bcd) < m::ATAN_SHORT));
+    rg.triangles(n_abc, n_abd, n_acd, n_bcd, t_abc, t_abd, t_acd, t_bcd);
     return m::atan_short(t_abc) + m::atan_short(t_abd) + m::atan_short(t_acd) + m::atan_short(t_bcd);
 }
 

@@ -2,23 +2,34 @@
 # Build one libossg_b200 per kernel experiment into build/variants/ (git-ignored, travels with gpurun);
 # `bash tools/gpu_variants.sh` on the GPU box then times each on the 1/12 degree construction and prints an
 # output checksum -- identical checksums = identical bits, so a faster variant can be adopted directly.
-#   base            the shipped configuration
-#   atanrng         -DOSSG_ATAN_RANGE_TABLE   coordinate kernel: atan range from a shared-memory byte table (hot loop 235 -> 223 instructions)
-#   magicdiv        -DOSSG_COORD_MAGIC_DIV    coordinate kernel: multiply-shift instead of the integer division of the block map
-#   coordx          both of the above
+#   cur             the shipped configuration (working tree, Makefile flags)
+#   head            the last commit's sources (git worktree), same flags: the baseline of the working tree's changes
+#   fprange         -DOSSG_RANGE_FP_TESTS     tile kernel: FP64 comparisons for the speculative range tests (round-1 form)
+#   lonsel          -DOSSG_LON_SPEC_SELECTS   tile kernel: select-chain form of sincosd_lon_spec (round-1 form)
+#   coordunr        -DOSSG_COORD_UNROLL       coordinate kernel: the four staggerings unrolled (compile-time locations)
 #   tile_TXxTY      -DOSSG_TX=.. -DOSSG_TY=.. other tile shapes of the metric kernel (measured in round 1: 32x8 stays)
 set -e
-cd "$(dirname "$0")/../orthogonalsphericalshellgrids.jl_b200/csrc"
-OUT=../../build/variants
+ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+OUT=$ROOT/build/variants
 mkdir -p $OUT
-build() { # name flags...
-  local name=$1; shift
-  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC "$@" -shared \
-       -o $OUT/libossg_$name.so ossg_api.cu ossg_tripolar.cu ossg_zipper.cu ossg_peer.cu ossg_nccl.cu -cudart shared -ldl
+rm -f $OUT/*.so
+BASE="-DOSSG_ATAN_RANGE_TABLE -DOSSG_COORD_MAGIC_DIV"
+build() { # srcdir name flags...
+  local src=$1 name=$2; shift 2
+  ( cd $src && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC $BASE "$@" -shared \
+       -o $OUT/libossg_$name.so ossg_api.cu ossg_tripolar.cu ossg_zipper.cu ossg_peer.cu ossg_nccl.cu -cudart shared -ldl )
   echo "built $name"
 }
-build base            # (the plain forms: no atan range table, integer division in the block map)
-build atanrng -DOSSG_ATAN_RANGE_TABLE
-build magicdiv -DOSSG_COORD_MAGIC_DIV
-build coordx -DOSSG_ATAN_RANGE_TABLE -DOSSG_COORD_MAGIC_DIV
-for shape in "$@"; do build tile_$shape -DOSSG_TX=${shape%x*} -DOSSG_TY=${shape#*x}; done
+CS=$ROOT/orthogonalsphericalshellgrids.jl_b200/csrc
+build $CS cur &
+build $CS fprange -DOSSG_RANGE_FP_TESTS &
+build $CS lonsel -DOSSG_LON_SPEC_SELECTS &
+build $CS coordunr -DOSSG_COORD_UNROLL &
+wait
+if [ "$1" == "--head" ]; then
+  shift
+  rm -rf /tmp/ossg_head && git -C $ROOT worktree prune && git -C $ROOT worktree add -f /tmp/ossg_head HEAD >/dev/null 2>&1
+  build /tmp/ossg_head/orthogonalsphericalshellgrids.jl_b200/csrc head
+  git -C $ROOT worktree remove --force /tmp/ossg_head
+fi
+for shape in "$@"; do build $CS tile_$shape -DOSSG_TX=${shape%x*} -DOSSG_TY=${shape#*x}; done
