@@ -187,11 +187,14 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ Bui
 }
 
 // ------------------------------------------------------------------ K1 (mirror pairs)
-// Used when the window spans the whole x extent (serial grids and Y-slab ranks).  In rows
-// 1..Ny-1 a thread evaluates the map once per staggering for pre-shift column ip = 1+u and
-// writes both ip and its mirror column (see tripolar_core): half the transcendental work of the
-// per-element kernel.  The x halos of those rows, row Ny (whose y-Center fields carry the fold
-// overwrite), the north halo and the south halo go through the per-element source map.
+// In rows 1..Ny-1 a thread evaluates the map once per staggering for pre-shift column ip = 1+t and
+// writes both ip and its mirror column (see tripolar_core) wherever they fall inside the window: half the
+// transcendental work of the per-element kernel for every window that holds its own mirror columns --
+// the whole x extent (serial grids, Y-slab ranks) and the halves of an Rx = 2 partition (post-shift
+// columns mirror as i <-> Nx/2+1-i resp. Nx/2+2-i, and the mirror of a half's east halo is its west halo).
+// Narrower windows run the same code with one stored image per evaluation.  Rows outside 1..Ny-1 (row Ny,
+// whose y-Center fields carry the fold overwrite, the north and the south halo) and, for full-x windows,
+// the x halos (second images of interior columns) go through the per-element source map.
 template <typename FT>
 __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t o, double lam, double phi)
 {
@@ -206,11 +209,16 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
 #ifndef OSSG_COORD_ILP
 #define OSSG_COORD_ILP 1
 #endif
+#ifndef OSSG_COORD_BLOCK
+#define OSSG_COORD_BLOCK 128      /* threads per block of coords_pair_kernel, 8 blocks per SM: 0.2086 -> 0.2022 ms against 256 x 4 (finer tail), profiles/r02k_tiles.txt */
+#endif
 // 1-D grid of coords_pair_kernel: the pair rows (J = 1..Ny-1) need Nx/2 + 1 + 2Hx threads, the other
 // rows one thread per padded element; a 2-D grid sized for the latter would launch an empty
 // second half for every pair row.
 struct PairGrid {
     int jw_lo, n_pair_rows, chunks_pair, chunks_full;
+    int t_lo, n_t;                 // pair threads of a row: t = t_lo .. t_lo + n_t - 1 (subset of 0 .. Nx/2)
+    int n_halo;                    // per-element x-halo threads of a row behind them (full-x windows: 2 Hx, else 0)
 #ifdef OSSG_COORD_MAGIC_DIV
     // ceil(2^40 / chunks) -- b / chunks == (b * magic) >> 40 for b * chunks < 2^40, three instructions instead of
     // the ~25 of an integer division in every block's prologue (default since round 2, see the Makefile)
@@ -223,8 +231,8 @@ __device__ __forceinline__ int magic_div(int b, int d, unsigned long long magic)
 __device__ __forceinline__ int magic_div(int b, int d, unsigned long long) { return b / d; }
 #endif
 
-template <typename FT>
-__global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
+template <typename FT, bool SPLIT /* window narrower than the x extent: images may fall outside */>
+__global__ void __launch_bounds__(OSSG_COORD_BLOCK, 1024 / OSSG_COORD_BLOCK) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
 {
     int jw, chunk;
     {
@@ -249,8 +257,10 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
     }
 #ifdef OSSG_ATAN_RANGE_TABLE
     __shared__ double s_atan[30 + 11];                       // atan reduction table + 88 bytes of range table (ossg_math.cuh)
-    if (threadIdx.x < 30) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
-    else if (threadIdx.x < 30 + 88) reinterpret_cast<unsigned char*>(s_atan + 30)[threadIdx.x - 30] = m::kATAN_RANGE[threadIdx.x - 30];
+    for (int e = threadIdx.x; e < 30 + 88; e += OSSG_COORD_BLOCK) {
+        if (e < 30) s_atan[e] = m::kATAN_LUT[e];
+        else reinterpret_cast<unsigned char*>(s_atan + 30)[e - 30] = m::kATAN_RANGE[e - 30];
+    }
 #else
     __shared__ double s_atan[30];                            // atan reduction table (ossg_math.cuh)
     if (threadIdx.x < 30) s_atan[threadIdx.x] = m::kATAN_LUT[threadIdx.x];
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
     __syncthreads();
     cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
     cudaTriggerProgrammaticLaunchCompletion();                // the tile kernel behind may take the slots this grid's tail frees
-    const int t = chunk * blockDim.x + threadIdx.x;
+    const int tt = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
     const int Nx = g.Nx, Hx = g.Hx;
     const int J = a.w.J0 + jw;
@@ -267,19 +277,35 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
     const double fpl = a.first_pole_longitude;
     if (J >= 1 && J < g.Ny) {
         const int half = Nx / 2;
-        if (t <= half) {
+        if (tt < pg.n_t) {
+            const int t = pg.t_lo + tt;
             const int ip = 1 + t;                               // pre-shift column of this pair
             const int shift = Nx / 4;
             int i = ip + shift; if (i > Nx) i -= Nx;            // its post-shift column
-            const double chF = __ldg(tb.chF + J - 1), shF = __ldg(tb.shF + J - 1);
-            const double chC = __ldg(tb.chC + J - 1), shC = __ldg(tb.shC + J - 1);
-            const size_t o = row + (size_t)(i + Hx - 1);
             // x-Face: ip <-> Nx+2-ip (ip = 1 and ip = Nx/2+1 are their own mirrors); x-Center: ip <-> Nx+1-ip
             const int ipmF = Nx + 2 - ip, ipmC = Nx + 1 - ip;
-            const bool mirrorF = (t != 0) && (t != half), pairC = t < half;
             int imF = ipmF + shift; if (imF > Nx) imF -= Nx;
             int imC = ipmC + shift; if (imC > Nx) imC -= Nx;
-            const size_t omF = row + (size_t)(imF + Hx - 1), omC = row + (size_t)(imC + Hx - 1);
+            // window column of global column c: the image c, c - Nx or c + Nx that lies inside the window, if any
+            // (a window no wider than Nx holds at most one; a full-x window holds the interior image, its x halos
+            // are served by the per-element threads below)
+            const int I0 = a.w.I0, wnx = a.w.wnx;
+            auto wcol = [&](int c, bool& inside) {
+                int wc = c - I0;
+                if (!SPLIT) { inside = true; return wc; }        // full-x window: c + Hx - 1, always inside
+                if (wc >= wnx) wc -= Nx;
+                if (wc < 0) wc += Nx;
+                inside = (unsigned)wc < (unsigned)wnx;
+                return wc;
+            };
+            bool in_i, in_mF, in_mC;
+            const size_t o = row + (size_t)wcol(i, in_i);
+            const size_t omF = row + (size_t)wcol(imF, in_mF), omC = row + (size_t)wcol(imC, in_mC);
+            const bool mirrorF = (t != 0) && (t != half) && in_mF, pairC = t < half;
+            const bool directC = pairC && in_i, mirrorC = pairC && in_mC;
+            if (SPLIT && !(in_i || mirrorF || mirrorC)) return; // (bounding thread range of a narrow window)
+            const double chF = __ldg(tb.chF + J - 1), shF = __ldg(tb.shF + J - 1);
+            const double chC = __ldg(tb.chC + J - 1), shC = __ldg(tb.shC + J - 1);
             const double asF = __ldg(tb.asF + i - 1), acF = __ldg(tb.acF + i - 1);
             const double asC = __ldg(tb.asC + i - 1), acC = __ldg(tb.acC + i - 1);
             const double fpl90 = fpl + 90.0;
@@ -300,8 +326,8 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
                     const bool fx = k < 2, fy = k & 1;
                     const PointCore c = tripolar_core_sl(fx ? asF : asC, fx ? acF : acC, fy ? chF : chC, fy ? shF : shC, s_atan, bad);
                     const int loc = fx ? (fy ? FF : FC) : (fy ? CF : CC);
-                    if (fx || pairC) store_coord<FT>(a, loc, o, tripolar_finish_sl(c.lam_a, ip <= half, fpl90, bad), c.phi);
-                    if (fx ? mirrorF : pairC)
+                    if (fx ? in_i : directC) store_coord<FT>(a, loc, o, tripolar_finish_sl(c.lam_a, ip <= half, fpl90, bad), c.phi);
+                    if (fx ? mirrorF : mirrorC)
                         store_coord<FT>(a, loc, fx ? omF : omC, tripolar_finish_sl(-c.lam_a, (fx ? ipmF : ipmC) <= half, fpl90, bad), c.phi);
                 }
             }
@@ -312,15 +338,15 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
                     if (!fx && !pairC) break;
                     const PointCore c = tripolar_core_lut(fx ? asF : asC, fx ? acF : acC, fy ? chF : chC, fy ? shF : shC, s_atan);
                     const int loc = fx ? (fy ? FF : FC) : (fy ? CF : CC);
-                    store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
-                    if (fx ? mirrorF : pairC)
+                    if (fx ? in_i : directC) store_coord<FT>(a, loc, o, tripolar_finish(c.lam_a, c.pole, ip == 1, ip <= half, fpl), c.phi);
+                    if (fx ? mirrorF : mirrorC)
                         store_coord<FT>(a, loc, fx ? omF : omC,
                                         tripolar_finish(-c.lam_a, c.pole, false, (fx ? ipmF : ipmC) <= half, fpl), c.phi);
                 }
             }
-        } else if (t <= half + 2 * Hx) {
-            // x halo element of this row: columns 1-Hx..0 and Nx+1..Nx+Hx
-            const int h = t - half - 1;                         // 0 .. 2Hx-1
+        } else if (tt < pg.n_t + pg.n_halo) {
+            // x halo element of this row (full-x windows): columns 1-Hx..0 and Nx+1..Nx+Hx
+            const int h = tt - pg.n_t;                          // 0 .. 2Hx-1
             const int I = h < Hx ? 1 - Hx + h : Nx + 1 + (h - Hx);
             const size_t o = row + (size_t)(I + Hx - 1);
 #pragma unroll 1
@@ -333,6 +359,7 @@ __global__ void __launch_bounds__(256, 4) coords_pair_kernel(const __grid_consta
         return;
     }
     // rows outside 1..Ny-1: one padded element per thread through the source map
+    const int t = tt;
     if (t >= a.w.wnx) return;
     const int I = a.w.I0 + t;
 #pragma unroll 1
@@ -990,20 +1017,41 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
 {
     dim3 block(256), grid(ceil_div(a.w.wnx, 256), a.w.wny);
     const bool full_x = a.w.I0 == 1 - a.g.Hx && a.w.wnx == a.g.Nx + 2 * a.g.Hx;
-    if (full_x && a.g.Hx <= a.g.Nx / 2) {       // (wnx >= Nx/2 + 1 + 2Hx threads per row are available)
-        PairGrid pg;
+    bool split_x = !full_x && a.w.wnx <= a.g.Nx;               // no column has two images inside the window
+    PairGrid pg;
+    memset(&pg, 0, sizeof(pg));
+    const int Nx = a.g.Nx, half = Nx / 2;
+    if (full_x) {
+        pg.t_lo = 0; pg.n_t = half + 1; pg.n_halo = 2 * a.g.Hx;
+    } else if (split_x) {
+        // bounding range of the pair threads with an image inside the window (kernel's own maps, on the host)
+        auto inside = [&](int c) { int wc = c - a.w.I0; if (wc >= a.w.wnx) wc -= Nx; if (wc < 0) wc += Nx; return wc >= 0 && wc < a.w.wnx; };
+        auto shifted = [&](int ip) { int i = ip + Nx / 4; return i > Nx ? i - Nx : i; };
+        int lo = half + 1, hi = -1;
+        for (int t = 0; t <= half; ++t) {
+            const int ip = 1 + t;
+            const bool any = inside(shifted(ip)) || (t != 0 && t != half && inside(shifted(Nx + 2 - ip))) || (t < half && inside(shifted(Nx + 1 - ip)));
+            if (any) { lo = min(lo, t); hi = max(hi, t); }
+        }
+        pg.t_lo = hi < 0 ? 0 : lo; pg.n_t = hi < 0 ? 0 : hi - lo + 1; pg.n_halo = 0;
+        // worth it only where evaluations are shared: with one stored image per evaluation (Rx >= 4) the
+        // per-element kernel measured 1-3 % faster (profiles/r02j_tiles.txt)
+        if (4 * pg.n_t > 3 * a.w.wnx) split_x = false;
+    }
+    if ((full_x && a.g.Hx <= a.g.Nx / 2) || split_x) {
         pg.jw_lo = max(0, 1 - a.w.J0);
         const int jw_hi = min(a.w.wny - 1, a.g.Ny - 1 - a.w.J0);
         pg.n_pair_rows = max(0, jw_hi - pg.jw_lo + 1);
         if (pg.n_pair_rows == 0) pg.jw_lo = 0;
-        pg.chunks_pair = ceil_div(a.g.Nx / 2 + 1 + 2 * a.g.Hx, 256);
-        pg.chunks_full = ceil_div(a.w.wnx, 256);
+        pg.chunks_pair = max(1, ceil_div(pg.n_t + pg.n_halo, OSSG_COORD_BLOCK));
+        pg.chunks_full = ceil_div(a.w.wnx, OSSG_COORD_BLOCK);
         const long long nb = (long long)pg.n_pair_rows * pg.chunks_pair + (long long)(a.w.wny - pg.n_pair_rows) * pg.chunks_full;
 #ifdef OSSG_COORD_MAGIC_DIV
         pg.magic_pair = ((1ull << 40) + pg.chunks_pair - 1) / pg.chunks_pair;     // (nb < 2^31 and chunks < 2^9 keep b * chunks below 2^40)
         pg.magic_full = ((1ull << 40) + pg.chunks_full - 1) / pg.chunks_full;
 #endif
-        OSSG_CUDA_TRY(launch_pdl(coords_pair_kernel<FT>, dim3((unsigned)nb), block, s, a, pg));
+        if (split_x) OSSG_CUDA_TRY(launch_pdl(coords_pair_kernel<FT, true>, dim3((unsigned)nb), dim3(OSSG_COORD_BLOCK), s, a, pg));
+        else OSSG_CUDA_TRY(launch_pdl(coords_pair_kernel<FT, false>, dim3((unsigned)nb), dim3(OSSG_COORD_BLOCK), s, a, pg));
         OSSG_LAUNCH_CHECK("coords_pair_kernel");
     } else {
         OSSG_CUDA_TRY(launch_pdl(coords_kernel<FT>, grid, block, s, a));

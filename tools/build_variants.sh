@@ -7,6 +7,8 @@
 #   fprange         -DOSSG_RANGE_FP_TESTS     tile kernel: FP64 comparisons for the speculative range tests (round-1 form)
 #   lonsel          -DOSSG_LON_SPEC_SELECTS   tile kernel: select-chain form of sincosd_lon_spec (round-1 form)
 #   coordunr        -DOSSG_COORD_UNROLL       coordinate kernel: the four staggerings unrolled (compile-time locations)
+#   cb256, cb64     -DOSSG_COORD_BLOCK=..     coordinate kernel: 256- / 64-thread blocks (default 128, 8 per SM)
+# (fprange, lonsel, coordunr only with --all)
 #   tile_TXxTY      -DOSSG_TX=.. -DOSSG_TY=.. other tile shapes of the metric kernel (measured in round 1: 32x8 stays)
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
@@ -22,9 +24,14 @@ build() { # srcdir name flags...
 }
 CS=$ROOT/orthogonalsphericalshellgrids.jl_b200/csrc
 build $CS cur &
-build $CS fprange -DOSSG_RANGE_FP_TESTS &
-build $CS lonsel -DOSSG_LON_SPEC_SELECTS &
-build $CS coordunr -DOSSG_COORD_UNROLL &
+if [ "$1" == "--all" ]; then
+  shift
+  build $CS fprange -DOSSG_RANGE_FP_TESTS &
+  build $CS lonsel -DOSSG_LON_SPEC_SELECTS &
+  build $CS coordunr -DOSSG_COORD_UNROLL &
+fi
+build $CS cb256 -DOSSG_COORD_BLOCK=256 &
+build $CS cb64 -DOSSG_COORD_BLOCK=64 &
 wait
 if [ "$1" == "--head" ]; then
   shift

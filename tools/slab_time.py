@@ -12,10 +12,14 @@ L = _lib.lib(); dev = torch.device('cuda', 0)
 Nx, Ny, H = 4320, 2160, 4
 s = torch.cuda.current_stream(dev)
 res = []
-for (Ry, r) in ((1, 0), (2, 1), (4, 3), (8, 0), (8, 3), (8, 7)):
+TILES = ((1, 1, 0, 0), (1, 2, 0, 1), (1, 4, 0, 3), (1, 8, 0, 0), (1, 8, 0, 3), (1, 8, 0, 7))
+if "--xsplit" in sys.argv:
+    TILES = ((2, 1, 0, 0), (2, 1, 1, 0), (4, 1, 1, 0), (8, 1, 3, 0), (2, 2, 1, 1), (2, 4, 0, 3), (4, 2, 2, 1))
+for (Rx, Ry, rx, r) in TILES:
     ny = Ny // Ry
-    p = make_params((Nx, Ny, 100), (H, H, H), -80.0, 55.0, 70.0, 6371.0e3, tile=(1, r * ny + 1, Nx, ny))
-    out = [torch.zeros((ny + 2 * H, Nx + 2 * H), dtype=torch.float64, device=dev) for _ in range(20)]
+    nx = Nx // Rx
+    p = make_params((Nx, Ny, 100), (H, H, H), -80.0, 55.0, 70.0, 6371.0e3, tile=(rx * nx + 1, r * ny + 1, nx, ny))
+    out = [torch.zeros((ny + 2 * H, nx + 2 * H), dtype=torch.float64, device=dev) for _ in range(20)]
     optr = _lib.ptr_array([t.data_ptr() for t in out])
     nb = L.ossg_tripolar_workspace_bytes(C.byref(p), _lib.OSSG_F64)
     ws = torch.zeros(max(nb, 128), dtype=torch.uint8, device=dev)
@@ -33,6 +37,6 @@ for (Ry, r) in ((1, 0), (2, 1), (4, 3), (8, 0), (8, 3), (8, 7)):
     chk = 0
     for t in out:
         chk ^= int(t.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
-    res.append('(1,%d)#%d %.4f %04x' % (Ry, r, best, chk & 0xffff))
+    res.append('(%d,%d)#%d,%d %.4f %04x' % (Rx, Ry, rx, r, best, chk & 0xffff))
     del out, ws
 print('%-22s frame=%-5s %s' % (os.path.basename(_lib.LIB_PATH), os.environ.get('OSSG_FRAME', 'dflt'), ' | '.join(res)), flush=True)
