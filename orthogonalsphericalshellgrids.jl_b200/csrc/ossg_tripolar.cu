@@ -456,12 +456,31 @@ __device__ __forceinline__ void store_metric(const BuildArgs& a, int id, size_t 
 
 // The three phases of the tile kernel as inline device functions (shared by metrics_tile_kernel and
 // the mirror-pair variant metrics_tile_pair_kernel below).
+#ifndef OSSG_PC_SOA
+#define OSSG_PC_SOA 1            /* 0: paired layout below; measured neutral (tile kernel -1.7 us, build +1.6 us, profiles/r02l_variants.txt) */
+#endif
+struct PatchPoint { double lam, hphi, cosphi; };           // what a haversine needs of one point
 template <bool TMA>
 struct TileSmem {
     static constexpr int PS = TileGeom<TMA>::PS;
+    // (deg2rad(phi)/2, cos(deg2rad(phi))) of a point as ONE 16-byte element: one LDS.128 per haversine operand instead
+    // of two LDS.64 (-DOSSG_PC_SOA=0; the default keeps two arrays).  Not with TMA staging (the box load writes phi densely).
+    static constexpr bool PAIRED = !TMA && !OSSG_PC_SOA;
     double* lam;      // [4][PS]  lambda (degrees)
-    double* phr;      // [4][PS]  phi (degrees) during staging, then deg2rad(phi)/2
+    double* phr;      // [4][PS]  phi (degrees) during staging, then deg2rad(phi)/2       (PAIRED: [4][PS][2] with cosp)
     double* cosp;     // [4][PS]  cos(deg2rad(phi))
+    __device__ __forceinline__ double& phi(int t) const { return PAIRED ? phr[2 * t] : phr[t]; }
+    __device__ __forceinline__ double& cosphi(int t) const { return PAIRED ? phr[2 * t + 1] : cosp[t]; }
+    __device__ __forceinline__ void set_point(int t, double hphi, double c) const
+    {
+        if (PAIRED) reinterpret_cast<double2*>(phr)[t] = make_double2(hphi, c);
+        else { phr[t] = hphi; cosp[t] = c; }
+    }
+    __device__ __forceinline__ PatchPoint point(int t) const
+    {
+        if (PAIRED) { const double2 q = reinterpret_cast<const double2*>(phr)[t]; return PatchPoint{ lam[t], q.x, q.y }; }
+        return PatchPoint{ lam[t], phr[t], cosp[t] };
+    }
     double2* uxy;     // [2][PS]  unit vectors, (x, y) as one 16-byte element (one LDS.128 / STS.128): slot 0 = CC, slot 1 = FF
     double* uz;       // [2][PS]
     __device__ __forceinline__ explicit TileSmem(double* smem)
@@ -489,10 +508,10 @@ __device__ __forceinline__ void tile_stage_points(const BuildArgs& a, const Wind
             if (!CHECK || (i2 >= 0 && i2 < w.wnx && j2 >= 0 && j2 < w.wny)) {
                 const long long o2 = o + (long long)dj * w.wnx + di;
                 cp_async_8(&S.lam[loc * PS + p], a.coords64[loc] + o2);
-                cp_async_8(&S.phr[loc * PS + p], a.coords64[4 + loc] + o2);
+                cp_async_8(&S.phi(loc * PS + p), a.coords64[4 + loc] + o2);
             } else {
                 S.lam[loc * PS + p] = 0.0;
-                S.phr[loc * PS + p] = 0.0;
+                S.phi(loc * PS + p) = 0.0;
             }
         }
     };
@@ -528,7 +547,7 @@ __device__ __forceinline__ void tile_point_stage(const TileSmem<TMA>& S, int tid
         const int u = h * 32 + lane;                  // index into the unit-vector arrays
         if (u < 2 * QPTS) {
             const int t = u < QPTS ? u : u - QPTS + 3 * PS;   // CC patch, then FF patch
-            const double lat = S.phr[t], lon = S.lam[t];
+            const double lat = S.phi(t), lon = S.lam[t];
             bool bad = false;
             Vec3 v = lat_lon_to_cartesian_spec(lat, lon, bad);
             if (bad) v = lat_lon_to_cartesian_ool(lat, lon);
@@ -536,8 +555,7 @@ __device__ __forceinline__ void tile_point_stage(const TileSmem<TMA>& S, int tid
             S.uxy[us] = make_double2(v.x, v.y);
             S.uz[us] = v.z;
             const double phr = lat * D2R;
-            S.phr[t] = 0.5 * phr;                     // the haversines want deg2rad(phi)/2
-            S.cosp[t] = m::cos_rad_inl(phr);
+            S.set_point(t, 0.5 * phr, m::cos_rad_inl(phr));   // the haversines want deg2rad(phi)/2
         }
     }
     if (W0 == 0 || warp >= W0) {
@@ -546,9 +564,8 @@ __device__ __forceinline__ void tile_point_stage(const TileSmem<TMA>& S, int tid
             const int v = l * 32 + lane;              // FC patch, then CF patch
             const int t = v < QPTS ? PS + v : 2 * PS + (v - QPTS);
             if (v < 2 * QPTS) {
-                const double phr = S.phr[t] * D2R;
-                S.phr[t] = 0.5 * phr;
-                S.cosp[t] = m::cos_rad_inl(phr);
+                const double phr = S.phi(t) * D2R;
+                S.set_point(t, 0.5 * phr, m::cos_rad_inl(phr));
             }
         }
     }
@@ -568,7 +585,6 @@ template <typename FT, bool TMA>
 __device__ __forceinline__ void tile_cell_stage(const BuildArgs& a, const TileSmem<TMA>& S, int tx, int ty, size_t o, int shC, int shF)
 {
     constexpr int QX = TileGeom<TMA>::QX, PS = TileGeom<TMA>::PS;
-    double* const s_lam = S.lam; double* const s_phr = S.phr; double* const s_cos = S.cosp;
     const double2* const s_uxy = S.uxy; double* const s_uz = S.uz;
     const double R = a.radius;
     // patch index of this cell's own point per staggering (index = loc)
@@ -577,7 +593,7 @@ __device__ __forceinline__ void tile_cell_stage(const BuildArgs& a, const TileSm
 
     const double R2 = 2 * R, RR = R * R;
     SpecRange rg;
-#define PT(L, p) s_lam[(L) * PS + (p)], s_phr[(L) * PS + (p)], s_cos[(L) * PS + (p)]
+#define PT(L, p) S.point((L) * PS + (p))
     {
         const double dx_fc = haversine_spec(PT(CC, own_cc), PT(CC, own_cc - 1), R2, rg);        // utils.jl:14
         const double dy_fc = haversine_spec(PT(FF, own_ff + QX), PT(FF, own_ff), R2, rg);       // :19
@@ -849,8 +865,9 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
         const int nC = hC + 1, nF = gF + 1;
         const int ntask = (nC + nF) * QY;                     // heavy tasks (CC, FF); as many light ones (CF, FC)
         const unsigned other = (unsigned)(member ^ 1);
-        double* const r_phr = cluster.map_shared_rank(S.phr, other);
-        double* const r_cos = cluster.map_shared_rank(S.cosp, other);
+        TileSmem<false> R = S;                                // the partner's arrays (same layout)
+        R.phr = cluster.map_shared_rank(S.phr, other);
+        R.cosp = cluster.map_shared_rank(S.cosp, other);
         double2* const r_uxy = cluster.map_shared_rank(S.uxy, other);
         double* const r_uz = cluster.map_shared_rank(S.uz, other);
         int* const r_flag = cluster.map_shared_rank(&s_flag, other);
@@ -873,18 +890,18 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
                 bool face, shared; int idx, idxr;
                 locate(u, face, idx, idxr, shared);
                 const int t = (face ? FF : CC) * PS + idx, us = (face ? PS : 0) + idx;
-                const double lat = S.phr[t];
+                const double lat = S.phi(t);
                 bool bad = false;
                 double sn, cs;
                 m::sincosd_lat_spec(lat, sn, cs, bad);
                 const double cphi = m::cos_rad_inl(lat * D2R);
                 S.uz[us] = sn;
                 S.uxy[us].x = cs;                             // (cosd(phi) until the longitude part multiplies it)
-                S.cosp[t] = cphi;
+                S.cosphi(t) = cphi;
                 if (bad) s_flag = 1;
                 if (shared) {
                     const int tr = (face ? FF : CC) * PS + idxr, ur = (face ? PS : 0) + idxr;
-                    if (!bad && f64_bits(r_phr[tr]) == f64_bits(lat)) { r_uz[ur] = sn; r_uxy[ur].x = cs; r_cos[tr] = cphi; }
+                    if (!bad && f64_bits(R.phi(tr)) == f64_bits(lat)) { r_uz[ur] = sn; r_uxy[ur].x = cs; R.cosphi(tr) = cphi; }
                     else *r_flag = 1;
                 }
             }
@@ -897,12 +914,12 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
                     bool face, shared; int idx, idxr;
                     locate(u, face, idx, idxr, shared);
                     const int t = (face ? FC : CF) * PS + idx;
-                    const double lat = S.phr[t];
+                    const double lat = S.phi(t);
                     const double cphi = m::cos_rad_inl(lat * D2R);
-                    S.cosp[t] = cphi;
+                    S.cosphi(t) = cphi;
                     if (shared) {
                         const int tr = (face ? FC : CF) * PS + idxr;
-                        if (f64_bits(r_phr[tr]) == f64_bits(lat)) r_cos[tr] = cphi;
+                        if (f64_bits(R.phi(tr)) == f64_bits(lat)) R.cosphi(tr) = cphi;
                         else *r_flag = 1;
                     }
                 }
@@ -922,8 +939,8 @@ metrics_tile_pair_kernel(const __grid_constant__ BuildArgs a, const FastRect fr)
         m::sincosd_lon_spec(S.lam[t], sl, cl, bad);
         const double cs = S.uxy[us].x;
         S.uxy[us] = make_double2(cl * cs, sl * cs);
-        S.phr[t] = 0.5 * (S.phr[t] * D2R);                    // the haversines want deg2rad(phi)/2
-        S.phr[t2] = 0.5 * (S.phr[t2] * D2R);
+        S.phi(t) = 0.5 * (S.phi(t) * D2R);                    // the haversines want deg2rad(phi)/2
+        S.phi(t2) = 0.5 * (S.phi(t2) * D2R);
         if (bad) s_flag = 1;
     }
     __syncthreads();

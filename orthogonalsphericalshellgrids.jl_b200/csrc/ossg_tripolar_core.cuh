@@ -359,6 +359,11 @@ OSSG_HD double haversine_spec(double lam_x, double hphi1, double c1, double lam_
     rg.haversine(hdphi, hdlam, hdphi * hdphi, hdlam * hdlam, a);      // (the squares are sin_small's own z)
     return radius2 * m::asin_small(m::sqrt_nb(a));        // radius2 = 2 R: == 2 (R asin), doubling is exact
 }
+template <class P>   // P: { lam, hphi, cosphi } of a staged patch point (csrc/ossg_tripolar.cu)
+OSSG_HD double haversine_spec(const P& x, const P& y, double radius2, SpecRange& rg)
+{
+    return haversine_spec(x.lam, x.hphi, x.cosphi, y.lam, y.hphi, y.cosphi, radius2, rg);
+}
 
 struct Vec3 { double x, y, z; };
 
@@ -453,6 +458,11 @@ OSSG_HD double spherical_area_quadrilateral_spec(const Vec3& a, const Vec3& b, c
 OSSG_HD_NOINLINE double haversine_pre_ool(double lam_x, double hphi1, double c1, double lam_y, double hphi2, double c2, double radius)
 {
     return haversine_pre(lam_x, hphi1, c1, lam_y, hphi2, c2, radius);
+}
+template <class P>
+OSSG_HD double haversine_pre_ool(const P& x, const P& y, double radius)
+{
+    return haversine_pre_ool(x.lam, x.hphi, x.cosphi, y.lam, y.hphi, y.cosphi, radius);
 }
 OSSG_HD_NOINLINE double cos_rad_ool(double x) { return m::cos_rad(x); }
 OSSG_HD_NOINLINE Vec3 lat_lon_to_cartesian_ool(double lat, double lon) { return lat_lon_to_cartesian(lat, lon); }

@@ -7,6 +7,7 @@
 #   fprange         -DOSSG_RANGE_FP_TESTS     tile kernel: FP64 comparisons for the speculative range tests (round-1 form)
 #   lonsel          -DOSSG_LON_SPEC_SELECTS   tile kernel: select-chain form of sincosd_lon_spec (round-1 form)
 #   coordunr        -DOSSG_COORD_UNROLL       coordinate kernel: the four staggerings unrolled (compile-time locations)
+#   pcpair          -DOSSG_PC_SOA=0           tile kernel: deg2rad(phi)/2 and cos(phi) of a patch point as one 16-byte shared element
 #   cb256, cb64     -DOSSG_COORD_BLOCK=..     coordinate kernel: 256- / 64-thread blocks (default 128, 8 per SM)
 # (fprange, lonsel, coordunr only with --all)
 #   tile_TXxTY      -DOSSG_TX=.. -DOSSG_TY=.. other tile shapes of the metric kernel (measured in round 1: 32x8 stays)
@@ -30,6 +31,7 @@ if [ "$1" == "--all" ]; then
   build $CS lonsel -DOSSG_LON_SPEC_SELECTS &
   build $CS coordunr -DOSSG_COORD_UNROLL &
 fi
+build $CS pcpair -DOSSG_PC_SOA=0 &
 build $CS cb256 -DOSSG_COORD_BLOCK=256 &
 build $CS cb64 -DOSSG_COORD_BLOCK=64 &
 wait
