@@ -43,7 +43,21 @@ struct BuildArgs {
     double* coords64[8];          // FP64 coordinates (outputs when FT = double, scratch otherwise)
     void* coords_out[8];          // FT coordinates (== coords64 when FT = double)
     void* metrics_out[12];        // FT metrics
+    // Row-band dependency between the coordinate and the tile kernel (nullptr: off).  One counter per window row:
+    // every coordinate block adds its weight when its stores are done, a row is complete at `rows_target`; the tile
+    // blocks wait for the ten rows of their patches instead of the whole coordinate grid (metrics_tile_kernel).
+    unsigned int* rows_done;
+    unsigned int rows_target;
 };
+
+__device__ __forceinline__ void row_block_done(unsigned int* rows_done, int jw, unsigned weight)
+{
+    __syncthreads();                                     // the block's coordinate stores are issued
+    if (rows_done && threadIdx.x == 0) {
+        __threadfence();                                 // ... and visible device-wide before the count moves
+        atomicAdd(rows_done + jw, weight);
+    }
+}
 
 __host__ __device__ inline Tables make_tables(const double* base, int Nx, int Ny)
 {
@@ -79,17 +93,28 @@ __host__ __device__ inline TableKeys table_keys(const GridDims& g, int flags, do
 }
 
 __global__ void __launch_bounds__(128) tables_kernel(GridDims g, int flags, double south, double north_poles_latitude,
-                                                     double radius, double* __restrict__ base, unsigned long long* stamp)
+                                                     double radius, double* __restrict__ base, unsigned long long* stamp,
+                                                     unsigned int* rows_done, int wny)
 {
+    // (row counters of the coordinate -> tile dependency: zero for this build; the coordinate kernel waits for this grid)
+    if (rows_done) { const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r < wny) rows_done[r] = 0u; }
     // programmatic dependent launch: the coordinate kernel behind this one may be scheduled right away; it
     // waits (cudaGridDependencySynchronize) for this grid to finish before it reads a table entry
     cudaTriggerProgrammaticLaunchCompletion();
     const TableKeys key = table_keys(g, flags, south, north_poles_latitude, radius);
-    bool xy_ok = true, ll_ok = true;
+    // all eleven header words in flight at once (six 16-byte loads: one L2 round trip, not eleven in a chain)
+    unsigned long long hw[12];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) xy_ok = xy_ok && __ldcg(stamp + q) == key.xy[q];
+    for (int q = 0; q < 6; ++q) {
+        const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(stamp) + q);
+        hw[2 * q] = v.x; hw[2 * q + 1] = v.y;
+    }
+    unsigned long long dxy = 0, dll = 0;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) ll_ok = ll_ok && __ldcg(stamp + 5 + q) == key.ll[q];
+    for (int q = 0; q < 5; ++q) dxy |= hw[q] ^ key.xy[q];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) dll |= hw[5 + q] ^ key.ll[q];
+    const bool xy_ok = dxy == 0, ll_ok = dll == 0;
     if (xy_ok && ll_ok) return;                             // (uniform over the grid: nobody writes the header before every block has read it)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int Nx = g.Nx, Ny = g.Ny;
@@ -146,12 +171,10 @@ __global__ void __launch_bounds__(128) tables_kernel(GridDims g, int flags, doub
 
 // ------------------------------------------------------------------ K1
 template <typename FT>
-__global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ BuildArgs a)
+__device__ __forceinline__ void coords_body(const BuildArgs& a)
 {
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
     const int jw = blockIdx.y;
-    cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
-    cudaTriggerProgrammaticLaunchCompletion();                // the tile kernel behind may take the slots this grid's tail frees
     if (iw >= a.w.wnx) return;
     const int I = a.w.I0 + iw, J = a.w.J0 + jw;
     const GridDims g = a.g;
@@ -184,6 +207,14 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ Bui
             static_cast<FT*>(a.coords_out[4 + loc])[o] = (FT)phi;
         }
     }
+}
+template <typename FT>
+__global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ BuildArgs a)
+{
+    cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
+    cudaTriggerProgrammaticLaunchCompletion();                // the tile kernel behind may take the slots this grid's tail frees
+    coords_body<FT>(a);
+    row_block_done(a.rows_done, blockIdx.y, 1u);              // (a row is complete at gridDim.x)
 }
 
 // ------------------------------------------------------------------ K1 (mirror pairs)
@@ -231,10 +262,14 @@ __device__ __forceinline__ int magic_div(int b, int d, unsigned long long magic)
 __device__ __forceinline__ int magic_div(int b, int d, unsigned long long) { return b / d; }
 #endif
 
+template <typename FT, bool SPLIT>
+__device__ __forceinline__ void coords_pair_body(const BuildArgs& a, const PairGrid& pg, int jw, int chunk, const double* s_atan);
+
 template <typename FT, bool SPLIT /* window narrower than the x extent: images may fall outside */>
 __global__ void __launch_bounds__(OSSG_COORD_BLOCK, 1024 / OSSG_COORD_BLOCK) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
 {
     int jw, chunk;
+    bool pair_row;
     {
         const int b = blockIdx.x, nb_pair = pg.n_pair_rows * pg.chunks_pair;
 #ifdef OSSG_COORD_MAGIC_DIV
@@ -245,7 +280,8 @@ __global__ void __launch_bounds__(OSSG_COORD_BLOCK, 1024 / OSSG_COORD_BLOCK) coo
         // the rows outside 1..Ny-1 (halo rows of the fold and of the south: one general evaluation per element, the
         // longest threads of the grid) take the FIRST blocks, so that they run next to the pair rows instead of after them
         const int nb_full = (int)gridDim.x - nb_pair;
-        if (b >= nb_full) {
+        pair_row = b >= nb_full;
+        if (pair_row) {
             const int r = magic_div(b - nb_full, pg.chunks_pair, mp);
             jw = pg.jw_lo + r;
             chunk = (b - nb_full) - r * pg.chunks_pair;
@@ -268,6 +304,14 @@ __global__ void __launch_bounds__(OSSG_COORD_BLOCK, 1024 / OSSG_COORD_BLOCK) coo
     __syncthreads();
     cudaGridDependencySynchronize();                          // the table kernel in front of this launch (see launch_coords)
     cudaTriggerProgrammaticLaunchCompletion();                // the tile kernel behind may take the slots this grid's tail frees
+    coords_pair_body<FT, SPLIT>(a, pg, jw, chunk, s_atan);
+    // every row reaches chunks_pair * chunks_full: a pair row has chunks_pair blocks, any other row chunks_full
+    row_block_done(a.rows_done, jw, pair_row ? (unsigned)pg.chunks_full : (unsigned)pg.chunks_pair);
+}
+
+template <typename FT, bool SPLIT>
+__device__ __forceinline__ void coords_pair_body(const BuildArgs& a, const PairGrid& pg, int jw, int chunk, const double* s_atan)
+{
     const int tt = chunk * blockDim.x + threadIdx.x;
     const GridDims g = a.g;
     const int Nx = g.Nx, Hx = g.Hx;
@@ -749,10 +793,12 @@ __global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __gri
                                                              const __grid_constant__ TileMaps tm, const __grid_constant__ FrameRide ride)
 {
     // Launched with programmatic stream serialisation behind the coordinate kernel: the block may be resident while
-    // that grid drains, and waits here for its completion (and flush) before it reads a coordinate.  Once every block
-    // has passed this point a frame kernel launched behind this grid may start (it needs the coordinates only).
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
+    // that grid drains.  A tile needs the ten coordinate rows of its patches only: with the row counters on
+    // (a.rows_done) it waits for those, so the first tile rows run next to the coordinate kernel's last blocks;
+    // otherwise, and in every frame block (whose sources lie anywhere), it waits for that grid's completion and
+    // flush.  (The frame blocks' wait also makes this grid's completion imply the coordinate grid's.)
+    const bool row_deps = RIDE && a.rows_done != nullptr && (int)blockIdx.x < ride.tile_cols;
+    if (!row_deps) cudaGridDependencySynchronize();
     if constexpr (RIDE) {
         if ((int)blockIdx.x >= ride.tile_cols) {
             if ((int)blockIdx.y < ride.rows) {
@@ -775,6 +821,25 @@ __global__ void __launch_bounds__(NT, TILE_CTAS) metrics_tile_kernel(const __gri
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int It0 = fr.I0 + blockIdx.x * TX, Jt0 = fr.J0 + by * TY;   // global index of tile cell (0,0)
     const Window w = a.w;
+    if (row_deps) {
+        // patch rows of the four staggerings: window rows Jt0 - 1 .. Jt0 + TY (clipped); one thread per row polls its
+        // counter with acquire semantics, the barrier hands the visibility to the block.  A counter that does not
+        // arrive (it always does: every coordinate block is resident or done when this grid starts) ends in the
+        // grid-wide wait instead of a hang.
+        const int tid0 = threadIdx.y * TX + threadIdx.x;
+        if (tid0 < TY + 2) {
+            const int r = min(max(Jt0 - 1 - w.J0 + tid0, 0), w.wny - 1);
+            const unsigned int* c = a.rows_done + r;
+            unsigned v, spins = 0;
+            do {                                                  // relaxed polls (an acquire load invalidates the SM's L1 every time)
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+            } while (v < a.rows_target && ++spins < (1u << 22));
+            if (v < a.rows_target) cudaGridDependencySynchronize();
+            else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        }
+        __syncthreads();
+    }
+    cudaTriggerProgrammaticLaunchCompletion();
 
     if constexpr (TMA) {
         // ---- stage the four coordinate patches with the Tensor Memory Accelerator: one thread issues
@@ -987,6 +1052,26 @@ static size_t window_elems(const ossg_tripolar_params& q)
 {
     return (size_t)(q.nx + 2 * q.Hx) * (size_t)(q.ny + 2 * q.Hy);
 }
+// workspace layout: [header + tables | FP64 coordinates of a Float32 build | one row counter per window row]
+static size_t row_counter_offset(const ossg_tripolar_params& q, int out_type)
+{
+    size_t b = table_bytes(q);
+    if (out_type == OSSG_F32) b += 8 * window_elems(q) * sizeof(double);
+    return b;
+}
+static size_t row_counter_bytes(const ossg_tripolar_params& q)
+{
+    return (((size_t)(q.ny + 2 * q.Hy) * sizeof(unsigned int)) + 15) & ~(size_t)15;
+}
+// Row-band dependency between the coordinate and the tile kernel: opt-in with OSSG_ROW_DEPS=1 (read once per process).
+// Measured slower than the grid-wide wait: 0.8325 against 0.8233 ms per build of the 1/12 degree grid, 0.1353 against
+// 0.1339 ms on the slowest slab of 8 ranks (profiles/r02m_rowdeps.txt) -- the poll, its L1 invalidation and the extra
+// barrier at the head of every tile cost more than the few microseconds of overlap at the kernel boundary give back.
+static bool row_deps_enabled()
+{
+    static const bool on = [] { const char* e = getenv("OSSG_ROW_DEPS"); return e && strcmp(e, "1") == 0; }();
+    return on;
+}
 
 static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* workspace)
 {
@@ -999,12 +1084,15 @@ static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* works
     a.radius = q.radius;
     a.stamp = static_cast<unsigned long long*>(workspace);
     a.tables = static_cast<double*>(workspace) + TABLE_HDR_WORDS;
+    a.rows_done = nullptr;
+    a.rows_target = 0;
 }
 
 static int launch_tables(const BuildArgs& a, cudaStream_t s)
 {
     const int n = 2 * a.g.Nx + 2 * a.g.Ny + a.g.Hy + 1;
-    tables_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a.g, a.flags, a.south, a.north_poles_latitude, a.radius, a.tables, a.stamp);
+    tables_kernel<<<ceil_div(max(n, a.w.wny), 128), 128, 0, s>>>(a.g, a.flags, a.south, a.north_poles_latitude, a.radius, a.tables, a.stamp,
+                                                              a.rows_done, a.w.wny);
     OSSG_LAUNCH_CHECK("tables_kernel");
     return 0;
 }
@@ -1030,7 +1118,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
 }
 
 template <typename FT>
-static int launch_coords(const BuildArgs& a, cudaStream_t s)
+static int launch_coords(BuildArgs& a, cudaStream_t s)        // sets a.rows_target (what a complete row counts to)
 {
     dim3 block(256), grid(ceil_div(a.w.wnx, 256), a.w.wny);
     const bool full_x = a.w.I0 == 1 - a.g.Hx && a.w.wnx == a.g.Nx + 2 * a.g.Hx;
@@ -1062,6 +1150,7 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
         if (pg.n_pair_rows == 0) pg.jw_lo = 0;
         pg.chunks_pair = max(1, ceil_div(pg.n_t + pg.n_halo, OSSG_COORD_BLOCK));
         pg.chunks_full = ceil_div(a.w.wnx, OSSG_COORD_BLOCK);
+        a.rows_target = (unsigned)pg.chunks_pair * (unsigned)pg.chunks_full;
         const long long nb = (long long)pg.n_pair_rows * pg.chunks_pair + (long long)(a.w.wny - pg.n_pair_rows) * pg.chunks_full;
 #ifdef OSSG_COORD_MAGIC_DIV
         pg.magic_pair = ((1ull << 40) + pg.chunks_pair - 1) / pg.chunks_pair;     // (nb < 2^31 and chunks < 2^9 keep b * chunks below 2^40)
@@ -1071,6 +1160,7 @@ static int launch_coords(const BuildArgs& a, cudaStream_t s)
         else OSSG_CUDA_TRY(launch_pdl(coords_pair_kernel<FT, false>, dim3((unsigned)nb), dim3(OSSG_COORD_BLOCK), s, a, pg));
         OSSG_LAUNCH_CHECK("coords_pair_kernel");
     } else {
+        a.rows_target = grid.x;
         OSSG_CUDA_TRY(launch_pdl(coords_kernel<FT>, grid, block, s, a));
         OSSG_LAUNCH_CHECK("coords_kernel");
     }
@@ -1334,9 +1424,7 @@ extern "C" size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, i
 {
     ossg_tripolar_params q;
     if (check_params(p, q)) return 0;
-    size_t b = table_bytes(q);
-    if (out_type == OSSG_F32) b += 8 * window_elems(q) * sizeof(double);
-    return b;
+    return row_counter_offset(q, out_type) + row_counter_bytes(q);
 }
 
 extern "C" int ossg_tripolar_workspace_init(void* workspace, size_t workspace_bytes, void* stream)
@@ -1378,6 +1466,8 @@ static int build_impl(const ossg_tripolar_params* p, int out_type, void* const o
     }
     cudaStream_t s = as_stream(stream);
     const bool whole = is_whole_grid(q);
+    if (!ev && row_deps_enabled() && frame_mode() == 2 && tile_form() == 0)
+        a.rows_done = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + row_counter_offset(q, out_type));
     if (ev) OSSG_CUDA_TRY(cudaEventRecord(ev[0], s));
     if ((rc = launch_tables(a, s))) return rc;
     if (ev) OSSG_CUDA_TRY(cudaEventRecord(ev[1], s));

@@ -828,6 +828,52 @@ def test_two_streams_build_concurrently(ossg, oracle):
         assert np.array_equal(t.cpu().numpy().view(np.uint32), rb[n].astype(np.float32).view(np.uint32)), n
 
 
+def test_back_to_back_builds_over_poisoned_outputs(ossg, oracle):
+    """Launch chain of the constructor (programmatic dependent launch; the tile blocks wait for the ten coordinate
+    rows of their patches, csrc/ossg_tripolar.cu row counters): grids with different poles are built back to back
+    into the SAME arrays, which are poisoned and read in between, with no host synchronisation inside the loop.
+    A tile that started before its rows were complete, or that was served a stale cache line of the previous
+    grid, shows as a NaN or a wrong bit.  Whole grid and an x-split tile (the per-row weights differ)."""
+    from ossg_b200.grids import build_arrays, make_params
+    dev = torch.device("cuda", 0)
+    size, halo = (1440, 720, 1), (4, 4, 4)
+    kws = [dict(north_poles_latitude=55, first_pole_longitude=70), dict(north_poles_latitude=62, first_pole_longitude=15)]
+    refs = [oracle.build(orc.make_params(size, halo, **kw)) for kw in kws]
+    for tile in (None, (721, 1, 720, 720)):
+        ny, nx = (size[1], size[0]) if tile is None else (tile[3], tile[2])
+        out = [torch.empty((ny + 2 * halo[1], nx + 2 * halo[0]), dtype=torch.float64, device=dev) for _ in range(20)]
+        got = []
+        for it in range(6):
+            kw = kws[it % 2]
+            for t in out:
+                t.fill_(float("nan"))
+            acc = sum(t[::7, ::5].sum() for t in out)          # a read pass over the poisoned arrays
+            p = make_params(size, halo, -80, kw["north_poles_latitude"], kw["first_pole_longitude"], orc.R_EARTH, tile=tile)
+            build_arrays(p, ossg.Float64, dev, out=out)
+            if it >= 4:
+                got.append([t.clone() for t in out])
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(acc))
+        for k, arrays in enumerate(got):
+            ref = refs[k % 2]
+            for n, t in zip(orc.ALL_NAMES, arrays):
+                want = ref[n] if tile is None else ref[n][tile[1] - 1:tile[1] - 1 + ny + 2 * halo[1], tile[0] - 1:tile[0] - 1 + nx + 2 * halo[0]]
+                assert np.array_equal(t.cpu().numpy().view(np.uint64), np.ascontiguousarray(want).view(np.uint64)), (tile, k, n)
+
+
+def test_row_dependency_option_in_a_child_process(ossg):
+    """OSSG_ROW_DEPS=1 (read once per process): the same back-to-back scenario with the tile blocks waiting on the
+    per-row counters instead of the whole coordinate grid."""
+    import os, subprocess, sys
+    if os.environ.get("OSSG_TEST_CHILD"):
+        pytest.skip("child process")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OSSG_ROW_DEPS="1", OSSG_TEST_CHILD="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
+                          "-k", "back_to_back_builds or construction_matches_oracle or tiles_equal_slices"], env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_missing_partner_traps_instead_of_passing_silently(ossg):
     """A rank whose partner never makes the matching call must fail loudly: the
     waiting kernel traps after OSSG_PEER_TIMEOUT_MS and the next CUDA call of that process raises.

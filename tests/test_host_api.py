@@ -79,8 +79,9 @@ def test_argument_errors_do_not_need_a_device(ossg):
     assert L.ossg_tripolar_build(C.byref(p), 0, ossg._lib.ptr_array([4] * 20), 16, 1 << 20, None) == ossg._lib.OSSG_EALIGN
     tb = ((16 + 4 * 60 + 4 * 30 + 9 * 5 + 1) // 2 * 2) * 8          # 128-byte stamp header + x/y tables + lat-lon rows
     assert L.ossg_tripolar_table_bytes(C.byref(p)) == tb
-    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 0) == tb
-    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 1) == tb + 8 * 68 * 38 * 8
+    rc = (38 * 4 + 15) // 16 * 16                                   # one 4-byte counter per window row (coordinate -> tile dependency)
+    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 0) == tb + rc
+    assert L.ossg_tripolar_workspace_bytes(C.byref(p), 1) == tb + 8 * 68 * 38 * 8 + rc
     assert L.ossg_tripolar_workspace_init(None, 1 << 20, None) == ossg._lib.OSSG_EALIGN
     assert L.ossg_tripolar_workspace_init(16, 64, None) == ossg._lib.OSSG_EWORKSPACE
     f = ossg._lib.FieldDesc(8, 0, 10, 10, 1, 4, 4, 4, 2, 0, 0, 0, 1.0)
