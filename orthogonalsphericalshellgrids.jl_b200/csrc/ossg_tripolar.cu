@@ -240,8 +240,14 @@ __device__ __forceinline__ void store_coord(const BuildArgs& a, int loc, size_t 
 #ifndef OSSG_COORD_ILP
 #define OSSG_COORD_ILP 1
 #endif
+#ifndef OSSG_COORD_SPLIT_X
+#define OSSG_COORD_SPLIT_X 1        /* one copy of the hot loop per x location: coordinate kernel 0.2055 -> 0.1914 ms (profiles/r02o_variants.txt) */
+#endif
 #ifndef OSSG_COORD_BLOCK
 #define OSSG_COORD_BLOCK 128      /* threads per block of coords_pair_kernel, 8 blocks per SM: 0.2086 -> 0.2022 ms against 256 x 4 (finer tail), profiles/r02k_tiles.txt */
+#endif
+#ifndef OSSG_COORD_MINBLOCKS
+#define OSSG_COORD_MINBLOCKS (1024 / OSSG_COORD_BLOCK)
 #endif
 // 1-D grid of coords_pair_kernel: the pair rows (J = 1..Ny-1) need Nx/2 + 1 + 2Hx threads, the other
 // rows one thread per padded element; a 2-D grid sized for the latter would launch an empty
@@ -266,7 +272,7 @@ template <typename FT, bool SPLIT>
 __device__ __forceinline__ void coords_pair_body(const BuildArgs& a, const PairGrid& pg, int jw, int chunk, const double* s_atan);
 
 template <typename FT, bool SPLIT /* window narrower than the x extent: images may fall outside */>
-__global__ void __launch_bounds__(OSSG_COORD_BLOCK, 1024 / OSSG_COORD_BLOCK) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
+__global__ void __launch_bounds__(OSSG_COORD_BLOCK, OSSG_COORD_MINBLOCKS) coords_pair_kernel(const __grid_constant__ BuildArgs a, const PairGrid pg)
 {
     int jw, chunk;
     bool pair_row;
@@ -358,6 +364,30 @@ __device__ __forceinline__ void coords_pair_body(const BuildArgs& a, const PairG
             // point that leaves the preconditions sets `bad`; the thread then redoes its four points
             // through the general functions and overwrites the speculative stores.
             bool bad = false;
+#if OSSG_COORD_SPLIT_X
+            // two copies of the loop body, one per x location (compile-time: the column tables, the mirror column and its
+            // conditions are no longer selected at run time), each rolled over the y location
+#pragma unroll
+            for (int kx = 0; kx < 2; ++kx) {
+                const bool fx = kx == 0;
+                const double as_i = fx ? asF : asC, ac_i = fx ? acF : acC;
+                const bool st_i = fx ? in_i : directC, st_m = fx ? mirrorF : mirrorC;
+                const size_t om = fx ? omF : omC;
+                const bool m_le_half = (fx ? ipmF : ipmC) <= half;
+#if defined(OSSG_COORD_UNROLL_Y)
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+                for (int ky = 0; ky < 2; ++ky) {                          // FC, FF | CC, CF
+                    const bool fy = ky != 0;
+                    const PointCore c = tripolar_core_sl(as_i, ac_i, fy ? chF : chC, fy ? shF : shC, s_atan, bad);
+                    const int loc = fx ? (fy ? FF : FC) : (fy ? CF : CC);
+                    if (st_i) store_coord<FT>(a, loc, o, tripolar_finish_sl(c.lam_a, ip <= half, fpl90, bad), c.phi);
+                    if (st_m) store_coord<FT>(a, loc, om, tripolar_finish_sl(-c.lam_a, m_le_half, fpl90, bad), c.phi);
+                }
+            }
+#else
 #if defined(OSSG_COORD_UNROLL)
 #pragma unroll
 #else
@@ -375,6 +405,7 @@ __device__ __forceinline__ void coords_pair_body(const BuildArgs& a, const PairG
                         store_coord<FT>(a, loc, fx ? omF : omC, tripolar_finish_sl(-c.lam_a, (fx ? ipmF : ipmC) <= half, fpl90, bad), c.phi);
                 }
             }
+#endif
             if (bad) {
 #pragma unroll 1
                 for (int k = 0; k < 4; ++k) {

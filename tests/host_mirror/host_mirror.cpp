@@ -135,6 +135,7 @@ int hm_math_eval(int fn, const double* x, double* y, size_t n)
         case 19: { double sn, cs; bool bad = false; m::sincosd_lon_spec(x[e], sn, cs, bad); if (bad) m::sincosd(x[e], sn, cs); y[e] = cs; break; }
         case 20: y[e] = m::atan_lut(x[e], m::kATAN_LUT); break;
         case 21: { bool bad = false; const double r = m::atan_sl(x[e], m::kATAN_LUT, bad); y[e] = bad ? m::atan_f(x[e]) : r; break; }
+        case 22: y[e] = m::cos_rad_inl(x[e]); break;
         case 13: { double p, sh, ch; m::asinh_sinh_cosh_cr(x[e], p, sh, ch); y[e] = p; break; }
         case 14: { double p, sh, ch; m::asinh_sinh_cosh_cr(x[e], p, sh, ch); y[e] = sh; break; }
         case 15: { double p, sh, ch; m::asinh_sinh_cosh_cr(x[e], p, sh, ch); y[e] = ch; break; }

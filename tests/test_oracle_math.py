@@ -169,6 +169,20 @@ def test_specialised_unit_vector_trig_is_bit_identical(mirror):
         assert np.array_equal(hm.math(mirror, fc, xs).view(np.uint64), hm.math(mirror, 1, xs).view(np.uint64))
 
 
+def test_inline_cosine_of_the_point_stage_is_bit_identical(mirror, oracle):
+    """cos_rad_inl (the tile kernel's cos(deg2rad(phi))) takes the direct cosine kernel below the HIGH WORD of pi/4 and
+    the n = 0 reduction between that bound and pi/4: the same bits as cos_rad / the oracle over the latitude range,
+    in particular on the interval between the two bounds and at its ends."""
+    pio4 = np.float64(float.fromhex("0x1.921fb54442d18p-1"))
+    lo = np.array([0x3FE921FB00000000], dtype=np.uint64).view(np.float64)[0]
+    band = np.linspace(lo, pio4, 20001)
+    edge = np.array([lo, pio4, np.nextafter(lo, 0), np.nextafter(lo, 1), np.nextafter(pio4, 0), np.nextafter(pio4, 1)])
+    xs = np.concatenate([RNG.uniform(-np.pi / 2, np.pi / 2, 300000), band, -band, edge, -edge, [0.0, -0.0, np.pi / 2, -np.pi / 2, 1e-300]])
+    got = hm.math(mirror, 22, xs)
+    assert np.array_equal(got.view(np.uint64), hm.math(mirror, orc.MATH_FN["cos"], xs).view(np.uint64))
+    assert np.array_equal(got.view(np.uint64), oracle.math("cos", xs).view(np.uint64))
+
+
 def test_table_driven_atan_is_bit_identical(mirror, oracle):
     """atan_lut (coordinate kernel) against atan_f / the oracle over all reduction ranges, at the
     range bounds, at the zero-numerator arguments 0.5, 1, 1.5 and at 0, inf, nan."""

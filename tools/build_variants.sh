@@ -7,6 +7,8 @@
 #   fprange         -DOSSG_RANGE_FP_TESTS     tile kernel: FP64 comparisons for the speculative range tests (round-1 form)
 #   lonsel          -DOSSG_LON_SPEC_SELECTS   tile kernel: select-chain form of sincosd_lon_spec (round-1 form)
 #   coordunr        -DOSSG_COORD_UNROLL       coordinate kernel: the four staggerings unrolled (compile-time locations)
+#   cxrolled        -DOSSG_COORD_SPLIT_X=0    coordinate kernel: one rolled loop over the four staggerings (default: one copy per x location)
+#   cxy64, cxy80    -DOSSG_COORD_UNROLL_Y [-DOSSG_COORD_MINBLOCKS=6]  all four staggerings unrolled, at 64 / 80 registers; cx80: default form at 80 registers
 #   pcpair          -DOSSG_PC_SOA=0           tile kernel: deg2rad(phi)/2 and cos(phi) of a patch point as one 16-byte shared element
 #   cb256, cb64     -DOSSG_COORD_BLOCK=..     coordinate kernel: 256- / 64-thread blocks (default 128, 8 per SM)
 # (fprange, lonsel, coordunr only with --all)
@@ -32,6 +34,10 @@ if [ "$1" == "--all" ]; then
   build $CS coordunr -DOSSG_COORD_UNROLL &
 fi
 build $CS pcpair -DOSSG_PC_SOA=0 &
+build $CS cxrolled -DOSSG_COORD_SPLIT_X=0 &
+build $CS cxy64 -DOSSG_COORD_UNROLL_Y &
+build $CS cxy80 -DOSSG_COORD_UNROLL_Y -DOSSG_COORD_MINBLOCKS=6 &
+build $CS cx80 -DOSSG_COORD_MINBLOCKS=6 &
 build $CS cb256 -DOSSG_COORD_BLOCK=256 &
 build $CS cb64 -DOSSG_COORD_BLOCK=64 &
 wait
