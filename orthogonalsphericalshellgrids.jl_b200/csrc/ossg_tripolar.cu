@@ -52,8 +52,9 @@ struct BuildArgs {
 
 __device__ __forceinline__ void row_block_done(unsigned int* rows_done, int jw, unsigned weight)
 {
+    if (!rows_done) return;                              // (uniform: off by default)
     __syncthreads();                                     // the block's coordinate stores are issued
-    if (rows_done && threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
         __threadfence();                                 // ... and visible device-wide before the count moves
         atomicAdd(rows_done + jw, weight);
     }
