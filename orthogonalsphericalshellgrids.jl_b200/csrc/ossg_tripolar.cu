@@ -2,18 +2,22 @@
 //
 // Kernels (all FP64 arithmetic, outputs FP64 or rounded once to FP32):
 //   K0  tables_kernel         1-D tables: a*sind/cosd(lam1D), cosh/sinh(psi(phi1D)), lat-lon rows
-//   K1  coords_pair_kernel    8 padded coordinate arrays for windows that span x: one thread per
-//                             mirror pair of columns (the map is exactly mirror symmetric), branch-free
-//                             straight-line point with a table-driven atan; circshift + zipper/periodic
-//                             halos are index maps (every element evaluated at its source)
-//   K1' coords_kernel         the same per padded element (windows that split x)
+//   K1  coords_pair_kernel    8 padded coordinate arrays, one thread per mirror pair of columns (the map is
+//                             exactly mirror symmetric): whole-x windows and the halves of an Rx = 2 partition;
+//                             branch-free straight-line point with a table-driven atan, one copy of the hot loop
+//                             per x location; circshift + zipper/periodic halos are index maps (every element
+//                             evaluated at its source)
+//   K1' coords_kernel         the same per padded element (windows narrower than half the x extent)
 //   K2  metrics_tile_kernel   12 metric arrays over the interior: four coordinate patches staged in
 //                             shared memory (cp.async; TMA box loads opt-in), per-point cos(phi) and
 //                             unit vectors once per patch point, then 8 haversines + 2 spherical
-//                             quadrilaterals per cell as one speculative straight-line block
-//   K2f metrics_frame_kernel  the halo frame (north fold image, x halos, fold row Ny, south
-//                             continuation rows): one thread per (element, metric) at its source,
-//                             on a side stream next to K2
+//                             quadrilaterals per cell as one speculative straight-line block whose
+//                             preconditions are integer max/min over high words.  The halo frame (north
+//                             fold image, x halos, fold row Ny, south continuation rows; one thread per
+//                             (element, metric) at its source) rides in extra block columns of this grid
+//   K2f metrics_frame_kernel  the halo frame on its own grid (profiled build, opt-in tile variants, windows
+//                             without a fast rectangle)
+// One stream, three launches per build, chained with programmatic dependent launch (K1 behind K0, K2 behind K1).
 //   cartesian_nodes_kernel    lat_lon_to_cartesian over a coordinate pair
 // Compile with -fmad=false: see ossg_math.cuh for the determinism contract.
 #include <cuda.h>
