@@ -102,7 +102,10 @@ int         ossg_device_ok(void);               /* 0 iff a CUDA device of comput
  * workspace: device scratch of at least ossg_tripolar_workspace_bytes() bytes, 16-byte aligned
  * (1-D tables; plus the 8 FP64 coordinate arrays when out_type = OSSG_F32, because the metrics
  * are always computed from FP64 coordinates and rounded once at the end,
- * src/tripolar_grid.jl:308-328).                                                               */
+ * src/tripolar_grid.jl:308-328; plus one 4-byte counter per window row for the optional row-band
+ * dependency between the coordinate and the metric kernel, OSSG_ROW_DEPS=1).  Every launch of a
+ * call goes to the caller's stream; the kernels of one build are chained with programmatic
+ * dependent launch.                                                                             */
 size_t ossg_tripolar_workspace_bytes(const ossg_tripolar_params* p, int out_type);
 
 /* The workspace starts with a 128-byte header and the 1-D tables (ossg_tripolar_table_bytes() bytes in

@@ -808,8 +808,8 @@ def test_with_halo_on_device_reuses_the_tables(ossg, oracle):
 
 
 def test_two_streams_build_concurrently(ossg, oracle):
-    """Re-entrancy: builds on two streams, each with its own workspace, share only the per-device
-    fork/join resources; both results are the oracle's."""
+    """Re-entrancy: builds on two streams, each with its own workspace, share nothing (every launch of a
+    build goes to the caller's stream); both results are the oracle's."""
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     from ossg_b200.grids import build_arrays, make_params
     dev = torch.device("cuda", 0)
