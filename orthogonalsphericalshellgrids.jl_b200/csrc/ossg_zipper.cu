@@ -169,9 +169,11 @@ __device__ __forceinline__ void fused_column(const ossg_field_desc& f, int i /*1
 // each other (91 ... 94 us for 4 fields, 99 us in two launches).  The L2 fetches 128 bytes around every
 // 32-byte piece by default (3 lines per 2 rows: the row pitch is an odd multiple of 64 bytes), 238 MB
 // of DRAM reads for 119 MB requested; the L2::64B prefetch-size qualifier brings that to 178 MB and
-// the time from 93 to 91 us.  Bytes are not what bounds this part: it issues ~3.7 M scattered DRAM
-// transactions, 34 KB apart, about 60 G/s -- the activation rate of the HBM3e stacks (tFAW), not their
-// bandwidth.  Kept: thread per row with the L2::64B loads (fewest bytes, fastest by 2 %).
+// the time from 93 to 91 us.  What bounds this part is the count of small accesses, not their bytes and not the
+// row pitch (it costs 51 ... 61 us for 1.87 M + 1.87 M pieces at every pitch from 576 bytes to 34 KB,
+// tools/fill_pitch_probe.py): 64-byte DRAM accesses move at ~3.3 TB/s here.  Full-granule stores and
+// interleaving this part with the fold part were measured too (no gain, profiles/r02_fill_dram.md).
+// Kept: thread per row with the L2::64B loads (fewest bytes, fastest by 2 %).
 struct Piece32 { double a, b, c, d; };
 // every halo piece of the field is a 32-byte aligned run of 4 doubles (base, row pitch and Nx all multiples of 32 bytes)
 __host__ __device__ inline bool piece32_ok(const ossg_field_desc& f)
