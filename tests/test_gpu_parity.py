@@ -861,14 +861,18 @@ def test_back_to_back_builds_over_poisoned_outputs(ossg, oracle):
                 assert np.array_equal(t.cpu().numpy().view(np.uint64), np.ascontiguousarray(want).view(np.uint64)), (tile, k, n)
 
 
-def test_row_dependency_option_in_a_child_process(ossg):
-    """OSSG_ROW_DEPS=1 (read once per process): the same back-to-back scenario with the tile blocks waiting on the
-    per-row counters instead of the whole coordinate grid."""
+@pytest.mark.parametrize("knob", ["OSSG_ROW_DEPS=1", "OSSG_FRAME=fork", "OSSG_FRAME=tail"])
+def test_launch_options_in_a_child_process(ossg, knob):
+    """The launch-form knobs are read once per process, so each runs in a child: OSSG_ROW_DEPS=1 (tile blocks wait on
+    per-row counters instead of the whole coordinate grid), OSSG_FRAME=fork (halo frame on a side stream with an event
+    pair) and OSSG_FRAME=tail (its own grid behind the tile kernel, programmatic launch).  Same parity tests, same bits."""
     import os, subprocess, sys
     if os.environ.get("OSSG_TEST_CHILD"):
         pytest.skip("child process")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, OSSG_ROW_DEPS="1", OSSG_TEST_CHILD="1")
+    name, value = knob.split("=")
+    env = dict(os.environ, OSSG_TEST_CHILD="1")
+    env[name] = value
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
                           "-k", "back_to_back_builds or construction_matches_oracle or tiles_equal_slices"], env=env, capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
