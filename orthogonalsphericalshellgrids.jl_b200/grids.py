@@ -12,6 +12,7 @@ array work happens in libossg_b200.so on the GPU; torch is used only to own devi
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field as _dc_field
 from typing import Optional, Sequence
 

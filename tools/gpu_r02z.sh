@@ -1,0 +1,14 @@
+#!/bin/bash
+# round-2 GPU call Z (1 GPU): halo images stored by the tile kernel (edge predicate kept across the cell stage): timings vs the last commit, poisoned suite
+set -x
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+for rep in 1 2; do
+for v in head cur; do
+OSSG_B200_LIB=$PWD/build/variants/libossg_$v.so timeout 120 python tools/variant_time.py 2>&1 | tail -1
+OSSG_B200_LIB=$PWD/build/variants/libossg_$v.so timeout 120 python tools/slab_time.py 2>&1 | tail -1
+OSSG_B200_LIB=$PWD/build/variants/libossg_$v.so timeout 120 python tools/slab_time.py --xsplit 2>&1 | tail -1
+done
+done | tee gpurun_out/r02z_images.log
+( time OSSG_TEST_POISON=1 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/r02z_pytest_poison.log 2>&1
+tail -6 gpurun_out/r02z_pytest_poison.log
