@@ -101,11 +101,17 @@ __global__ void __launch_bounds__(128) tables_kernel(GridDims g, int flags, doub
                                                      double radius, double* __restrict__ base, unsigned long long* stamp,
                                                      unsigned int* rows_done, int wny)
 {
+    // This grid is itself launched with programmatic stream serialisation: behind a tile kernel of an earlier build on the
+    // same stream (which lets its dependents go early) its blocks -- and behind them the coordinate kernel's -- are
+    // resident before that grid has finished, and wait here.  Nothing of this build touches memory before the wait, and
+    // the coordinate kernel waits for this grid in turn, so a build never overtakes the one before it; what is saved is
+    // the launch latency of two kernels.  Behind any other operation the launch is an ordinary one.
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
     // (row counters of the coordinate -> tile dependency: zero for this build; the coordinate kernel waits for this grid)
     if (rows_done) { const int r = blockIdx.x * blockDim.x + threadIdx.x; if (r < wny) rows_done[r] = 0u; }
-    // programmatic dependent launch: the coordinate kernel behind this one may be scheduled right away; it
-    // waits (cudaGridDependencySynchronize) for this grid to finish before it reads a table entry
-    cudaTriggerProgrammaticLaunchCompletion();
+    // (the coordinate kernel behind this one was let go above; it waits -- cudaGridDependencySynchronize -- for this grid
+    // to finish before it reads a table entry)
     const TableKeys key = table_keys(g, flags, south, north_poles_latitude, radius);
     // all eleven header words in flight at once (six 16-byte loads: one L2 round trip, not eleven in a chain)
     unsigned long long hw[12];
@@ -1124,15 +1130,6 @@ static void fill_common(BuildArgs& a, const ossg_tripolar_params& q, void* works
     a.rows_target = 0;
 }
 
-static int launch_tables(const BuildArgs& a, cudaStream_t s)
-{
-    const int n = 2 * a.g.Nx + 2 * a.g.Ny + a.g.Hy + 1;
-    tables_kernel<<<ceil_div(max(n, a.w.wny), 128), 128, 0, s>>>(a.g, a.flags, a.south, a.north_poles_latitude, a.radius, a.tables, a.stamp,
-                                                              a.rows_done, a.w.wny);
-    OSSG_LAUNCH_CHECK("tables_kernel");
-    return 0;
-}
-
 // Launch with programmatic stream serialisation: the kernel may start while its predecessor in the stream (the
 // table kernel, which triggers its dependents at once) is still running; it synchronises on that grid itself.
 // The table kernel is a stamp check in the steady state, so this removes one full kernel boundary per build.
@@ -1151,6 +1148,15 @@ template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args)
 {
     return launch_pdl_smem(kernel, grid, block, 0, true, s, std::forward<Args>(args)...);
+}
+
+static int launch_tables(const BuildArgs& a, cudaStream_t s)
+{
+    const int n = 2 * a.g.Nx + 2 * a.g.Ny + a.g.Hy + 1;
+    OSSG_CUDA_TRY(launch_pdl(tables_kernel, dim3((unsigned)ceil_div(max(n, a.w.wny), 128)), dim3(128), s, a.g, a.flags, a.south, a.north_poles_latitude,
+                             a.radius, a.tables, a.stamp, a.rows_done, a.w.wny));
+    OSSG_LAUNCH_CHECK("tables_kernel");
+    return 0;
 }
 
 template <typename FT>
