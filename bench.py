@@ -32,7 +32,7 @@ METRIC = "grid cells/s for coords+metrics (FP64)"
 UNIT = "cells/s"
 
 # FP64 pipe work per launch, counted by ncu on the 1/12 degree workload (SASS opcode mix of the
-# committed capture profiles/r02q_*_opcodes.md, taken at the round-2 kernels of HEAD: DFMA + DMUL + DADD + DSETP
+# committed capture profiles/r02ac_*_opcodes.md, taken at the round-2 kernels of HEAD: DFMA + DMUL + DADD + DSETP
 # thread-instructions):
 #   metrics_tile_kernel : 843.7 per tile cell (4320 x 2158 cells)        245.79 M warp-instructions for the tiles
 #                         (the capture's 251.59 M include the halo frame riding in this grid: 5.80 M, counted on its own
@@ -41,13 +41,13 @@ UNIT = "cells/s"
 #                         FP64 fractions below fall while the kernel gets faster.
 #   coords_pair_kernel  : 194.9 per padded element (4328 x 2168 elements)  57.16 M warp-instructions
 # and the DRAM traffic of one metrics_tile_kernel launch from the same capture
-# (dram__bytes_read.sum + dram__bytes_write.sum = 615.9 MB + 886.2 MB; algorithmic 1491.6 MB).
+# (dram__bytes_read.sum + dram__bytes_write.sum = 616.0 MB + 888.7 MB; algorithmic 1491.6 MB).
 # These are properties of the code, not of the timing; refresh them whenever the kernels change.
 FP64_INST_PER_CELL_TILE = 843.7
 FP64_INST_FRAME = 5796220 * 32          # thread-instructions of the whole-grid halo frame (scaled by the frame size of a window below)
 FP64_INST_PER_ELEM_COORDS = 194.9
-NCU_TRAFFIC_TILE_BYTES = 615948032 + 886192384
-PROFILE_TAG = "r02q"
+NCU_TRAFFIC_TILE_BYTES = 616029440 + 888712192
+PROFILE_TAG = "r02ac"
 
 
 def partition_for(n):

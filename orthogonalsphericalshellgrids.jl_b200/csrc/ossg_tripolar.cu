@@ -780,17 +780,34 @@ template <typename FT>
 __device__ __noinline__ void frame_element(const BuildArgs& a, const Frame& f, long long t)
 {
     const long long n = f.n_south + f.n_north + f.n_west + f.n_east;
-    const int mtr = (int)(t / n);
-    t -= (long long)mtr * n;
     const Window w = a.w;
-    int iw, jw;
-    if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
-    else if ((t -= f.n_south) < f.n_north) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); jw += f.jhi; }
-    else if ((t -= f.n_north) < f.n_west) { jw = (int)(t / f.ilo); iw = (int)(t - (long long)jw * f.ilo); jw += f.jlo; }
-    else {
-        t -= f.n_west;
-        const int ne = w.wnx - f.ihi;
-        jw = (int)(t / ne); iw = (int)(t - (long long)jw * ne) + f.ihi; jw += f.jlo;
+    int mtr, iw, jw;
+    if (N_METRIC * n < 0x7fffffffLL) {
+        // (every realistic frame: 32-bit index arithmetic -- a 64-bit division costs ~100 instructions, and the decode
+        // would be a third of this function)
+        const unsigned n32 = (unsigned)n, ns = (unsigned)f.n_south, nn = (unsigned)f.n_north, nw = (unsigned)f.n_west;
+        unsigned u = (unsigned)t;
+        mtr = (int)(u / n32);
+        u -= (unsigned)mtr * n32;
+        if (u < ns) { jw = (int)(u / (unsigned)w.wnx); iw = (int)(u - (unsigned)jw * (unsigned)w.wnx); }
+        else if ((u -= ns) < nn) { jw = (int)(u / (unsigned)w.wnx); iw = (int)(u - (unsigned)jw * (unsigned)w.wnx); jw += f.jhi; }
+        else if ((u -= nn) < nw) { jw = (int)(u / (unsigned)f.ilo); iw = (int)(u - (unsigned)jw * (unsigned)f.ilo); jw += f.jlo; }
+        else {
+            u -= nw;
+            const unsigned ne = (unsigned)(w.wnx - f.ihi);
+            jw = (int)(u / ne); iw = (int)(u - (unsigned)jw * ne) + f.ihi; jw += f.jlo;
+        }
+    } else {
+        mtr = (int)(t / n);
+        t -= (long long)mtr * n;
+        if (t < f.n_south) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); }
+        else if ((t -= f.n_south) < f.n_north) { jw = (int)(t / w.wnx); iw = (int)(t - (long long)jw * w.wnx); jw += f.jhi; }
+        else if ((t -= f.n_north) < f.n_west) { jw = (int)(t / f.ilo); iw = (int)(t - (long long)jw * f.ilo); jw += f.jlo; }
+        else {
+            t -= f.n_west;
+            const int ne = w.wnx - f.ihi;
+            jw = (int)(t / ne); iw = (int)(t - (long long)jw * ne) + f.ihi; jw += f.jlo;
+        }
     }
     const GridDims g = a.g;
     const Tables tb = make_tables(a.tables, g.Nx, g.Ny);
