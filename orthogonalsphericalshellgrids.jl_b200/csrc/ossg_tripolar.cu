@@ -451,19 +451,7 @@ __device__ __forceinline__ void coords_pair_body(const BuildArgs& a, const PairG
 #pragma unroll 1
     for (int loc = 0; loc < 4; ++loc) {
         double lam, phi;
-        int si, sj; bool wrapped, done = false;
-        if (halo_source(loc_x(loc), loc_y(loc), I, J, g.Nx, g.Ny, si, sj, wrapped) && sj >= 1 && sj < g.Ny) {
-            // the image of a point of an ordinary row (north halo): the straight-line point of the pair rows, evaluated at
-            // the source column -- the same bits as the general function unless it raises `bad` (then that one decides)
-            const bool fx = loc_x(loc) != 0, fy = loc_y(loc) != 0;
-            bool bad = false;
-            const PointCore c = tripolar_core_sl(__ldg((fx ? tb.asF : tb.asC) + si - 1), __ldg((fx ? tb.acF : tb.acC) + si - 1),
-                                                 __ldg((fy ? tb.chF : tb.chC) + sj - 1), __ldg((fy ? tb.shF : tb.shC) + sj - 1), s_atan, bad);
-            lam = tripolar_finish_sl(c.lam_a, preshift(si, g.Nx) <= g.Nx / 2, fpl + 90.0, bad);
-            phi = c.phi;
-            done = !bad;
-        }
-        if (!done) coord_at(tb, g, fpl, loc, I, J, lam, phi);
+        coord_at(tb, g, fpl, loc, I, J, lam, phi);
         store_coord<FT>(a, loc, row + t, lam, phi);
     }
 }
