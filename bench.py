@@ -46,6 +46,9 @@ UNIT = "cells/s"
 FP64_INST_PER_CELL_TILE = 843.7
 FP64_INST_FRAME = 5796220 * 32          # thread-instructions of the whole-grid halo frame (scaled by the frame size of a window below)
 FP64_INST_PER_ELEM_COORDS = 194.9
+# The same without the comparisons (DFMA + DMUL + DADD only), whole build incl. the frame: 249.61 M (tile + frame) + 54.36 M
+# (coordinates) warp-instructions in capture r02ac; capture r02d (start of round 2): 249.22 M + ~5.3 M (frame, own grid) + 54.36 M.
+FP64_ARITH_WARP_INST_STEP = 249613243 + 54357486
 NCU_TRAFFIC_TILE_BYTES = 616029440 + 888712192
 PROFILE_TAG = "r02ac"
 
@@ -652,6 +655,9 @@ def run_own(args):
             "frac": inst_tile / (tile_ms * 1e-3) / peak_inst,
             "coords_kernel_frac": inst_coords / (kernel_ms["coords"] * 1e-3) / peak_inst,
             "whole_step_frac": (inst_tile + inst_coords + FP64_INST_FRAME / world) / (ms_step * 1e-3) / peak_inst,
+            # arithmetic only (no DSETP): comparable across the round -- the range tests that were FP64 comparisons in round 1
+            # are integer instructions now, which lowers the fractions above while the kernels get faster
+            "whole_step_arith_frac": (FP64_ARITH_WARP_INST_STEP * 32 / world) / (ms_step * 1e-3) / peak_inst if world == 1 else None,
             "fp64_inst_source": f"ncu SASS opcode counts, profiles/{PROFILE_TAG}_*_opcodes.md"})
 
     roofline_zipper = None
