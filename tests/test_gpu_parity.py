@@ -181,6 +181,31 @@ def test_tiles_equal_slices_of_the_serial_grid(ossg, oracle, Rx, Ry, dtype):
                 assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8)), (name, rx, ry)
 
 
+@pytest.mark.parametrize("size,halo", [((20, 12, 1), (4, 4, 4)), ((10, 10, 1), (4, 4, 4)), ((26, 14, 1), (3, 5, 1)), ((64, 20, 1), (8, 2, 1))])
+def test_arbitrary_windows_equal_slices_of_the_serial_grid(ossg, oracle, size, halo):
+    """Windows that are not tiles of a regular partition (any i0, nx, j0, ny the C ABI accepts): halves and other
+    x ranges whose padded columns wrap around either end of the grid, with and without their own mirror columns --
+    every launch form of the coordinate kernel (pair form for whole-x and mirror-closed windows, bounding thread
+    range with idle threads, per-element form) against slices of the oracle's serial grid, Nx % 4 != 0 included."""
+    from ossg_b200.grids import build_arrays, make_params
+    Nx, Ny = size[0], size[1]
+    Hx, Hy = halo[0], halo[1]
+    ref = oracle.build(orc.make_params(size, halo))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xs = [(1, Nx), (1, Nx // 2), (Nx // 2 + 1, Nx - Nx // 2), (1, 1), (Nx, 1), (2, Nx - 2), (Nx // 4 + 1, Nx // 2), (3, max(1, Nx // 3)), (Nx - 2, 3)]
+    ys = [(1, Ny), (1, max(1, Ny // 2)), (Ny // 2 + 1, Ny - Ny // 2), (Ny, 1), (Ny - 2, 3), (2, 1)]
+    for (i0, nx) in xs:
+        for (j0, ny) in ys:
+            if (ny - 1 < Hy and j0 + ny - 1 == Ny and False):
+                continue
+            params = make_params(size, halo, -80, 55, 70, orc.R_EARTH, tile=(i0, j0, nx, ny))
+            tiles = build_arrays(params, torch.float64, dev)
+            torch.cuda.synchronize()
+            for name, t in zip(orc.ALL_NAMES, tiles):
+                want = ref[name][j0 - 1:j0 - 1 + ny + 2 * Hy, i0 - 1:i0 - 1 + nx + 2 * Hx]
+                assert np.array_equal(t.cpu().numpy().view(np.uint64), np.ascontiguousarray(want).view(np.uint64)), (name, i0, nx, j0, ny)
+
+
 @pytest.mark.parametrize("Rx,Ry,dtype", [(1, 8, torch.float64), (2, 2, torch.float64), (3, 2, torch.float32), (1, 4, torch.float32)])
 def test_fine_grid_tiles_equal_slices_of_the_serial_grid(ossg, oracle, Rx, Ry, dtype):
     """The same on a 1/4 degree grid, where every tile runs the tile kernel's straight-line path,
