@@ -24,6 +24,27 @@ __device__ __host__ inline int fold_rows(const ossg_field_desc& f) { return f.Hy
 // One thread serves one (i, level): it issues the loads of all Hy source rows (in chunks of 4)
 // before any store, so that every warp keeps 4 x 256 B in flight -- the fill is a pure
 // latency/bandwidth problem (zero flops).
+// Source rows are read once and halo rows written once per fill: streaming accesses (ld/st.global.cs, evict-first in the
+// L2), so that the fill replaces its own lines rather than lines a neighbouring kernel still wants -- or, in the flushed
+// benchmark configuration, rather than forcing the write-back of another kernel's dirty lines.  -DOSSG_ZIPPER_PLAIN_ACCESS
+// keeps ordinary loads and stores.
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p)
+{
+#if defined(OSSG_ZIPPER_PLAIN_ACCESS)
+    return *p;
+#else
+    return __ldcs(p);
+#endif
+}
+template <typename T> __device__ __forceinline__ void st_stream(T* p, T v)
+{
+#if defined(OSSG_ZIPPER_PLAIN_ACCESS)
+    *p = v;
+#else
+    __stcs(p, v);
+#endif
+}
+
 template <typename T, bool UNIT>
 __device__ __forceinline__ void zipper_column_impl(const ossg_field_desc& f, int i /*1..Nx*/, int kk, double s, int ip)
 {
@@ -40,14 +61,14 @@ __device__ __forceinline__ void zipper_column_impl(const ossg_field_desc& f, int
     if (fix_row) vrow = c[(size_t)(Ny + Hy - 1) * sx + (ip + f.Hx - 1)];
     int r = 0;
     for (; r + 4 <= Hy; r += 4) {
-        const T v0 = src[-(ptrdiff_t)((r + 0) * sx)], v1 = src[-(ptrdiff_t)((r + 1) * sx)];
-        const T v2 = src[-(ptrdiff_t)((r + 2) * sx)], v3 = src[-(ptrdiff_t)((r + 3) * sx)];
-        dst[(size_t)(r + 0) * sx] = fold_value<UNIT>(v0, s, flip);
-        dst[(size_t)(r + 1) * sx] = fold_value<UNIT>(v1, s, flip);
-        dst[(size_t)(r + 2) * sx] = fold_value<UNIT>(v2, s, flip);
-        dst[(size_t)(r + 3) * sx] = fold_value<UNIT>(v3, s, flip);
+        const T v0 = ld_stream(src - (ptrdiff_t)((r + 0) * sx)), v1 = ld_stream(src - (ptrdiff_t)((r + 1) * sx));
+        const T v2 = ld_stream(src - (ptrdiff_t)((r + 2) * sx)), v3 = ld_stream(src - (ptrdiff_t)((r + 3) * sx));
+        st_stream(dst + (size_t)(r + 0) * sx, fold_value<UNIT>(v0, s, flip));
+        st_stream(dst + (size_t)(r + 1) * sx, fold_value<UNIT>(v1, s, flip));
+        st_stream(dst + (size_t)(r + 2) * sx, fold_value<UNIT>(v2, s, flip));
+        st_stream(dst + (size_t)(r + 3) * sx, fold_value<UNIT>(v3, s, flip));
     }
-    for (; r < Hy; ++r) dst[(size_t)r * sx] = fold_value<UNIT>(src[-(ptrdiff_t)(r * sx)], s, flip);
+    for (; r < Hy; ++r) st_stream(dst + (size_t)r * sx, fold_value<UNIT>(ld_stream(src - (ptrdiff_t)(r * sx)), s, flip));
     if (fix_row) c[(size_t)(Ny + Hy - 1) * sx + (i + f.Hx - 1)] = fold_value<UNIT>(vrow, s, flip);
 }
 
@@ -127,17 +148,17 @@ __device__ __forceinline__ void fused_column_impl(const ossg_field_desc& f, int 
     for (; r + 4 <= Hy; r += 4) {
         T v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = src[-(ptrdiff_t)((r + u) * sx)];
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream(src - (ptrdiff_t)((r + u) * sx));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const T o = fold_value<UNIT>(v[u], s, flip);
-            dst[(size_t)(r + u) * sx] = o;
+            st_stream(dst + (size_t)(r + u) * sx, o);
             if (has_img) dst[(ptrdiff_t)((r + u) * sx) + img] = o;
         }
     }
     for (; r < Hy; ++r) {
-        const T o = fold_value<UNIT>(src[-(ptrdiff_t)(r * sx)], s, flip);
-        dst[(size_t)r * sx] = o;
+        const T o = fold_value<UNIT>(ld_stream(src - (ptrdiff_t)(r * sx)), s, flip);
+        st_stream(dst + (size_t)r * sx, o);
         if (has_img) dst[(ptrdiff_t)(r * sx) + img] = o;
     }
     if (f.locy == OSSG_CENTER) {
@@ -188,7 +209,11 @@ __device__ __forceinline__ Piece32 ld_piece32(const void* p)
 }
 __device__ __forceinline__ void st_piece32(void* p, const Piece32& v)
 {
+#if defined(OSSG_ZIPPER_PLAIN_ACCESS)
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
+#else
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
+#endif
 }
 
 // rows whose periodic images part A writes: north-halo rows (and row Ny of y-Center fields) of the zipper levels

@@ -14,16 +14,22 @@ fields = [torch.rand(shape, dtype=torch.float64, device=dev, generator=g) for _ 
 descs = (_lib.FieldDesc * 4)(*[_lib.FieldDesc(t.data_ptr(), _lib.OSSG_F64, Nx, Ny, Nz, H, H, H, loc[0], loc[1], 0, 0, sg)
                                 for t, (loc, sg) in zip(fields, specs)])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-ts = []
-for it in range(12):
-    flush.fill_(it)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(s)
-    _lib.check(L.ossg_fill_halo_regions_batch(descs, 4, s.cuda_stream))
-    e1.record(s); torch.cuda.synchronize()
-    if it >= 3: ts.append(e0.elapsed_time(e1) * 1e3)
-ts.sort()
+def timed(fn, nf, clean=False):
+    ts = []
+    for it in range(12):
+        flush.fill_(it)
+        if clean:
+            flush.sum()                      # write, then read: no dirty lines left in the L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        _lib.check(fn(descs, nf, s.cuda_stream))
+        e1.record(s); torch.cuda.synchronize()
+        if it >= 3: ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+res = [("zipper 4 fields, flushed", timed(L.ossg_zipper_fill_batch, 4)), ("zipper 4 fields, clean flush", timed(L.ossg_zipper_fill_batch, 4, True)),
+       ("zipper 1 field, flushed", timed(L.ossg_zipper_fill_batch, 1)), ("fill_halo_regions! 4 fields, flushed", timed(L.ossg_fill_halo_regions_batch, 4))]
 chk = 0
 for t in fields:
     chk ^= int(t.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
-print("fill_halo_regions! 4 fields: median %.1f us (min %.1f)  chk %016x" % (ts[len(ts) // 2], ts[0], chk), flush=True)
+print("%-24s " % os.path.basename(_lib.LIB_PATH) + " | ".join("%s %.1f us" % kv for kv in res) + " | chk %016x" % chk, flush=True)
