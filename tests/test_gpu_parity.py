@@ -886,6 +886,39 @@ def test_back_to_back_builds_over_poisoned_outputs(ossg, oracle):
                 assert np.array_equal(t.cpu().numpy().view(np.uint64), np.ascontiguousarray(want).view(np.uint64)), (tile, k, n)
 
 
+def test_build_is_capturable_in_a_cuda_graph(ossg, oracle):
+    """The constructor enqueues three kernels on the caller's stream and nothing else (no allocation, no
+    synchronisation, no host wait), chained with programmatic dependent launch: it can be captured into a CUDA graph
+    and replayed.  Every replay (outputs poisoned in between) gives the oracle's bits."""
+    from ossg_b200.grids import make_params
+    L = ossg._lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    size, halo = (360, 180, 1), (4, 4, 4)
+    p = make_params(size, halo, -80, 55, 70, orc.R_EARTH)
+    out = [torch.empty((size[1] + 2 * halo[1], size[0] + 2 * halo[0]), dtype=torch.float64, device=dev) for _ in range(20)]
+    optr = ossg._lib.ptr_array([t.data_ptr() for t in out])
+    ws = torch.empty(L.ossg_tripolar_workspace_bytes(C.byref(p), ossg._lib.OSSG_F64), dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ossg._lib.check(L.ossg_tripolar_workspace_init(ws.data_ptr(), ws.numel(), side.cuda_stream))
+        ossg._lib.check(L.ossg_tripolar_build(C.byref(p), ossg._lib.OSSG_F64, optr, ws.data_ptr(), ws.numel(), side.cuda_stream))   # warm-up (module load, attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ossg._lib.check(L.ossg_tripolar_build(C.byref(p), ossg._lib.OSSG_F64, optr, ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream().cuda_stream))
+    ref = oracle.build(orc.make_params(size, halo))
+    for rep in range(3):
+        for t in out:
+            t.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        for n, t in zip(orc.ALL_NAMES, out):
+            assert np.array_equal(t.cpu().numpy().view(np.uint64), ref[n].view(np.uint64)), (rep, n)
+
+
 @pytest.mark.parametrize("knob", ["OSSG_ROW_DEPS=1", "OSSG_FRAME=fork", "OSSG_FRAME=tail"])
 def test_launch_options_in_a_child_process(ossg, knob):
     """The launch-form knobs are read once per process, so each runs in a child: OSSG_ROW_DEPS=1 (tile blocks wait on
