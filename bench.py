@@ -761,6 +761,26 @@ def bench_small_configs(ctx):
             t = ctx.timed(step, 50, warm=5)
             tc = ctx.timed(cold, 50, warm=5)
             res[f"construct_{tag}"] = {"ms": t, "cells_per_s": Nx * Ny / (t * 1e-3), "first_call_ms": tc}
+            if tag == "f64":
+                # the same build captured into a CUDA graph and replayed (the three launches of a build are enqueued on the
+                # caller's stream only, so it is capturable): what a caller that rebuilds small grids often would do
+                try:
+                    cs = torch.cuda.Stream(device=ctx.dev)          # capture needs a non-default stream
+
+                    def gstep():
+                        _lib.check(L.ossg_tripolar_build(C.byref(p), et, optr, ws.data_ptr(), ws.numel(), cs.cuda_stream))
+                    torch.cuda.synchronize(ctx.dev)
+                    with torch.cuda.stream(cs):
+                        gstep()
+                    torch.cuda.synchronize(ctx.dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=cs):
+                        gstep()
+                    tg = ctx.timed(graph.replay, 50, warm=5)
+                    res["construct_f64"]["graph_replay_ms"] = tg
+                    del graph
+                except Exception as e:      # never fatal for the benchmark line
+                    res["construct_f64"]["graph_replay_error"] = f"{type(e).__name__}: {e}"[:200]
             # fill_halo_regions! of c,u,v,zeta, repeated back to back (BASELINE config 3: "repeated fill_halo_regions!")
             fshape = (Nz + 2 * H, Ny + 2 * H, Nx + 2 * H)
             specs = [((0, 0), 1.0), ((1, 0), -1.0), ((0, 1), -1.0), ((1, 1), 1.0)]
