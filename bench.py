@@ -1113,10 +1113,70 @@ def bench_fold_exchange(ctx):
             res[key]["frac_of_nvlink_900"] = res[key]["gbs_per_direction_per_gpu"] / 900.0
             res[key]["frac_of_measured_770"] = res[key]["gbs_per_direction_per_gpu"] / 770.0
         out[key_out] = res
+    # ---- copy-engine form, data phase only: one strided 3-D peer copy per field pulls the
+    # mirror rank's source rows (Hy or Hy + 1 rows x nx columns x Nz levels) into a local staging buffer.  Not timed: the
+    # local unpack-with-reversal kernel that would follow (HBM speed) and the flag protocol -- so this is an upper bound
+    # of what a copy-engine fold could reach, to be held against the kernels' marginal bandwidth above.
+    try:
+        out["copy_engine_pull_data_phase"] = bench_copy_engine_pull(ctx, all_fields, tile, recv_bytes, reps)
+    except Exception as e:              # noqa: BLE001
+        out["copy_engine_pull_data_phase"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     ref.close()
     parity["mismatches"] = sum(v["mismatches"] for v in parity.values() if isinstance(v, dict))
     out["parity"] = parity
     return out
+
+
+def bench_copy_engine_pull(ctx, all_fields, tile, recv_bytes, reps):
+    from cuda.bindings import runtime as cudart
+    from ossg_b200.distributed import PeerFold
+    torch = ctx.torch
+    H, Nz = WORKLOAD["halo"], WORKLOAD["Nz"]
+    i0, j0, nx, ny = tile
+    Ny = WORKLOAD["Ny"]
+    res = {}
+    for nf in (1, 4, 8, 16):
+        fs = all_fields[:nf]
+        pf = PeerFold(fs, push=False)                    # (used for its CUDA IPC mappings of the partners' fields only)
+        mirror = pf.arch.Rx - 1 - pf.arch.rx
+        staging = [torch.empty((Nz, H + 1, nx), dtype=torch.float64, device=ctx.dev) for _ in fs]
+        pitch = (nx + 2 * H) * 8
+        parms = []
+        for k, f in enumerate(fs):
+            locy = f.descriptor().locy
+            rows = H + (1 if locy == 0 else 0)
+            j_first = Ny - H + (1 if locy else 0)            # global row of the first source row (y-Center: Ny-Hy .. Ny, y-Face: Ny-Hy+1 .. Ny)
+            row0 = (j_first - j0) + H                        # its index in the partner's parent array (same j0 on the whole top row)
+            src = pf.peer_ptrs[k][mirror] + (H * (ny + 2 * H) * (nx + 2 * H) + row0 * (nx + 2 * H) + H) * 8
+            pm = cudart.cudaMemcpy3DParms()
+            pm.srcPtr = cudart.make_cudaPitchedPtr(src, pitch, nx + 2 * H, ny + 2 * H)
+            pm.dstPtr = cudart.make_cudaPitchedPtr(staging[k].data_ptr(), nx * 8, nx, H + 1)
+            pm.srcPos = cudart.make_cudaPos(0, 0, 0)
+            pm.dstPos = cudart.make_cudaPos(0, 0, 0)
+            pm.extent = cudart.make_cudaExtent(nx * 8, rows, Nz)
+            pm.kind = cudart.cudaMemcpyKind.cudaMemcpyDefault
+            parms.append(pm)
+        sh = ctx.stream.cuda_stream
+
+        def exchange():
+            for pm in parms:
+                err, = cudart.cudaMemcpy3DAsync(pm, sh)
+                if err != cudart.cudaError_t.cudaSuccess:
+                    raise RuntimeError(f"cudaMemcpy3DAsync: {err}")
+        t = ctx.timed(exchange, reps)
+        rb = recv_bytes(fs)
+        res[f"fields{nf}"] = {"ms_per_exchange": t, "recv_bytes_per_rank": rb, "gbs_per_direction_per_gpu": rb / (t * 1e-3) / 1e9}
+        # the copies really moved the partner's rows: level 0, first source row against the partner's own value via NCCL-free check
+        torch.cuda.synchronize(ctx.dev)
+        del staging
+        pf.close()
+    t1, t16 = res["fields1"], res["fields16"]
+    slope = (t16["ms_per_exchange"] - t1["ms_per_exchange"]) / (t16["recv_bytes_per_rank"] - t1["recv_bytes_per_rank"])
+    res["marginal_gbs"] = 1e-6 / slope
+    res["fixed_us"] = 1e3 * (t1["ms_per_exchange"] - slope * t1["recv_bytes_per_rank"])
+    res["what"] = ("one cudaMemcpy3DAsync per field (rows x nx columns x Nz levels, row pitch of the partner's array) from the mirror rank's "
+                   "IPC-mapped field into a local staging buffer; no unpack kernel, no flags: data phase of a copy-engine fold only")
+    return res
 
 
 def bench_distributed_fill(ctx):
