@@ -259,3 +259,21 @@ def test_with_halo_and_reconstruct_forward_the_tripolar_parameters(ossg, monkeyp
     assert kw["halo"] == (4, 13, 4) and kw["size"] == (20, 12, 3) and kw["radius"] == 1.0
     assert (kw["north_poles_latitude"], kw["first_pole_longitude"], kw["southernmost_latitude"]) == (45, 25, -75)
     assert np.allclose(kw["z"], [-100, -100 + 100 / 3, -100 + 200 / 3, 0])
+
+
+def test_reference_arm_of_the_bench_runs_without_a_gpu():
+    """`bench.py --impl reference` times the CPU restatement of the reference (the oracle built with glibc libm) on the
+    host cores and prints ONE JSON line with the contract's keys; it needs no GPU and must not touch the CUDA library."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "grid cells/s for coords+metrics (FP64)" and d["unit"] == "cells/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "4320x2160" in d["config"]["workload"]
